@@ -1,0 +1,321 @@
+// Attention pooling (score unit + masked softmax + weighted sum, clsr.py:371-381,154,221), the
+// history proxies hist_mean / hist_recent (clsr.py:157,173-177), and the group-structured
+// backward helpers of the factorised first attention layer.
+#pragma once
+#include "common.cuh"
+
+namespace clsr {
+
+// One warp per row.  score[t] = relu(bn(h1[row,t,:])) . wout + bout for t < len, masked softmax
+// over t, att[row,:] = sum_t w[t] * V[seq,t,:].  With hm/hr non-null also the two proxies.
+__global__ void __launch_bounds__(128)
+pool_fwd_kernel(const float* __restrict__ h1, int A1, const float* __restrict__ scale,
+                const float* __restrict__ shift, const float* __restrict__ wout,
+                const float* __restrict__ bout, const float* __restrict__ V, int Dv,
+                const int* __restrict__ len, int rows, int T, int G, float* __restrict__ w_out,
+                float* __restrict__ att, float* __restrict__ hm, float* __restrict__ hr, int recent_k) {
+  extern __shared__ float sm[];
+  float* s_scale = sm;
+  float* s_shift = s_scale + A1;
+  float* s_w = s_shift + A1;
+  float* s_sc = s_w + A1;  // [warps][T]
+  for (int i = threadIdx.x; i < A1; i += blockDim.x) {
+    s_scale[i] = scale[i]; s_shift[i] = shift[i]; s_w[i] = wout[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* sc = s_sc + wid * T;
+  const float b0 = bout[0];
+  for (int row = blockIdx.x * wpb + wid; row < rows; row += gridDim.x * wpb) {
+    const int s = row / G;
+    const int L = len[s];
+    float mx = -INFINITY;
+    for (int t = lane; t < L; t += 32) {
+      const float* hp = h1 + ((size_t)row * T + t) * A1;
+      float dot = b0;
+      for (int n = 0; n < A1; ++n) dot = fmaf(fmaxf(0.f, fmaf(hp[n], s_scale[n], s_shift[n])), s_w[n], dot);
+      sc[t] = dot;
+      mx = fmaxf(mx, dot);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int t = lane; t < L; t += 32) {
+      float e = expf(sc[t] - mx);
+      sc[t] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    for (int t = lane; t < T; t += 32) {
+      float w = (t < L) ? sc[t] / sum : 0.f;
+      sc[t] = w;
+      w_out[(size_t)row * T + t] = w;
+    }
+    __syncwarp();
+    const int kk = min(L, recent_k);
+    for (int d = lane; d < Dv; d += 32) {
+      float acc = 0.f, am = 0.f, ar = 0.f;
+      const float* vp = V + (size_t)s * T * Dv + d;
+      for (int t = 0; t < L; ++t) {
+        float v = vp[(size_t)t * Dv];
+        acc = fmaf(sc[t], v, acc);
+        am += v;
+        if (t >= L - kk) ar += v;
+      }
+      att[(size_t)row * Dv + d] = acc;
+      if (hm) {
+        hm[(size_t)s * Dv + d] = am / (float)L;
+        hr[(size_t)s * Dv + d] = ar / (float)kk;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Backward of pool_fwd, one warp per group of G rows sharing the values V[seq].
+//   dsc[t]  = w[t] * (datt.V[t] - sum_t' w[t'] datt.V[t'])
+//   dy1[row,t,n] = dsc[t]*wout[n] where bn(h1)>0 (zero elsewhere and on padded positions)
+//   stat += (sum dy1, sum dy1*xhat) per channel;  dwout += sum relu(bn(h1))*dsc;  dbout += sum dsc
+//   dV[seq,t,:] (=|+=) sum_g w[g,t] * datt[g,:]  (+ proxy gradients dhm/L, dhr/k when given)
+__global__ void __launch_bounds__(128)
+pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, const float* __restrict__ V,
+                int Dv, const float* __restrict__ h1, int A1, const float* __restrict__ scale,
+                const float* __restrict__ shift, const float* __restrict__ mean,
+                const float* __restrict__ rstd, const float* __restrict__ wout,
+                const int* __restrict__ len, int nseq, int T, int G, float* __restrict__ dy1,
+                double* __restrict__ stat, float* __restrict__ dwout, float* __restrict__ dbout,
+                float* __restrict__ dV, int dV_accum, const float* __restrict__ dhm,
+                const float* __restrict__ dhr, int recent_k) {
+  extern __shared__ float sm[];
+  const int wpb = blockDim.x >> 5;
+  float* s_scale = sm;
+  float* s_shift = s_scale + A1;
+  float* s_mean = s_shift + A1;
+  float* s_rstd = s_mean + A1;
+  float* s_w = s_rstd + A1;
+  float* s_acc = s_w + A1;            // [3][A1] + 1 : stat1, stat2, dwout, dbout
+  float* s_warp = s_acc + 3 * A1 + 1;  // per warp: dsc[T], wrow[T], dat[Dv]
+  for (int i = threadIdx.x; i < A1; i += blockDim.x) {
+    s_scale[i] = scale[i]; s_shift[i] = shift[i]; s_mean[i] = mean[i]; s_rstd[i] = rstd[i]; s_w[i] = wout[i];
+  }
+  for (int i = threadIdx.x; i < 3 * A1 + 1; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* dsc = s_warp + wid * (2 * T + Dv);
+  float* wrow = dsc + T;
+  float* dat = wrow + T;
+  constexpr int MAXSLOT = 4;  // A1 <= 128
+  float st1[MAXSLOT], st2[MAXSLOT], dwo[MAXSLOT], dbo = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXSLOT; ++i) { st1[i] = 0.f; st2[i] = 0.f; dwo[i] = 0.f; }
+
+  for (int s = blockIdx.x * wpb + wid; s < nseq; s += gridDim.x * wpb) {
+    const int L = len[s];
+    const int kk = min(L, recent_k);
+    for (int g = 0; g < G; ++g) {
+      const size_t row = (size_t)s * G + g;
+      for (int d = lane; d < Dv; d += 32) dat[d] = datt[row * Dv + d];
+      __syncwarp();
+      float dot = 0.f;
+      for (int t = lane; t < T; t += 32) {
+        float dwt = 0.f, wt = 0.f;
+        if (t < L) {
+          const float* vp = V + ((size_t)s * T + t) * Dv;
+          for (int d = 0; d < Dv; ++d) dwt = fmaf(dat[d], vp[d], dwt);
+          wt = w[row * T + t];
+          dot = fmaf(wt, dwt, dot);
+        }
+        dsc[t] = dwt;
+        wrow[t] = wt;
+      }
+      dot = warp_sum(dot);
+      for (int t = lane; t < T; t += 32) {
+        float v = wrow[t] * (dsc[t] - dot);
+        dsc[t] = v;
+        dbo += v;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int sl = 0; sl < MAXSLOT; ++sl) {
+        const int n = lane + 32 * sl;
+        if (n < A1) {
+          const float scn = s_scale[n], shn = s_shift[n], mn = s_mean[n], rs = s_rstd[n], wo = s_w[n];
+          const float* hp = h1 + row * T * A1 + n;
+          float* dp = dy1 + row * T * A1 + n;
+          for (int t = 0; t < T; ++t) {
+            float h = hp[(size_t)t * A1];
+            float y = fmaf(h, scn, shn);
+            float d = dsc[t];
+            float v = (y > 0.f) ? d * wo : 0.f;
+            dp[(size_t)t * A1] = v;
+            st1[sl] += v;
+            st2[sl] = fmaf(v, (h - mn) * rs, st2[sl]);
+            dwo[sl] = fmaf(fmaxf(y, 0.f), d, dwo[sl]);
+          }
+        }
+      }
+      for (int d = lane; d < Dv; d += 32) {
+        const float da = dat[d];
+        const float pm = dhm ? dhm[(size_t)s * Dv + d] / (float)L : 0.f;
+        const float pr = dhr ? dhr[(size_t)s * Dv + d] / (float)kk : 0.f;
+        float* op = dV + (size_t)s * T * Dv + d;
+        for (int t = 0; t < T; ++t) {
+          float v = 0.f;
+          if (t < L) {
+            v = wrow[t] * da;
+            if (g == 0) { v += pm; if (t >= L - kk) v += pr; }
+          }
+          if (g == 0 && !dV_accum) op[(size_t)t * Dv] = v;
+          else if (t < L) op[(size_t)t * Dv] += v;
+        }
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int sl = 0; sl < MAXSLOT; ++sl) {
+    const int n = lane + 32 * sl;
+    if (n < A1) {
+      atomicAdd(&s_acc[n], st1[sl]); atomicAdd(&s_acc[A1 + n], st2[sl]); atomicAdd(&s_acc[2 * A1 + n], dwo[sl]);
+    }
+  }
+  dbo = warp_sum(dbo);
+  if (lane == 0) atomicAdd(&s_acc[3 * A1], dbo);
+  __syncthreads();
+  for (int i = threadIdx.x; i < A1; i += blockDim.x) {
+    atomicAdd(stat + i, (double)s_acc[i]);
+    atomicAdd(stat + A1 + i, (double)s_acc[A1 + i]);
+    atomicAdd(dwout + i, s_acc[2 * A1 + i]);
+  }
+  if (threadIdx.x == 0) atomicAdd(dbout, s_acc[3 * A1]);
+}
+
+// dh0 = al*dy0 + be*h0 + ga (BatchNorm backward of the first attention layer), reduced two ways:
+//   dinv[s,t,n] = sum_g dh0[(s*G+g), t, n]      (skipped when dinv == nullptr)
+//   dqb[b,n]    = sum_t dh0[b, t, n]
+// One CTA per sequence; blockDim = (NX >= A0, NY).
+__global__ void h0_reduce_kernel(const float* __restrict__ dy0, const float* __restrict__ h0, int A0,
+                                 const float* __restrict__ al, const float* __restrict__ be,
+                                 const float* __restrict__ ga, int T, int G, float* __restrict__ dinv,
+                                 float* __restrict__ dqb) {
+  extern __shared__ float sq[];  // [NY][A0]
+  const int s = blockIdx.x;
+  const int n = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
+  const bool act = n < A0;
+  const float a = act ? al[n] : 0.f, b = act ? be[n] : 0.f, c = act ? ga[n] : 0.f;
+  for (int g = 0; g < G; ++g) {
+    const size_t row = (size_t)s * G + g;
+    float accq = 0.f;
+    if (act) {
+      for (int t = ty; t < T; t += ny) {
+        size_t o = (row * T + t) * A0 + n;
+        float v = fmaf(a, dy0[o], fmaf(b, h0[o], c));
+        accq += v;
+        if (dinv) {
+          size_t oi = ((size_t)s * T + t) * A0 + n;
+          if (g == 0) dinv[oi] = v; else dinv[oi] += v;
+        }
+      }
+      sq[ty * A0 + n] = accq;
+    }
+    __syncthreads();
+    if (act && ty == 0) {
+      float tot = 0.f;
+      for (int y = 0; y < ny; ++y) tot += sq[y * A0 + n];
+      dqb[row * A0 + n] = tot;
+    }
+    __syncthreads();
+  }
+}
+
+// Backward of the per-target product P[b,t,k] = a2[s,t,k] * tgt[b,k]:
+//   da2[s,t,k] = sum_g dP[(s*G+g),t,k] * tgt[(s*G+g),k];   dtgt[b,k] += sum_t dP[b,t,k] * a2[s,t,k]
+// a2 = as[:, off:off+D].  One CTA per sequence; blockDim = (NX >= D, NY).
+__global__ void mulrow_bwd_kernel(const float* __restrict__ dP, int D, const float* __restrict__ as, int lda,
+                                  int off, const float* __restrict__ tgt, int ldt, int T, int G,
+                                  float* __restrict__ da2, float* __restrict__ dtgt, int lddt) {
+  extern __shared__ float sq[];  // [NY][D]
+  const int s = blockIdx.x;
+  const int k = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
+  const bool act = k < D;
+  for (int g = 0; g < G; ++g) {
+    const size_t row = (size_t)s * G + g;
+    float acct = 0.f;
+    if (act) {
+      const float tg = tgt[row * ldt + k];
+      for (int t = ty; t < T; t += ny) {
+        float d = dP[(row * T + t) * D + k];
+        size_t m = (size_t)s * T + t;
+        acct = fmaf(d, as[m * lda + off + k], acct);
+        float v = d * tg;
+        if (g == 0) da2[m * D + k] = v; else da2[m * D + k] += v;
+      }
+      sq[ty * D + k] = acct;
+    }
+    __syncthreads();
+    if (act && ty == 0) {
+      float tot = 0.f;
+      for (int y = 0; y < ny; ++y) tot += sq[y * D + k];
+      dtgt[row * lddt + k] += tot;
+    }
+    __syncthreads();
+  }
+}
+
+// Backward of the feature map F = [a (W1 cols), a[:, :W2] * V[s] (W2 cols)]:
+//   da[m,k] = dF[m,k] + (k<W2 ? dF[m,W1+k]*V[s,k] : 0) + (add && k>=add_off ? add[m,k-add_off] : 0)
+//   dVout[s,k] = sum_t dF[m,W1+k] * a[m,k]     (k < W2; written, not accumulated)
+// One CTA per sequence; blockDim = (NX >= W1, NY).
+__global__ void catmul_bwd_kernel(const float* __restrict__ dF, int W1, int W2, const float* __restrict__ a,
+                                  int lda, const float* __restrict__ Vq, int ldv,
+                                  const float* __restrict__ add, int ldadd, int add_off, int T,
+                                  float* __restrict__ da, int ldda, float* __restrict__ dVout, int lddv) {
+  extern __shared__ float sq[];  // [NY][W2]
+  const int s = blockIdx.x;
+  const int k = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
+  const int ldf = W1 + W2;
+  float acc = 0.f;
+  if (k < W1) {
+    const float vq = (k < W2) ? Vq[(size_t)s * ldv + k] : 0.f;
+    for (int t = ty; t < T; t += ny) {
+      size_t m = (size_t)s * T + t;
+      float v = dF[m * ldf + k];
+      if (k < W2) {
+        float d2 = dF[m * ldf + W1 + k];
+        v = fmaf(d2, vq, v);
+        acc = fmaf(d2, a[m * lda + k], acc);
+      }
+      if (add && k >= add_off) v += add[m * ldadd + (k - add_off)];
+      da[m * ldda + k] = v;
+    }
+    if (k < W2) sq[ty * W2 + k] = acc;
+  }
+  __syncthreads();
+  if (k < W2 && ty == 0) {
+    float tot = 0.f;
+    for (int y = 0; y < ny; ++y) tot += sq[y * W2 + k];
+    dVout[(size_t)s * lddv + k] = tot;
+  }
+}
+
+// dq[b, 0:Q] = gradient of the short-term query [sti[s] (U), tgt[b] (D)]:
+//   dsti[s,k] += sum_g dq[(s*G+g), k];   dtgt[b,k] += dq[b, U+k]
+__global__ void qs_bwd_kernel(const float* __restrict__ dq, int U, int D, int G, int S,
+                              float* __restrict__ dsti, float* __restrict__ dtgt) {
+  const int Q = U + D;
+  int n = S * Q;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int s = i / Q, k = i - s * Q;
+    if (k < U) {
+      float acc = 0.f;
+      for (int g = 0; g < G; ++g) acc += dq[((size_t)s * G + g) * Q + k];
+      dsti[(size_t)s * U + k] += acc;
+    } else {
+      for (int g = 0; g < G; ++g) {
+        size_t b = (size_t)s * G + g;
+        dtgt[b * D + (k - U)] += dq[b * Q + k];
+      }
+    }
+  }
+}
+
+}  // namespace clsr

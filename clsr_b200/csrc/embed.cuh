@@ -1,0 +1,292 @@
+// Embedding-side kernels: history gather (K1+K3), row gathers, id de-duplication through a
+// direct-address slot table (K2), sparse-gradient scatter-add (K13), involved-row terms
+// (L2 / discrepancy), and the sparse Adam updates (K15).
+//
+// Reference semantics: tf.nn.embedding_lookup / tf.unique / IndexedSlices gradients
+// (sequential_base_model.py:381-437, clsr.py:103-127) and AdamOptimizer's sparse path
+// (base_model.py:263-297); see SURVEY.md section 8a rows a2, a18.
+#pragma once
+#include "common.cuh"
+
+namespace clsr {
+
+// hist_input[p, :] = concat(item_table[ih[p]], cate_table[ch[p]]); p = s*T + t.
+// Index arrays are addressed as base[(p / T) * seq_stride + p % T] so a [B,T] feed can be read at
+// every G-th row without a compaction pass.  One thread moves one 16-byte vector; the V = (Di+Dc)/4
+// threads of a position read one 128-byte item row + one 32-byte category sector and write one
+// contiguous D*4-byte output row, so both sides are fully coalesced.  UNROLL positions per thread
+// keep UNROLL independent row loads in flight behind the dependent index loads.
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+gather_hist_kernel(const int32_t* __restrict__ ih, const int32_t* __restrict__ ch, int seq_stride, int T,
+                   const float* __restrict__ item_tab, const float* __restrict__ cate_tab, int Di, int Dc,
+                   float* __restrict__ out, long long npos) {
+  const int VI = Di >> 2, V = (Di + Dc) >> 2;
+  const long long nvec = npos * V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; g0 < nvec; g0 += stride * UNROLL) {
+    const float4* src[UNROLL];
+    long long gi[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      long long g = g0 + u * stride;
+      gi[u] = g;
+      src[u] = nullptr;
+      if (g < nvec) {
+        long long p = g / V;
+        int q = (int)(g - p * V);
+        long long s = p / T;
+        int t = (int)(p - s * T);
+        long long io = s * seq_stride + t;
+        if (q < VI) {
+          src[u] = reinterpret_cast<const float4*>(item_tab + (size_t)__ldg(ih + io) * Di) + q;
+        } else {
+          src[u] = reinterpret_cast<const float4*>(cate_tab + (size_t)__ldg(ch + io) * Dc) + (q - VI);
+        }
+      }
+    }
+    float4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      if (src[u]) v[u] = ldg_stream(src[u]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      if (src[u]) stg_stream(reinterpret_cast<float4*>(out) + gi[u], v[u]);
+  }
+}
+
+// out[r, col0 : col0+dim] = table[idx[r*idx_stride], :]   (targets, users)
+__global__ void gather_rows_kernel(const int32_t* __restrict__ idx, int idx_stride,
+                                   const float* __restrict__ tab, int dim, float* __restrict__ out, int ldo,
+                                   int col0, int rows) {
+  const int V = dim >> 2;
+  long long n = (long long)rows * V;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n;
+       g += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(g / V), q = (int)(g % V);
+    int id = __ldg(idx + (size_t)r * idx_stride);
+    float4 v = __ldg(reinterpret_cast<const float4*>(tab + (size_t)id * dim) + q);
+    *reinterpret_cast<float4*>(out + (size_t)r * ldo + col0 + q * 4) = v;
+  }
+}
+
+// tf.unique through a direct-address table: slot[id] = compact row (or -1).  The first thread to
+// claim an id appends it to uniq[]; later kernels translate ids through slot[].
+__global__ void mark_unique_kernel(const int32_t* __restrict__ ids, long long n, int T, int seq_stride,
+                                   int32_t* __restrict__ slot, int32_t* __restrict__ uniq,
+                                   int32_t* __restrict__ counter) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long s = i / T;
+    int id = __ldg(ids + s * seq_stride + (i - s * T));
+    if (slot[id] == -1) {
+      if (atomicCAS(&slot[id], -1, -2) == -1) {
+        int c = atomicAdd(counter, 1);
+        uniq[c] = id;
+        slot[id] = c;
+      }
+    }
+  }
+}
+
+__global__ void reset_slots_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict__ counter,
+                                   int32_t* __restrict__ slot) {
+  int n = *counter;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) slot[uniq[c]] = -1;
+}
+
+// Zero the compact gradient rows that this step will use (count is device-resident).
+__global__ void zero_compact_kernel(float* __restrict__ g, const int32_t* __restrict__ counter, int dim) {
+  long long n = (long long)(*counter) * dim / 4;
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(g)[i] = z;
+}
+
+// Sparse-gradient scatter-add of d_hist[p, 0:Di | Di:D] into compact rows gi[slot_i[ih[p]]] /
+// gc[slot_c[ch[p]]].  d_hist is streamed once with 16-byte loads; each vector becomes one
+// red.global.add.v4.f32.  Padded positions (id 0: a large share of every batch and all aimed at
+// one row) are first summed per CTA in shared memory and flushed once.  sumsq[0/1] receive the
+// squared norm of the un-deduplicated slice values (tf.clip_by_norm on IndexedSlices).
+__global__ void __launch_bounds__(256)
+scatter_hist_kernel(const float* __restrict__ dX, const int32_t* __restrict__ ih,
+                    const int32_t* __restrict__ ch, int seq_stride, int T,
+                    const int32_t* __restrict__ slot_i, const int32_t* __restrict__ slot_c,
+                    float* __restrict__ gi, float* __restrict__ gc, int Di, int Dc, long long npos,
+                    double* __restrict__ sumsq) {
+  extern __shared__ float pad_acc[];  // [Di + Dc]
+  __shared__ float red[2][8];
+  const int VI = Di >> 2, V = (Di + Dc) >> 2;
+  for (int i = threadIdx.x; i < Di + Dc; i += blockDim.x) pad_acc[i] = 0.f;
+  __syncthreads();
+  const long long nvec = npos * V;
+  float ssi = 0.f, ssc = 0.f;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < nvec;
+       g += (long long)gridDim.x * blockDim.x) {
+    long long p = g / V;
+    int q = (int)(g - p * V);
+    long long s = p / T;
+    long long io = s * seq_stride + (p - s * T);
+    float4 v = ldg_stream(reinterpret_cast<const float4*>(dX) + g);
+    float sq = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    int id;
+    if (q < VI) { id = __ldg(ih + io); ssi += sq; } else { id = __ldg(ch + io); ssc += sq; }
+    if (id == 0) {
+      float* a = pad_acc + q * 4;
+      atomicAdd(a + 0, v.x); atomicAdd(a + 1, v.y); atomicAdd(a + 2, v.z); atomicAdd(a + 3, v.w);
+    } else if (q < VI) {
+      red_add_v4(gi + (size_t)slot_i[id] * Di + q * 4, v);
+    } else {
+      red_add_v4(gc + (size_t)slot_c[id] * Dc + (q - VI) * 4, v);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Di + Dc; i += blockDim.x) {
+    float v = pad_acc[i];
+    if (v != 0.f) {
+      if (i < Di) atomicAdd(gi + (size_t)slot_i[0] * Di + i, v);
+      else atomicAdd(gc + (size_t)slot_c[0] * Dc + (i - Di), v);
+    }
+  }
+  ssi = warp_sum(ssi); ssc = warp_sum(ssc);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = ssi; red[1][w] = ssc; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[threadIdx.x][i];
+    atomicAdd(sumsq + threadIdx.x, (double)t);
+  }
+}
+
+// Scatter-add of dense per-row gradients d[r, col0:col0+dim] into compact rows (targets, users).
+__global__ void scatter_rows_kernel(const float* __restrict__ d, int ldd, int col0, int dim,
+                                    const int32_t* __restrict__ idx, int idx_stride,
+                                    const int32_t* __restrict__ slot, float* __restrict__ g, int rows,
+                                    double* __restrict__ sumsq) {
+  const int V = dim >> 2;
+  long long n = (long long)rows * V;
+  float ss = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(i / V), q = (int)(i % V);
+    float4 v = *reinterpret_cast<const float4*>(d + (size_t)r * ldd + col0 + q * 4);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    int id = __ldg(idx + (size_t)r * idx_stride);
+    red_add_v4(g + (size_t)slot[id] * dim + q * 4, v);
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0 && ss != 0.f) atomicAdd(sumsq, (double)ss);
+}
+
+// Involved-row terms, one warp per unique id: the slice TF forms for the `involved_*` lookup
+// (embed_l2 * row, plus the discrepancy gradient for the two user tables) is added to the compact
+// gradient row; its squared norm joins sumsq; acc[0] += sum(row^2) (regular loss),
+// acc[1] += sum((long-short)^2) (discrepancy loss; only when `other` is given and count_disc != 0).
+__global__ void involved_kernel(const float* __restrict__ tab, const float* __restrict__ other, int dim,
+                                const int32_t* __restrict__ uniq, const int32_t* __restrict__ counter,
+                                float* __restrict__ g, float l2, float disc_w, int count_disc,
+                                double* __restrict__ sumsq, double* __restrict__ acc) {
+  const int n = *counter;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  float ss = 0.f, rr = 0.f, dd = 0.f;
+  // d/d(this) of -w*mean((this-other)^2) = -2w/(n*dim)*(this-other), the same form for both tables.
+  const float dcoef = other ? -2.0f * disc_w / ((float)n * (float)dim) : 0.f;
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < n; c += gridDim.x * wpb) {
+    size_t row = (size_t)uniq[c] * dim;
+    for (int k = lane; k < dim; k += 32) {
+      float x = tab[row + k];
+      float v = l2 * x;
+      rr += x * x;
+      if (other) {
+        float df = x - other[row + k];
+        v += dcoef * df;
+        dd += df * df;
+      }
+      g[(size_t)c * dim + k] += v;
+      ss += v * v;
+    }
+  }
+  ss = warp_sum(ss); rr = warp_sum(rr); dd = warp_sum(dd);
+  if (lane == 0) {
+    if (ss != 0.f) atomicAdd(sumsq, (double)ss);
+    if (rr != 0.f) atomicAdd(acc, (double)rr);
+    if (other && count_disc && dd != 0.f) atomicAdd(acc + 1, (double)dd);
+  }
+}
+
+struct AdamHyper {
+  float lr_t, beta1, beta2, eps, clip;  // clip <= 0: no clipping
+};
+
+// TF's non-lazy sparse Adam: m and v decay and the variable moves on EVERY row;
+// rows present in the batch add their (clipped) compact gradient.  Pure streaming over
+// var / m / v (3 reads + 3 writes of the whole table) plus the 4-byte slot lookup per row.
+__global__ void __launch_bounds__(256)
+adam_sweep_kernel(float* __restrict__ var, float* __restrict__ m, float* __restrict__ v,
+                  const int32_t* __restrict__ slot, const float* __restrict__ g, int dim, long long rows,
+                  AdamHyper hp, const double* __restrict__ sumsq) {
+  const int V = dim >> 2;
+  float scale = 1.f;
+  if (hp.clip > 0.f) {
+    float nrm = (float)sqrt(*sumsq);
+    scale = hp.clip / fmaxf(nrm, hp.clip);
+  }
+  const long long nvec = rows * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / V;
+    int q = (int)(i - r * V);
+    int c = __ldg(slot + r);
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c >= 0) {
+      gv = *reinterpret_cast<const float4*>(g + (size_t)c * dim + q * 4);
+      gv.x *= scale; gv.y *= scale; gv.z *= scale; gv.w *= scale;
+    }
+    float4 mv = ldg_stream(reinterpret_cast<const float4*>(m) + i);
+    float4 vv = ldg_stream(reinterpret_cast<const float4*>(v) + i);
+    float4 xv = ldg_stream(reinterpret_cast<const float4*>(var) + i);
+#define CLSR_ADAM1(c_)                                          \
+  mv.c_ = hp.beta1 * mv.c_ + (1.f - hp.beta1) * gv.c_;          \
+  vv.c_ = hp.beta2 * vv.c_ + (1.f - hp.beta2) * gv.c_ * gv.c_;  \
+  xv.c_ -= hp.lr_t * mv.c_ / (sqrtf(vv.c_) + hp.eps);
+    CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
+    stg_stream(reinterpret_cast<float4*>(m) + i, mv);
+    stg_stream(reinterpret_cast<float4*>(v) + i, vv);
+    stg_stream(reinterpret_cast<float4*>(var) + i, xv);
+  }
+}
+
+// LazyAdam (tf.contrib.opt.LazyAdamOptimizer, base_model.py:275-276): only rows in the batch move.
+__global__ void adam_lazy_kernel(float* __restrict__ var, float* __restrict__ m, float* __restrict__ v,
+                                 const int32_t* __restrict__ uniq, const int32_t* __restrict__ counter,
+                                 const float* __restrict__ g, int dim, AdamHyper hp,
+                                 const double* __restrict__ sumsq) {
+  const int V = dim >> 2;
+  float scale = 1.f;
+  if (hp.clip > 0.f) {
+    float nrm = (float)sqrt(*sumsq);
+    scale = hp.clip / fmaxf(nrm, hp.clip);
+  }
+  const long long nvec = (long long)(*counter) * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long c = i / V;
+    int q = (int)(i - c * V);
+    size_t off = (size_t)uniq[c] * dim + q * 4;
+    float4 gv = *reinterpret_cast<const float4*>(g + (size_t)c * dim + q * 4);
+    gv.x *= scale; gv.y *= scale; gv.z *= scale; gv.w *= scale;
+    float4 mv = *reinterpret_cast<const float4*>(m + off);
+    float4 vv = *reinterpret_cast<const float4*>(v + off);
+    float4 xv = *reinterpret_cast<const float4*>(var + off);
+    CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
+    *reinterpret_cast<float4*>(m + off) = mv;
+    *reinterpret_cast<float4*>(v + off) = vv;
+    *reinterpret_cast<float4*>(var + off) = xv;
+  }
+}
+#undef CLSR_ADAM1
+
+}  // namespace clsr

@@ -1,0 +1,1397 @@
+// clsr_b200 engine: host-side orchestration of one CLSR step on one B200 and the C ABI of
+// include/clsr_b200.h.  Replaces the TensorFlow session executor under
+// CLSRModel.train / eval / infer (clsr.py:383-408, base_model.py:366-392).
+//
+// The step is a fixed sequence of kernel launches on one stream over a workspace allocated at
+// creation; no allocation, no host synchronisation until the scalar losses are read back.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/clsr_b200.h"
+#include "attn.cuh"
+#include "embed.cuh"
+#include "gemm.cuh"
+#include "head.cuh"
+#include "rnn.cuh"
+
+using namespace clsr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DenseEntry {
+  std::string name;
+  long long off;
+  long long n;
+  int rows, cols;
+  int trainable;
+};
+
+struct BnLayer {
+  int N;
+  long long gamma, beta, mmean, mvar;  // offsets into P
+  double* stat_f;                      // [2N] forward sums
+  double* stat_b;                      // [2N] backward sums
+  float *scale, *shift, *mean, *rstd, *al, *be, *ga;
+};
+
+struct Mlp {  // one _fcn_net: two hidden layers with BN + ReLU and a scalar output unit
+  long long w0, b0, w1, b1, wo, bo;  // offsets into P
+  int in, n0, n1;
+  BnLayer bn0, bn1;
+};
+
+}  // namespace
+
+struct clsr_engine {
+  clsr_config cfg;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool debug_sync = false;
+  long long launches = 0;
+  long long adam_step = 0;
+  int num_sms = 148;
+
+  int T, Di, Dc, D, U, H, Q, A0, A1, L0, L1, CA, NX;
+  int oG1, oC1, oG2, oC2, oL, oO, oTN, oTL;
+  int Bmax, Smax;
+
+  // dense variables
+  std::vector<DenseEntry> dense;
+  std::map<std::string, int> dense_ix;
+  long long Ptot = 0;
+  float *P = nullptr, *Pm = nullptr, *Pv = nullptr, *Pg = nullptr;
+  DenseVar* d_vars = nullptr;
+  float* d_norms = nullptr;
+  // folded / transposed weights and their gradients
+  std::map<std::string, long long> wd_off;
+  long long Wtot = 0;
+  float *Wd = nullptr, *dWd = nullptr;
+  BlockOp *ops_prep = nullptr, *ops_unprep = nullptr;
+  int n_prep = 0, n_unprep = 0;
+
+  Mlp mlp_long, mlp_short, mlp_alpha, mlp_logit;
+  long long p_wattl, p_watts;
+  long long p_tw1, p_tb1, p_tw2, p_tb2;
+
+  // tables
+  float* tab[CLSR_NUM_TABLES] = {nullptr, nullptr, nullptr, nullptr};
+  float* tab_m[CLSR_NUM_TABLES] = {nullptr, nullptr, nullptr, nullptr};
+  float* tab_v[CLSR_NUM_TABLES] = {nullptr, nullptr, nullptr, nullptr};
+  long long tab_rows[CLSR_NUM_TABLES];
+  int tab_dim[CLSR_NUM_TABLES];
+  int32_t* slot[3] = {nullptr, nullptr, nullptr};  // item, cate, user
+  int32_t* uniq[3] = {nullptr, nullptr, nullptr};
+  long long uniq_cap[3];
+  float* cg[CLSR_NUM_TABLES] = {nullptr, nullptr, nullptr, nullptr};
+  int32_t* counts = nullptr;  // [0] contrastive rows, [1] uniq items, [2] uniq cates, [3] uniq users
+  double* sumsq = nullptr;    // [4]
+  double* acc = nullptr;      // [16]
+  float* d_losses = nullptr;  // [5]
+  float* h_losses = nullptr;  // pinned
+
+  // staged inputs
+  int32_t *in_users, *in_items, *in_cates, *in_ih, *in_ch, *in_mask, *d_len;
+  float *in_tfa, *in_ttn, *in_labels;
+  char* h_stage = nullptr;  // pinned staging
+  size_t h_stage_bytes = 0;
+  float* h_out = nullptr;  // pinned [2*Bmax]
+
+  // workspace
+  std::vector<void*> allocs;
+  std::map<std::string, std::pair<float*, long long>> bufs;
+  long long ws_bytes = 0;
+
+  float* B(const char* n) { return bufs.at(n).first; }
+};
+
+namespace {
+
+int fail(clsr_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _c = (call);                                                                       \
+    if (_c != cudaSuccess)                                                                         \
+      return fail(e, CLSR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_c), __FILE__, \
+                  __LINE__);                                                                       \
+  } while (0)
+
+// Launch bookkeeping: count, optional sync-and-check per kernel (debug).
+#define POST(name)                                                                                 \
+  do {                                                                                             \
+    e->launches++;                                                                                 \
+    cudaError_t _c = cudaGetLastError();                                                           \
+    if (_c == cudaSuccess && e->debug_sync) _c = cudaStreamSynchronize(e->stream);                 \
+    if (_c != cudaSuccess)                                                                         \
+      return fail(e, CLSR_ERR_CUDA, "kernel %s failed: %s (%s:%d)", name, cudaGetErrorString(_c),  \
+                  __FILE__, __LINE__);                                                             \
+  } while (0)
+
+template <typename Tp>
+int dalloc(clsr_engine* e, Tp** p, long long n, bool zero = true) {
+  size_t bytes = (size_t)(n > 0 ? n : 1) * sizeof(Tp);
+  bytes = (bytes + 255) & ~(size_t)255;
+  CK(cudaMalloc((void**)p, bytes));
+  e->allocs.push_back((void*)*p);
+  e->ws_bytes += (long long)bytes;
+  if (zero) CK(cudaMemset(*p, 0, bytes));
+  return 0;
+}
+
+int fbuf(clsr_engine* e, const char* name, long long n) {
+  float* p = nullptr;
+  int rc = dalloc(e, &p, n);
+  if (rc) return rc;
+  e->bufs[name] = std::make_pair(p, n);
+  return 0;
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline int grid1d(clsr_engine* e, long long n, int block, int per_sm = 8) {
+  long long g = (n + block - 1) / block;
+  long long cap = (long long)e->num_sms * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---- dense variable inventory (mirrors clsr_b200/params.py::dense_spec) ---------------------------
+void add_dense(clsr_engine* e, const std::string& name, int rows, int cols, int trainable) {
+  DenseEntry d;
+  d.name = name;
+  d.off = e->Ptot;
+  d.rows = rows;
+  d.cols = cols;
+  d.n = (long long)rows * cols;
+  d.trainable = trainable;
+  e->dense_ix[name] = (int)e->dense.size();
+  e->dense.push_back(d);
+  e->Ptot += (d.n + 3) & ~3LL;  // keep every variable 16-byte aligned
+}
+long long poff(clsr_engine* e, const std::string& name) { return e->dense[e->dense_ix.at(name)].off; }
+
+void add_fcn(clsr_engine* e, const std::string& scope, int in, int n0, int n1, Mlp* m) {
+  int sizes[2] = {n0, n1};
+  int last = in;
+  for (int i = 0; i < 2; ++i) {
+    std::string li = std::to_string(i);
+    add_dense(e, scope + "w_nn_layer" + li, last, sizes[i], 1);
+    add_dense(e, scope + "b_nn_layer" + li, 1, sizes[i], 1);
+    std::string bn = scope + (i == 0 ? "batch_normalization/" : "batch_normalization_1/");
+    add_dense(e, bn + "gamma", 1, sizes[i], 1);
+    add_dense(e, bn + "beta", 1, sizes[i], 1);
+    add_dense(e, bn + "moving_mean", 1, sizes[i], 0);
+    add_dense(e, bn + "moving_variance", 1, sizes[i], 0);
+    last = sizes[i];
+  }
+  add_dense(e, scope + "w_nn_output", last, 1, 1);
+  add_dense(e, scope + "b_nn_output", 1, 1, 1);
+  m->in = in; m->n0 = n0; m->n1 = n1;
+  m->w0 = poff(e, scope + "w_nn_layer0"); m->b0 = poff(e, scope + "b_nn_layer0");
+  m->w1 = poff(e, scope + "w_nn_layer1"); m->b1 = poff(e, scope + "b_nn_layer1");
+  m->wo = poff(e, scope + "w_nn_output"); m->bo = poff(e, scope + "b_nn_output");
+  BnLayer* bl[2] = {&m->bn0, &m->bn1};
+  for (int i = 0; i < 2; ++i) {
+    std::string bn = scope + (i == 0 ? "batch_normalization/" : "batch_normalization_1/");
+    bl[i]->N = sizes[i];
+    bl[i]->gamma = poff(e, bn + "gamma"); bl[i]->beta = poff(e, bn + "beta");
+    bl[i]->mmean = poff(e, bn + "moving_mean"); bl[i]->mvar = poff(e, bn + "moving_variance");
+  }
+}
+
+const char* kSC = "sequential/clsr/";
+
+void build_inventory(clsr_engine* e) {
+  const int D = e->D, U = e->U, H = e->H, Q = e->Q;
+  std::string sc = kSC;
+  std::string lt = sc + "long_term/attention_fcn/";
+  add_dense(e, lt + "attention_mat", D, U, 1);
+  add_fcn(e, lt + "att_fcn/nn_part/", 4 * U, e->A0, e->A1, &e->mlp_long);
+  std::string st = sc + "short_term/";
+  add_dense(e, st + "attention_fcn/attention_mat", H, Q, 1);
+  add_fcn(e, st + "attention_fcn/att_fcn/nn_part/", 4 * Q, e->A0, e->A1, &e->mlp_short);
+  const std::string gs[2] = {st + "short_term_intention/gru_cell/", sc + "causal2/causal2/gru_cell/"};
+  const int gu[2] = {U, H};
+  for (int i = 0; i < 2; ++i) {
+    add_dense(e, gs[i] + "gates/kernel", D + gu[i], 2 * gu[i], 1);
+    add_dense(e, gs[i] + "gates/bias", 1, 2 * gu[i], 1);
+    add_dense(e, gs[i] + "candidate/kernel", D + gu[i], gu[i], 1);
+    add_dense(e, gs[i] + "candidate/bias", 1, gu[i], 1);
+  }
+  std::string tl = st + "time4lstm/time4lstm_cell/";
+  add_dense(e, tl + "kernel", D + H, 4 * H, 1);
+  add_dense(e, tl + "bias", 1, 4 * H, 1);
+  const char* v1[] = {"_time_input_w1", "_time_input_bias1", "_time_input_w2", "_time_input_bias2",
+                      "_time_bias1", "_time_bias2"};
+  for (const char* n : v1) add_dense(e, tl + n, 1, H, 1);
+  add_dense(e, tl + "_time_kernel_w1", D, H, 1);
+  add_dense(e, tl + "_time_kernel_w2", D, H, 1);
+  const char* v2[] = {"_time_kernel_t1", "_time_kernel_t2", "_o_kernel_t1", "_o_kernel_t2"};
+  for (const char* n : v2) add_dense(e, tl + n, H, H, 1);
+  add_fcn(e, sc + "fcn_alpha/nn_part/", e->CA, e->A0, e->A1, &e->mlp_alpha);
+  add_fcn(e, "sequential/logit_fcn/nn_part/", H + D, e->L0, e->L1, &e->mlp_logit);
+  e->p_wattl = poff(e, lt + "attention_mat");
+  e->p_watts = poff(e, st + "attention_fcn/attention_mat");
+  e->p_tw1 = poff(e, tl + "_time_input_w1"); e->p_tb1 = poff(e, tl + "_time_input_bias1");
+  e->p_tw2 = poff(e, tl + "_time_input_w2"); e->p_tb2 = poff(e, tl + "_time_input_bias2");
+}
+
+long long wd_add(clsr_engine* e, const char* name, long long n) {
+  long long o = e->Wtot;
+  e->wd_off[name] = o;
+  e->Wtot += (n + 3) & ~3LL;
+  return o;
+}
+
+BlockOp mk(long long dst, int ldd, long long s1, int lds1, int rows, int cols, float c1 = 1.f,
+           long long s2 = -1, int lds2 = 0, float c2 = 0.f, int transpose = 0) {
+  BlockOp o;
+  o.dst = dst; o.src1 = s1; o.src2 = s2; o.rows = rows; o.cols = cols; o.ldd = ldd; o.lds1 = lds1;
+  o.lds2 = lds2; o.c1 = c1; o.c2 = c2; o.transpose = transpose; o.accumulate = 0;
+  return o;
+}
+
+// Folded weights (forward) and the inverse map of their gradients onto the TF variables.
+int build_weight_maps(clsr_engine* e) {
+  const int D = e->D, U = e->U, H = e->H, Q = e->Q, A0 = e->A0, A1 = e->A1, NX = e->NX, CA = e->CA;
+  const int L0 = e->L0, L1 = e->L1;
+  std::vector<BlockOp> prep, unprep;
+  std::string sc = kSC, st = sc + "short_term/", tl = st + "time4lstm/time4lstm_cell/";
+  auto W = [&](const char* n) { return e->wd_off.at(n); };
+
+  // ---- long attention: W0 rows [a | b | c | d], each U rows: feat = [a, q, a-q, a*q] ----
+  {
+    long long w0 = e->mlp_long.w0;
+    long long wl0 = wd_add(e, "Wl0", 2LL * U * A0), wl0q = wd_add(e, "Wl0q", (long long)U * A0);
+    long long wl0T = wd_add(e, "Wl0T", 2LL * U * A0), wl0qT = wd_add(e, "Wl0qT", (long long)U * A0);
+    long long wattT = wd_add(e, "WattlT", (long long)U * D), w1T = wd_add(e, "W1lT", (long long)A1 * A0);
+    prep.push_back(mk(wl0, A0, w0, A0, U, A0, 1.f, w0 + 2LL * U * A0, A0, 1.f));          // a + c
+    prep.push_back(mk(wl0 + (long long)U * A0, A0, w0 + 3LL * U * A0, A0, U, A0));          // d
+    prep.push_back(mk(wl0q, A0, w0 + (long long)U * A0, A0, U, A0, 1.f, w0 + 2LL * U * A0, A0, -1.f));
+    prep.push_back(mk(wl0T, 2 * U, w0, A0, U, A0, 1.f, w0 + 2LL * U * A0, A0, 1.f, 1));
+    prep.push_back(mk(wl0T + U, 2 * U, w0 + 3LL * U * A0, A0, U, A0, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(wl0qT, U, w0 + (long long)U * A0, A0, U, A0, 1.f, w0 + 2LL * U * A0, A0, -1.f, 1));
+    prep.push_back(mk(wattT, D, e->p_wattl, U, D, U, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(w1T, A0, e->mlp_long.w1, A1, A0, A1, 1.f, -1, 0, 0.f, 1));
+    // gradients: dW0[a] = dWl0[0:U]; dW0[b] = dWl0q; dW0[c] = dWl0[0:U] - dWl0q; dW0[d] = dWl0[U:2U]
+    unprep.push_back(mk(w0, A0, wl0, A0, U, A0));
+    unprep.push_back(mk(w0 + (long long)U * A0, A0, wl0q, A0, U, A0));
+    unprep.push_back(mk(w0 + 2LL * U * A0, A0, wl0, A0, U, A0, 1.f, wl0q, A0, -1.f));
+    unprep.push_back(mk(w0 + 3LL * U * A0, A0, wl0 + (long long)U * A0, A0, U, A0));
+  }
+  // ---- short attention: W0 rows [a | b | c | d], each Q rows; d splits into sti (U) / target (D) ----
+  {
+    long long w0 = e->mlp_short.w0;
+    long long wi = wd_add(e, "Ws0i", (long long)(Q + U) * A0), wt = wd_add(e, "Ws0t", (long long)D * A0);
+    long long wq = wd_add(e, "Ws0q", (long long)Q * A0);
+    long long wiT = wd_add(e, "Ws0iT", (long long)(Q + U) * A0), wtT = wd_add(e, "Ws0tT", (long long)D * A0);
+    long long wqT = wd_add(e, "Ws0qT", (long long)Q * A0);
+    long long wattT = wd_add(e, "WattsT", (long long)Q * H), w1T = wd_add(e, "W1sT", (long long)A1 * A0);
+    long long a = w0, b = w0 + (long long)Q * A0, c = w0 + 2LL * Q * A0, d = w0 + 3LL * Q * A0;
+    prep.push_back(mk(wi, A0, a, A0, Q, A0, 1.f, c, A0, 1.f));
+    prep.push_back(mk(wi + (long long)Q * A0, A0, d, A0, U, A0));
+    prep.push_back(mk(wt, A0, d + (long long)U * A0, A0, D, A0));
+    prep.push_back(mk(wq, A0, b, A0, Q, A0, 1.f, c, A0, -1.f));
+    prep.push_back(mk(wiT, Q + U, a, A0, Q, A0, 1.f, c, A0, 1.f, 1));
+    prep.push_back(mk(wiT + Q, Q + U, d, A0, U, A0, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(wtT, D, d + (long long)U * A0, A0, D, A0, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(wqT, Q, b, A0, Q, A0, 1.f, c, A0, -1.f, 1));
+    prep.push_back(mk(wattT, H, e->p_watts, Q, H, Q, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(w1T, A0, e->mlp_short.w1, A1, A0, A1, 1.f, -1, 0, 0.f, 1));
+    unprep.push_back(mk(a, A0, wi, A0, Q, A0));
+    unprep.push_back(mk(b, A0, wq, A0, Q, A0));
+    unprep.push_back(mk(c, A0, wi, A0, Q, A0, 1.f, wq, A0, -1.f));
+    unprep.push_back(mk(d, A0, wi + (long long)Q * A0, A0, U, A0));
+    unprep.push_back(mk(d + (long long)U * A0, A0, wt, A0, D, A0));
+  }
+  // ---- recurrences: input halves of every kernel side by side in Wx_all [D, NX] ----
+  {
+    long long wx = wd_add(e, "Wx_all", (long long)D * NX), bx = wd_add(e, "bx_all", NX);
+    long long wxT = wd_add(e, "Wx_allT", (long long)D * NX);
+    long long wt = wd_add(e, "Wt", 2LL * H * 3 * H), wtT = wd_add(e, "WtT", 2LL * H * 3 * H);
+    const std::string gs[2] = {st + "short_term_intention/gru_cell/", sc + "causal2/causal2/gru_cell/"};
+    const int gu[2] = {U, H};
+    const int og[2] = {e->oG1, e->oG2}, oc[2] = {e->oC1, e->oC2};
+    const char* ng[2][4] = {{"Wgh1", "Wch1", "Wgh1T", "Wch1T"}, {"Wgh2", "Wch2", "Wgh2T", "Wch2T"}};
+    for (int i = 0; i < 2; ++i) {
+      int u = gu[i];
+      long long gk = poff(e, gs[i] + "gates/kernel"), gb = poff(e, gs[i] + "gates/bias");
+      long long ck = poff(e, gs[i] + "candidate/kernel"), cb = poff(e, gs[i] + "candidate/bias");
+      long long wgh = wd_add(e, ng[i][0], (long long)u * 2 * u), wch = wd_add(e, ng[i][1], (long long)u * u);
+      long long wghT = wd_add(e, ng[i][2], (long long)u * 2 * u), wchT = wd_add(e, ng[i][3], (long long)u * u);
+      prep.push_back(mk(wx + og[i], NX, gk, 2 * u, D, 2 * u));
+      prep.push_back(mk(wx + oc[i], NX, ck, u, D, u));
+      prep.push_back(mk(wxT + (long long)og[i] * D, D, gk, 2 * u, D, 2 * u, 1.f, -1, 0, 0.f, 1));
+      prep.push_back(mk(wxT + (long long)oc[i] * D, D, ck, u, D, u, 1.f, -1, 0, 0.f, 1));
+      prep.push_back(mk(bx + og[i], NX, gb, 2 * u, 1, 2 * u));
+      prep.push_back(mk(bx + oc[i], NX, cb, u, 1, u));
+      prep.push_back(mk(wgh, 2 * u, gk + (long long)D * 2 * u, 2 * u, u, 2 * u));
+      prep.push_back(mk(wch, u, ck + (long long)D * u, u, u, u));
+      prep.push_back(mk(wghT, u, gk + (long long)D * 2 * u, 2 * u, u, 2 * u, 1.f, -1, 0, 0.f, 1));
+      prep.push_back(mk(wchT, u, ck + (long long)D * u, u, u, u, 1.f, -1, 0, 0.f, 1));
+      unprep.push_back(mk(gk, 2 * u, wx + og[i], NX, D, 2 * u));
+      unprep.push_back(mk(ck, u, wx + oc[i], NX, D, u));
+      unprep.push_back(mk(gb, 2 * u, bx + og[i], NX, 1, 2 * u));
+      unprep.push_back(mk(cb, u, bx + oc[i], NX, 1, u));
+      unprep.push_back(mk(gk + (long long)D * 2 * u, 2 * u, wgh, 2 * u, u, 2 * u));
+      unprep.push_back(mk(ck + (long long)D * u, u, wch, u, u, u));
+    }
+    long long lk = poff(e, tl + "kernel"), lb = poff(e, tl + "bias");
+    long long km = wd_add(e, "Km", (long long)H * 4 * H), kmT = wd_add(e, "KmT", (long long)H * 4 * H);
+    long long k1 = poff(e, tl + "_time_kernel_w1"), k2 = poff(e, tl + "_time_kernel_w2");
+    long long tb1 = poff(e, tl + "_time_bias1"), tb2 = poff(e, tl + "_time_bias2");
+    long long t1 = poff(e, tl + "_time_kernel_t1"), t2 = poff(e, tl + "_time_kernel_t2");
+    long long o1 = poff(e, tl + "_o_kernel_t1"), o2 = poff(e, tl + "_o_kernel_t2");
+    prep.push_back(mk(wx + e->oL, NX, lk, 4 * H, D, 4 * H));
+    prep.push_back(mk(wx + e->oTN, NX, k1, H, D, H));
+    prep.push_back(mk(wx + e->oTL, NX, k2, H, D, H));
+    prep.push_back(mk(wxT + (long long)e->oL * D, D, lk, 4 * H, D, 4 * H, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(wxT + (long long)e->oTN * D, D, k1, H, D, H, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(wxT + (long long)e->oTL * D, D, k2, H, D, H, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(bx + e->oL, NX, lb, 4 * H, 1, 4 * H));
+    prep.push_back(mk(bx + e->oTN, NX, tb1, H, 1, H));
+    prep.push_back(mk(bx + e->oTL, NX, tb2, H, 1, H));
+    prep.push_back(mk(km, 4 * H, lk + (long long)D * 4 * H, 4 * H, H, 4 * H));
+    prep.push_back(mk(kmT, H, lk + (long long)D * 4 * H, 4 * H, H, 4 * H, 1.f, -1, 0, 0.f, 1));
+    // Wt [2H, 3H]: rows [tanh-now | tanh-last], cols [o | time-now gate | time-last gate]
+    prep.push_back(mk(wt, 3 * H, o1, H, H, H));
+    prep.push_back(mk(wt + (long long)H * 3 * H, 3 * H, o2, H, H, H));
+    prep.push_back(mk(wt + H, 3 * H, t1, H, H, H));
+    prep.push_back(mk(wt + (long long)H * 3 * H + 2 * H, 3 * H, t2, H, H, H));
+    prep.push_back(mk(wtT, 2 * H, o1, H, H, H, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(wtT + H, 2 * H, o2, H, H, H, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(wtT + (long long)H * 2 * H, 2 * H, t1, H, H, H, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(wtT + 2LL * H * 2 * H + H, 2 * H, t2, H, H, H, 1.f, -1, 0, 0.f, 1));
+    unprep.push_back(mk(lk, 4 * H, wx + e->oL, NX, D, 4 * H));
+    unprep.push_back(mk(lk + (long long)D * 4 * H, 4 * H, km, 4 * H, H, 4 * H));
+    unprep.push_back(mk(lb, 4 * H, bx + e->oL, NX, 1, 4 * H));
+    unprep.push_back(mk(k1, H, wx + e->oTN, NX, D, H));
+    unprep.push_back(mk(k2, H, wx + e->oTL, NX, D, H));
+    unprep.push_back(mk(tb1, H, bx + e->oTN, NX, 1, H));
+    unprep.push_back(mk(tb2, H, bx + e->oTL, NX, 1, H));
+    unprep.push_back(mk(o1, H, wt, 3 * H, H, H));
+    unprep.push_back(mk(o2, H, wt + (long long)H * 3 * H, 3 * H, H, H));
+    unprep.push_back(mk(t1, H, wt + H, 3 * H, H, H));
+    unprep.push_back(mk(t2, H, wt + (long long)H * 3 * H + 2 * H, 3 * H, H, H));
+  }
+  // ---- alpha / logit MLPs: transposed copies for the data-gradient GEMMs ----
+  {
+    long long a0T = wd_add(e, "Wa0T", (long long)CA * A0), a1T = wd_add(e, "Wa1T", (long long)A0 * A1);
+    long long g0T = wd_add(e, "Wg0T", (long long)(H + D) * L0), g1T = wd_add(e, "Wg1T", (long long)L0 * L1);
+    prep.push_back(mk(a0T, CA, e->mlp_alpha.w0, A0, CA, A0, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(a1T, A0, e->mlp_alpha.w1, A1, A0, A1, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(g0T, H + D, e->mlp_logit.w0, L0, H + D, L0, 1.f, -1, 0, 0.f, 1));
+    prep.push_back(mk(g1T, L0, e->mlp_logit.w1, L1, L0, L1, 1.f, -1, 0, 0.f, 1));
+  }
+  (void)W;
+  e->n_prep = (int)prep.size();
+  e->n_unprep = (int)unprep.size();
+  int rc;
+  if ((rc = dalloc(e, &e->Wd, e->Wtot))) return rc;
+  if ((rc = dalloc(e, &e->dWd, e->Wtot))) return rc;
+  if ((rc = dalloc(e, &e->ops_prep, e->n_prep, false))) return rc;
+  if ((rc = dalloc(e, &e->ops_unprep, e->n_unprep, false))) return rc;
+  CK(cudaMemcpy(e->ops_prep, prep.data(), prep.size() * sizeof(BlockOp), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->ops_unprep, unprep.data(), unprep.size() * sizeof(BlockOp), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int alloc_bn(clsr_engine* e, BnLayer* b) {
+  int rc;
+  if ((rc = dalloc(e, &b->stat_f, 2 * b->N))) return rc;
+  if ((rc = dalloc(e, &b->stat_b, 2 * b->N))) return rc;
+  float** ps[] = {&b->scale, &b->shift, &b->mean, &b->rstd, &b->al, &b->be, &b->ga};
+  for (float** p : ps)
+    if ((rc = dalloc(e, p, b->N))) return rc;
+  return 0;
+}
+
+// ---- launch helpers --------------------------------------------------------------------------------
+int gemm(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, const float* W, int ldw,
+         const EpiOp& ep, bool stats) {
+  if (M <= 0) return 0;
+  auto launch = [&](auto kern, int BM, int BN) {
+    int tiles = cdiv(M, BM);
+    int gx = tiles < e->num_sms * 4 ? tiles : e->num_sms * 4;
+    dim3 grid(gx, cdiv(N, BN));
+    kern<<<grid, 256, 0, e->stream>>>(M, N, K, a, W, ldw, ep);
+  };
+  if (N <= 40) {
+    if (stats) launch(gemm_kernel<8, 5, 8, true>, 256, 40); else launch(gemm_kernel<8, 5, 8, false>, 256, 40);
+  } else if (N <= 64) {
+    if (stats) launch(gemm_kernel<8, 4, 16, true>, 128, 64); else launch(gemm_kernel<8, 4, 16, false>, 128, 64);
+  } else if (N <= 80) {
+    if (stats) launch(gemm_kernel<8, 5, 16, true>, 128, 80); else launch(gemm_kernel<8, 5, 16, false>, 128, 80);
+  } else {
+    if (stats) launch(gemm_kernel<8, 4, 32, true>, 64, 128); else launch(gemm_kernel<8, 4, 32, false>, 64, 128);
+  }
+  POST(name);
+  return 0;
+}
+
+int dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& a, const AOp& b, float* dW,
+           int lddw, float* colsum) {
+  if (M <= 0) return 0;
+  int ty = cdiv(K, 64), tz = cdiv(N, 64);
+  int want = (e->num_sms * 4) / (ty * tz);
+  if (want < 1) want = 1;
+  int rows_per = cdiv(M, want);
+  rows_per = ((rows_per + 31) / 32) * 32;
+  dim3 grid(cdiv(M, rows_per), ty, tz);
+  if (colsum) dw_kernel<true><<<grid, 256, 0, e->stream>>>(M, K, N, a, b, dW, lddw, colsum, rows_per);
+  else dw_kernel<false><<<grid, 256, 0, e->stream>>>(M, K, N, a, b, dW, lddw, nullptr, rows_per);
+  POST(name);
+  return 0;
+}
+
+AOp a_plain(const float* A, int lda) {
+  AOp a; a.mode = A_PLAIN; a.A = A; a.lda = lda; return a;
+}
+AOp a_bnrelu(const float* A, int lda, const BnLayer& b) {
+  AOp a; a.mode = A_BNRELU; a.A = A; a.lda = lda; a.v0 = b.scale; a.v1 = b.shift; return a;
+}
+AOp a_affine2(const float* dy, const float* h, int ld, const BnLayer& b) {
+  AOp a; a.mode = A_AFFINE2; a.A = dy; a.A2 = h; a.lda = ld; a.lda2 = ld; a.v0 = b.al; a.v1 = b.be; a.v2 = b.ga;
+  return a;
+}
+AOp a_catmul(const float* A, int lda, int W1, int off, const float* V, int ldv, int T) {
+  AOp a; a.mode = A_CATMUL; a.A = A; a.lda = lda; a.W1 = W1; a.off = off; a.A2 = V; a.lda2 = ldv; a.T = T;
+  return a;
+}
+AOp a_mulrow(const float* A, int lda, int off, const float* V, int ldv, int T, int G) {
+  AOp a; a.mode = A_MULROW; a.A = A; a.lda = lda; a.off = off; a.A2 = V; a.lda2 = ldv; a.T = T; a.G = G;
+  return a;
+}
+AOp a_cat2row(const float* P, int ldp, int W1, const float* V, int ldv, int G) {
+  AOp a; a.mode = A_CAT2ROW; a.A = P; a.lda = ldp; a.W1 = W1; a.A2 = V; a.lda2 = ldv; a.G = G; return a;
+}
+EpiOp e_store(float* C, int ldc, const float* bias = nullptr, int flags = 0) {
+  EpiOp p; p.C = C; p.ldc = ldc; p.bias = bias; p.flags = flags; return p;
+}
+
+int bn_fwd(clsr_engine* e, BnLayer& b, double count, int train, int update) {
+  bn_fwd_finalize_kernel<<<cdiv(b.N, 128), 128, 0, e->stream>>>(
+      b.stat_f, b.N, count, e->P + b.gamma, e->P + b.beta, e->cfg.bn_eps, e->cfg.bn_momentum,
+      e->P + b.mmean, e->P + b.mvar, train, update, b.scale, b.shift, b.mean, b.rstd);
+  POST("bn_fwd_finalize");
+  return 0;
+}
+int bn_bwd(clsr_engine* e, BnLayer& b, double count) {
+  bn_bwd_finalize_kernel<<<cdiv(b.N, 128), 128, 0, e->stream>>>(
+      b.stat_b, b.N, count, e->P + b.gamma, b.mean, b.rstd, b.al, b.be, b.ga, e->Pg + b.gamma, e->Pg + b.beta);
+  POST("bn_bwd_finalize");
+  return 0;
+}
+
+// Forward of a row-wise _fcn_net (alpha gate, logit): in [rows, m.in] -> h0, h1, out[rows].
+int mlp_fwd(clsr_engine* e, Mlp& m, const float* in, int rows, float* h0, float* h1, float* out, int train,
+            int update) {
+  int rc;
+  EpiOp ep = e_store(h0, m.n0, e->P + m.b0);
+  ep.stat = m.bn0.stat_f;
+  if ((rc = gemm(e, "mlp_l0", rows, m.n0, m.in, a_plain(in, m.in), e->P + m.w0, m.n0, ep, train != 0))) return rc;
+  if ((rc = bn_fwd(e, m.bn0, rows, train, update))) return rc;
+  ep = e_store(h1, m.n1, e->P + m.b1);
+  ep.stat = m.bn1.stat_f;
+  if ((rc = gemm(e, "mlp_l1", rows, m.n1, m.n0, a_bnrelu(h0, m.n0, m.bn0), e->P + m.w1, m.n1, ep, train != 0)))
+    return rc;
+  if ((rc = bn_fwd(e, m.bn1, rows, train, update))) return rc;
+  rowdot_kernel<<<grid1d(e, (long long)rows * 32, 256), 256, 0, e->stream>>>(
+      h1, m.n1, m.bn1.scale, m.bn1.shift, e->P + m.wo, e->P + m.bo, rows, out);
+  POST("rowdot");
+  return 0;
+}
+
+// Backward of a row-wise _fcn_net from dout[rows]: weight/BN gradients into Pg, d(in) into din.
+int mlp_bwd(clsr_engine* e, Mlp& m, const float* in, int rows, const float* h0, const float* h1,
+            const float* dout, float* dy1, float* dy0, const float* w0T, const float* w1T, float* din) {
+  int rc;
+  {
+    int nx = ((m.n1 + 31) / 32) * 32;
+    dim3 blk(nx, 256 / nx > 0 ? 256 / nx : 1);
+    rowdot_bwd_kernel<<<grid1d(e, rows, blk.y, 2), blk, 0, e->stream>>>(
+        dout, h1, m.n1, m.bn1.scale, m.bn1.shift, m.bn1.mean, m.bn1.rstd, e->P + m.wo, rows, dy1,
+        m.bn1.stat_b, e->Pg + m.wo, e->Pg + m.bo);
+    POST("rowdot_bwd");
+  }
+  if ((rc = bn_bwd(e, m.bn1, rows))) return rc;
+  EpiOp ep = e_store(dy0, m.n0, nullptr, E_RELUMASK | E_STAT_XHAT);
+  ep.hpre = h0; ep.ldh = m.n0; ep.scale = m.bn0.scale; ep.shift = m.bn0.shift; ep.mean = m.bn0.mean;
+  ep.rstd = m.bn0.rstd; ep.stat = m.bn0.stat_b;
+  if ((rc = gemm(e, "mlp_dy0", rows, m.n0, m.n1, a_affine2(dy1, h1, m.n1, m.bn1), w1T, m.n0, ep, true))) return rc;
+  if ((rc = dwgemm(e, "mlp_dw1", rows, m.n0, m.n1, a_bnrelu(h0, m.n0, m.bn0), a_affine2(dy1, h1, m.n1, m.bn1),
+                   e->Pg + m.w1, m.n1, nullptr)))
+    return rc;
+  if ((rc = bn_bwd(e, m.bn0, rows))) return rc;
+  if ((rc = gemm(e, "mlp_din", rows, m.in, m.n0, a_affine2(dy0, h0, m.n0, m.bn0), w0T, m.in,
+                 e_store(din, m.in), false)))
+    return rc;
+  if ((rc = dwgemm(e, "mlp_dw0", rows, m.in, m.n0, a_plain(in, m.in), a_affine2(dy0, h0, m.n0, m.bn0),
+                   e->Pg + m.w0, m.n0, nullptr)))
+    return rc;
+  return 0;
+}
+
+struct StepCtx {
+  int B, G, S, T;
+  int seq_stride;   // elements between consecutive sequences in the [*,T] input arrays
+  int user_stride;  // elements between consecutive sequences in users[]
+  const int32_t *users, *items, *cates, *ih, *ch, *mask;
+  const float *tfa, *ttn, *labels;
+};
+
+// Copy (host) or alias (device) the feed arrays.
+int stage_inputs(clsr_engine* e, const clsr_batch* b, StepCtx* c, bool need_labels) {
+  const int T = e->T;
+  c->B = b->rows; c->G = b->group; c->S = b->rows / b->group; c->T = T;
+  if (b->on_device) {
+    c->users = b->users; c->items = b->items; c->cates = b->cates; c->ih = b->item_history;
+    c->ch = b->cate_history; c->mask = b->mask; c->tfa = b->time_from_first_action; c->ttn = b->time_to_now;
+    c->labels = b->labels;
+    c->seq_stride = c->G * T;
+    c->user_stride = c->G;
+    return 0;
+  }
+  // Host feed: pack only what the step reads (one row per sequence) into pinned staging, then a
+  // single async H2D copy.
+  const int S = c->S, B = c->B, G = c->G;
+  size_t seq_i = (size_t)S * T * 4;
+  size_t need = 5 * seq_i + (size_t)S * 4 + (size_t)B * 4 * 3;
+  if (need > e->h_stage_bytes) return fail(e, CLSR_ERR_ARG, "batch exceeds staging capacity");
+  char* hp = e->h_stage;
+  auto pack_rows = [&](const void* src, size_t row_bytes) {
+    const char* s = (const char*)src;
+    if (G == 1) memcpy(hp, s, row_bytes * S);
+    else for (int i = 0; i < S; ++i) memcpy(hp + row_bytes * i, s + row_bytes * (size_t)i * G, row_bytes);
+    char* r = hp;
+    hp += row_bytes * S;
+    return r;
+  };
+  size_t rowb = (size_t)T * 4;
+  char* base = hp;
+  pack_rows(b->item_history, rowb);
+  pack_rows(b->cate_history, rowb);
+  pack_rows(b->mask, rowb);
+  pack_rows(b->time_from_first_action, rowb);
+  pack_rows(b->time_to_now, rowb);
+  pack_rows(b->users, 4);
+  memcpy(hp, b->items, (size_t)B * 4); hp += (size_t)B * 4;
+  memcpy(hp, b->cates, (size_t)B * 4); hp += (size_t)B * 4;
+  if (need_labels && b->labels) memcpy(hp, b->labels, (size_t)B * 4);
+  hp += (size_t)B * 4;
+  // device layout mirrors the staging layout inside one contiguous block starting at in_ih
+  CK(cudaMemcpyAsync(e->in_ih, base, (size_t)(hp - base), cudaMemcpyHostToDevice, e->stream));
+  char* d = (char*)e->in_ih;
+  c->ih = (const int32_t*)d; d += seq_i;
+  c->ch = (const int32_t*)d; d += seq_i;
+  c->mask = (const int32_t*)d; d += seq_i;
+  c->tfa = (const float*)d; d += seq_i;
+  c->ttn = (const float*)d; d += seq_i;
+  c->users = (const int32_t*)d; d += (size_t)S * 4;
+  c->items = (const int32_t*)d; d += (size_t)B * 4;
+  c->cates = (const int32_t*)d; d += (size_t)B * 4;
+  c->labels = (const float*)d;
+  c->seq_stride = T;
+  c->user_stride = 1;
+  return 0;
+}
+
+int check_batch(clsr_engine* e, const clsr_batch* b, bool train) {
+  if (!b || b->rows <= 0 || b->group <= 0 || b->rows % b->group) return fail(e, CLSR_ERR_ARG, "bad rows/group");
+  if (b->rows > e->Bmax) return fail(e, CLSR_ERR_ARG, "rows %d exceed max_rows %d", b->rows, e->Bmax);
+  if (b->rows / b->group > e->Smax)
+    return fail(e, CLSR_ERR_ARG, "sequences %d exceed max_seqs %d", b->rows / b->group, e->Smax);
+  if (!b->users || !b->items || !b->cates || !b->item_history || !b->cate_history || !b->mask ||
+      !b->time_from_first_action || !b->time_to_now)
+    return fail(e, CLSR_ERR_ARG, "null feed array");
+  if (train) {
+    if (!b->labels) return fail(e, CLSR_ERR_ARG, "labels required for training");
+    if (b->rows % e->cfg.train_group) return fail(e, CLSR_ERR_ARG, "rows not a multiple of train_group");
+  }
+  for (int t = 0; t < CLSR_NUM_TABLES; ++t)
+    if (!e->tab[t]) return fail(e, CLSR_ERR_STATE, "table %d not bound", t);
+  return 0;
+}
+
+int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
+  const int B = c.B, G = c.G, S = c.S, T = c.T;
+  const int D = e->D, U = e->U, H = e->H, Q = e->Q, A0 = e->A0, A1 = e->A1, NX = e->NX, Di = e->Di, Dc = e->Dc;
+  const long long M = (long long)S * T, MB = (long long)B * T;
+  cudaStream_t st = e->stream;
+  int rc;
+  auto W = [&](const char* n) { return e->Wd + e->wd_off.at(n); };
+
+  seq_prep_kernel<<<grid1d(e, S, 128), 128, 0, st>>>(c.mask, c.seq_stride, T, S, e->cfg.contrastive_len_threshold,
+                                                     e->d_len, e->counts);
+  POST("seq_prep");
+  blockop_kernel<<<e->n_prep, 256, 0, st>>>(e->ops_prep, e->Wd, e->P);
+  POST("prep_weights");
+
+  // ---- K1+K3: embedding gathers ----
+  float* X = e->B("X");
+  {
+    long long nvec = M * (D / 4);
+    gather_hist_kernel<4><<<grid1d(e, cdiv(nvec, 4), 256, 8), 256, 0, st>>>(
+        c.ih, c.ch, c.seq_stride, T, e->tab[CLSR_TABLE_ITEM], e->tab[CLSR_TABLE_CATE], Di, Dc, X, M);
+    POST("gather_hist");
+  }
+  float* tgt = e->B("tgt");
+  gather_rows_kernel<<<grid1d(e, (long long)B * Di / 4, 256), 256, 0, st>>>(c.items, 1, e->tab[CLSR_TABLE_ITEM], Di, tgt, D, 0, B);
+  POST("gather_tgt_item");
+  gather_rows_kernel<<<grid1d(e, (long long)B * Dc / 4, 256), 256, 0, st>>>(c.cates, 1, e->tab[CLSR_TABLE_CATE], Dc, tgt, D, Di, B);
+  POST("gather_tgt_cate");
+  float *ul = e->B("ul"), *us = e->B("us");
+  gather_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(c.users, c.user_stride, e->tab[CLSR_TABLE_USER_LONG], U, ul, U, 0, S);
+  POST("gather_ul");
+  gather_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(c.users, c.user_stride, e->tab[CLSR_TABLE_USER_SHORT], U, us, U, 0, S);
+  POST("gather_us");
+
+  // ---- hoisted input projections of the three recurrences ----
+  float *TNL = e->B("TNL"), *PX = e->B("PX");
+  time_feat_kernel<<<grid1d(e, M * 2 * H, 256), 256, 0, st>>>(c.ttn, c.tfa, c.seq_stride, T, e->P + e->p_tw1, e->P + e->p_tb1,
+                                                             e->P + e->p_tw2, e->P + e->p_tb2, H, TNL, M);
+  POST("time_feat");
+  if ((rc = gemm(e, "px", (int)M, NX, D, a_plain(X, D), W("Wx_all"), NX, e_store(PX, NX, W("bx_all")), false))) return rc;
+  if ((rc = gemm(e, "px_time", (int)M, 3 * H, 2 * H, a_plain(TNL, 2 * H), W("Wt"), 3 * H,
+                 e_store(PX + e->oO, NX, nullptr, E_ACCUM), false)))
+    return rc;
+
+  // ---- recurrences ----
+  const int nblk = cdiv(S, RNN_NSEQ);
+  {
+    size_t smg = (size_t)(U * 2 * U + U * U + 3 * U * RNN_LD) * 4;
+    gru_fwd_kernel<<<nblk, RNN_THREADS, smg, st>>>(PX, NX, e->oG1, e->oC1, us, W("Wgh1"), W("Wch1"), e->d_len, S, T, U,
+                                                   e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"));
+    POST("gru_fwd_sti");
+    size_t smg2 = (size_t)(H * 2 * H + H * H + 3 * H * RNN_LD) * 4;
+    gru_fwd_kernel<<<nblk, RNN_THREADS, smg2, st>>>(PX, NX, e->oG2, e->oC2, nullptr, W("Wgh2"), W("Wch2"), e->d_len, S, T, H,
+                                                    e->B("g2"), e->B("c2"), e->B("hp2"), e->B("rh2"), e->B("fs"));
+    POST("gru_fwd_causal2");
+    size_t sml = (size_t)(H * 4 * H + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
+    lstm_fwd_kernel<<<nblk, RNN_THREADS, sml, st>>>(PX, NX, e->oL, e->oTN, e->oTL, W("Km"), e->d_len, S, T, H,
+                                                    e->B("G4"), e->B("cp"), e->B("mp"), e->B("R"));
+    POST("lstm_fwd");
+  }
+
+  // ---- long-term attention (all per sequence) ----
+  Mlp& ml = e->mlp_long;
+  float *al = e->B("al"), *qbl = e->B("qbl"), *h0l = e->B("h0l"), *h1l = e->B("h1l");
+  if ((rc = gemm(e, "al", (int)M, U, D, a_plain(X, D), e->P + e->p_wattl, U, e_store(al, U), false))) return rc;
+  if ((rc = gemm(e, "qbl", S, A0, U, a_plain(ul, U), W("Wl0q"), A0, e_store(qbl, A0, e->P + ml.b0), false))) return rc;
+  {
+    EpiOp ep = e_store(h0l, A0, nullptr, E_ROWBIAS);
+    ep.rb = qbl; ep.ldrb = A0; ep.rbT = T; ep.stat = ml.bn0.stat_f;
+    if ((rc = gemm(e, "h0l", (int)M, A0, 2 * U, a_catmul(al, U, U, 0, ul, U, T), W("Wl0"), A0, ep, train != 0))) return rc;
+    if ((rc = bn_fwd(e, ml.bn0, (double)M, train, update_bn))) return rc;
+    ep = e_store(h1l, A1, e->P + ml.b1);
+    ep.stat = ml.bn1.stat_f;
+    if ((rc = gemm(e, "h1l", (int)M, A1, A0, a_bnrelu(h0l, A0, ml.bn0), e->P + ml.w1, A1, ep, train != 0))) return rc;
+    if ((rc = bn_fwd(e, ml.bn1, (double)M, train, update_bn))) return rc;
+  }
+  {
+    int wpb = 4;
+    size_t sm = (size_t)(3 * A1 + wpb * T) * 4;
+    pool_fwd_kernel<<<grid1d(e, cdiv(S, wpb), 1, 8), 128, sm, st>>>(
+        h1l, A1, ml.bn1.scale, ml.bn1.shift, e->P + ml.wo, e->P + ml.bo, X, D, e->d_len, S, T, 1, e->B("wl"),
+        e->B("afl"), e->B("hm"), e->B("hr"), e->cfg.contrastive_recent_k);
+    POST("pool_fwd_long");
+  }
+
+  // ---- short-term attention ----
+  Mlp& ms = e->mlp_short;
+  float *R = e->B("R"), *as = e->B("as"), *invs = e->B("invs"), *qbs = e->B("qbs"), *h0s = e->B("h0s"),
+        *h1s = e->B("h1s"), *sti = e->B("sti");
+  if ((rc = gemm(e, "as", (int)M, Q, H, a_plain(R, H), e->P + e->p_watts, Q, e_store(as, Q), false))) return rc;
+  if ((rc = gemm(e, "invs", (int)M, A0, Q + U, a_catmul(as, Q, Q, 0, sti, U, T), W("Ws0i"), A0, e_store(invs, A0), false)))
+    return rc;
+  if ((rc = gemm(e, "qbs", B, A0, Q, a_cat2row(sti, U, U, tgt, D, G), W("Ws0q"), A0, e_store(qbs, A0, e->P + ms.b0), false)))
+    return rc;
+  {
+    EpiOp ep = e_store(h0s, A0, nullptr, E_ROWBIAS | E_GROUPADD);
+    ep.rb = qbs; ep.ldrb = A0; ep.rbT = T; ep.ga = invs; ep.ldga = A0; ep.T = T; ep.G = G; ep.stat = ms.bn0.stat_f;
+    if ((rc = gemm(e, "h0s", (int)MB, A0, D, a_mulrow(as, Q, U, tgt, D, T, G), W("Ws0t"), A0, ep, train != 0))) return rc;
+    if ((rc = bn_fwd(e, ms.bn0, (double)MB, train, update_bn))) return rc;
+    ep = e_store(h1s, A1, e->P + ms.b1);
+    ep.stat = ms.bn1.stat_f;
+    if ((rc = gemm(e, "h1s", (int)MB, A1, A0, a_bnrelu(h0s, A0, ms.bn0), e->P + ms.w1, A1, ep, train != 0))) return rc;
+    if ((rc = bn_fwd(e, ms.bn1, (double)MB, train, update_bn))) return rc;
+  }
+  {
+    int wpb = 4;
+    size_t sm = (size_t)(3 * A1 + wpb * T) * 4;
+    pool_fwd_kernel<<<grid1d(e, cdiv(B, wpb), 1, 8), 128, sm, st>>>(
+        h1s, A1, ms.bn1.scale, ms.bn1.shift, e->P + ms.wo, e->P + ms.bo, R, H, e->d_len, B, T, G, e->B("ws"),
+        e->B("afs"), nullptr, nullptr, e->cfg.contrastive_recent_k);
+    POST("pool_fwd_short");
+  }
+
+  // ---- alpha gate, fusion, prediction MLP ----
+  float *ca = e->B("ca"), *mo = e->B("mo");
+  concat_alpha_kernel<<<grid1d(e, (long long)B * e->CA, 256), 256, 0, st>>>(
+      e->B("fs"), tgt, e->B("afl"), e->B("afs"), c.ttn, c.seq_stride, T, H, D, G, B, ca);
+  POST("concat_alpha");
+  if ((rc = mlp_fwd(e, e->mlp_alpha, ca, B, e->B("ha0"), e->B("ha1"), e->B("alogit"), train, update_bn))) return rc;
+  head_mid_kernel<<<grid1d(e, (long long)B * (H + D), 256), 256, 0, st>>>(e->B("alogit"), e->B("afl"), e->B("afs"), tgt, H,
+                                                                        D, G, B, e->B("alpha"), mo);
+  POST("head_mid");
+  if ((rc = mlp_fwd(e, e->mlp_logit, mo, B, e->B("hl0"), e->B("hl1"), e->B("logit"), train, update_bn))) return rc;
+  return 0;
+}
+
+int backward(clsr_engine* e, const StepCtx& c) {
+  const int B = c.B, G = c.G, S = c.S, T = c.T;
+  const int D = e->D, U = e->U, H = e->H, Q = e->Q, A0 = e->A0, A1 = e->A1, NX = e->NX, Di = e->Di, Dc = e->Dc;
+  const int CA = e->CA;
+  const long long M = (long long)S * T, MB = (long long)B * T;
+  cudaStream_t st = e->stream;
+  int rc;
+  auto W = [&](const char* n) { return e->Wd + e->wd_off.at(n); };
+  auto dW = [&](const char* n) { return e->dWd + e->wd_off.at(n); };
+  float *tgt = e->B("tgt"), *X = e->B("X");
+
+  // ---- data loss + prediction MLP ----
+  softmax_loss_kernel<<<grid1d(e, B / e->cfg.train_group, 128), 128, 0, st>>>(
+      e->B("logit"), c.labels, e->cfg.train_group, B, e->B("dlogit"), e->B("pred"), e->acc);
+  POST("softmax_loss");
+  if ((rc = mlp_bwd(e, e->mlp_logit, e->B("mo"), B, e->B("hl0"), e->B("hl1"), e->B("dlogit"), e->B("dhl1"), e->B("dhl0"),
+                    W("Wg0T"), W("Wg1T"), e->B("dmo"))))
+    return rc;
+  head_mid_bwd_kernel<<<grid1d(e, (long long)B * 32, 256), 256, 0, st>>>(e->B("dmo"), H + D, e->B("afl"), e->B("afs"),
+                                                                       e->B("alpha"), H, G, B, e->B("dalogit"));
+  POST("head_mid_bwd");
+  if ((rc = mlp_bwd(e, e->mlp_alpha, e->B("ca"), B, e->B("ha0"), e->B("ha1"), e->B("dalogit"), e->B("dha1"), e->B("dha0"),
+                    W("Wa0T"), W("Wa1T"), e->B("dca"))))
+    return rc;
+  head_final_bwd_kernel<<<grid1d(e, (long long)S * D, 128), 128, 0, st>>>(
+      e->B("dmo"), e->B("dca"), e->B("alpha"), e->B("afl"), e->B("afs"), e->B("hm"), e->B("hr"), e->d_len, e->counts,
+      e->cfg.contrastive_len_threshold, e->cfg.triplet_margin, e->cfg.contrastive_weight, H, D, G, S, e->B("dfs"),
+      e->B("dtgt"), e->B("dafl"), e->B("dafs"), e->B("dhm"), e->B("dhr"), e->acc);
+  POST("head_final_bwd");
+
+  // ---- short-term attention ----
+  Mlp& ms = e->mlp_short;
+  float *R = e->B("R"), *as = e->B("as"), *h0s = e->B("h0s"), *h1s = e->B("h1s"), *sti = e->B("sti");
+  float *dy1s = e->B("dy1s"), *dy0s = e->B("dy0s"), *dR = e->B("dR");
+  {
+    int wpb = 4;
+    size_t sm = (size_t)(5 * A1 + 3 * A1 + 1 + wpb * (2 * T + H)) * 4;
+    pool_bwd_kernel<<<grid1d(e, cdiv(S, wpb), 1, 8), 128, sm, st>>>(
+        e->B("dafs"), e->B("ws"), R, H, h1s, A1, ms.bn1.scale, ms.bn1.shift, ms.bn1.mean, ms.bn1.rstd, e->P + ms.wo,
+        e->d_len, S, T, G, dy1s, ms.bn1.stat_b, e->Pg + ms.wo, e->Pg + ms.bo, dR, 0, nullptr, nullptr,
+        e->cfg.contrastive_recent_k);
+    POST("pool_bwd_short");
+  }
+  if ((rc = bn_bwd(e, ms.bn1, (double)MB))) return rc;
+  {
+    EpiOp ep = e_store(dy0s, A0, nullptr, E_RELUMASK | E_STAT_XHAT);
+    ep.hpre = h0s; ep.ldh = A0; ep.scale = ms.bn0.scale; ep.shift = ms.bn0.shift; ep.mean = ms.bn0.mean;
+    ep.rstd = ms.bn0.rstd; ep.stat = ms.bn0.stat_b;
+    if ((rc = gemm(e, "dy0s", (int)MB, A0, A1, a_affine2(dy1s, h1s, A1, ms.bn1), W("W1sT"), A0, ep, true))) return rc;
+  }
+  if ((rc = dwgemm(e, "dW1s", (int)MB, A0, A1, a_bnrelu(h0s, A0, ms.bn0), a_affine2(dy1s, h1s, A1, ms.bn1),
+                   e->Pg + ms.w1, A1, nullptr)))
+    return rc;
+  if ((rc = bn_bwd(e, ms.bn0, (double)MB))) return rc;
+  {
+    int nx = ((A0 + 31) / 32) * 32;
+    dim3 blk(nx, 4);
+    h0_reduce_kernel<<<S, blk, (size_t)4 * A0 * 4, st>>>(dy0s, h0s, A0, ms.bn0.al, ms.bn0.be, ms.bn0.ga, T, G,
+                                                        e->B("dinvs"), e->B("dqbs"));
+    POST("h0_reduce_short");
+  }
+  AOp dh0s = a_affine2(dy0s, h0s, A0, ms.bn0);
+  if ((rc = gemm(e, "dP", (int)MB, D, A0, dh0s, W("Ws0tT"), D, e_store(e->B("dP"), D), false))) return rc;
+  if ((rc = dwgemm(e, "dWs0t", (int)MB, D, A0, a_mulrow(as, Q, U, tgt, D, T, G), dh0s, dW("Ws0t"), A0, nullptr))) return rc;
+  {
+    int nx = ((D + 31) / 32) * 32;
+    dim3 blk(nx, 4);
+    mulrow_bwd_kernel<<<S, blk, (size_t)4 * D * 4, st>>>(e->B("dP"), D, as, Q, U, tgt, D, T, G, e->B("da2"), e->B("dtgt"), D);
+    POST("mulrow_bwd");
+  }
+  if ((rc = gemm(e, "dFs", (int)M, Q + U, A0, a_plain(e->B("dinvs"), A0), W("Ws0iT"), Q + U, e_store(e->B("dFs"), Q + U), false)))
+    return rc;
+  if ((rc = dwgemm(e, "dWs0i", (int)M, Q + U, A0, a_catmul(as, Q, Q, 0, sti, U, T), a_plain(e->B("dinvs"), A0), dW("Ws0i"),
+                   A0, nullptr)))
+    return rc;
+  {
+    int nx = ((Q + 31) / 32) * 32;
+    dim3 blk(nx, 256 / nx > 0 ? 256 / nx : 1);
+    catmul_bwd_kernel<<<S, blk, (size_t)blk.y * U * 4, st>>>(e->B("dFs"), Q, U, as, Q, sti, U, e->B("da2"), D, U, T,
+                                                            e->B("das"), Q, e->B("dsti"), U);
+    POST("catmul_bwd_short");
+  }
+  if ((rc = gemm(e, "dqs", B, Q, A0, a_plain(e->B("dqbs"), A0), W("Ws0qT"), Q, e_store(e->B("dqs"), Q), false))) return rc;
+  if ((rc = dwgemm(e, "dWs0q", B, Q, A0, a_cat2row(sti, U, U, tgt, D, G), a_plain(e->B("dqbs"), A0), dW("Ws0q"), A0, nullptr)))
+    return rc;
+  qs_bwd_kernel<<<grid1d(e, (long long)S * Q, 256), 256, 0, st>>>(e->B("dqs"), U, D, G, S, e->B("dsti"), e->B("dtgt"));
+  POST("qs_bwd");
+  if ((rc = gemm(e, "dR", (int)M, H, Q, a_plain(e->B("das"), Q), W("WattsT"), H, e_store(dR, H, nullptr, E_ACCUM), false)))
+    return rc;
+  if ((rc = dwgemm(e, "dWatts", (int)M, H, Q, a_plain(R, H), a_plain(e->B("das"), Q), e->Pg + e->p_watts, Q, nullptr)))
+    return rc;
+
+  // ---- BPTT through the three recurrences ----
+  float *PX = e->B("PX"), *dPX = e->B("dPX");
+  CK(cudaMemsetAsync(dPX, 0, (size_t)M * NX * 4, st));
+  const int nblk = cdiv(S, RNN_NSEQ);
+  {
+    size_t sml = (size_t)(H * 4 * H + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
+    lstm_bwd_kernel<<<nblk, RNN_THREADS, sml, st>>>(PX, NX, e->oL, e->oTN, e->oTL, e->B("G4"), e->B("cp"), W("KmT"), dR,
+                                                    e->d_len, S, T, H, dPX);
+    POST("lstm_bwd");
+    size_t smg = (size_t)(2 * U * U + U * U + 5 * U * RNN_LD) * 4;
+    gru_bwd_kernel<<<nblk, RNN_THREADS, smg, st>>>(e->B("g1"), e->B("c1"), e->B("hp1"), W("Wgh1T"), W("Wch1T"), e->B("dsti"),
+                                                   e->d_len, S, T, U, dPX, NX, e->oG1, e->oC1, e->B("dus"));
+    POST("gru_bwd_sti");
+    size_t smg2 = (size_t)(2 * H * H + H * H + 5 * H * RNN_LD) * 4;
+    gru_bwd_kernel<<<nblk, RNN_THREADS, smg2, st>>>(e->B("g2"), e->B("c2"), e->B("hp2"), W("Wgh2T"), W("Wch2T"), e->B("dfs"),
+                                                    e->d_len, S, T, H, dPX, NX, e->oG2, e->oC2, nullptr);
+    POST("gru_bwd_causal2");
+  }
+  float *dX = e->B("dX"), *TNL = e->B("TNL"), *dTNL = e->B("dTNL");
+  if ((rc = gemm(e, "dX", (int)M, D, NX, a_plain(dPX, NX), W("Wx_allT"), D, e_store(dX, D), false))) return rc;
+  if ((rc = dwgemm(e, "dWx", (int)M, D, NX, a_plain(X, D), a_plain(dPX, NX), dW("Wx_all"), NX, dW("bx_all")))) return rc;
+  if ((rc = gemm(e, "dTNL", (int)M, 2 * H, 3 * H, a_plain(dPX + e->oO, NX), W("WtT"), 2 * H, e_store(dTNL, 2 * H), false)))
+    return rc;
+  if ((rc = dwgemm(e, "dWt", (int)M, 2 * H, 3 * H, a_plain(TNL, 2 * H), a_plain(dPX + e->oO, NX), dW("Wt"), 3 * H, nullptr)))
+    return rc;
+  {
+    int ppc = cdiv(M, (long long)e->num_sms * 4);
+    time_feat_bwd_kernel<<<cdiv(M, ppc), ((2 * H + 31) / 32) * 32, 0, st>>>(
+        dTNL, TNL, c.ttn, c.tfa, c.seq_stride, T, H, M, ppc, e->Pg + e->p_tw1, e->Pg + e->p_tb1, e->Pg + e->p_tw2,
+        e->Pg + e->p_tb2);
+    POST("time_feat_bwd");
+  }
+  if ((rc = dwgemm(e, "dWgh1", (int)M, U, 2 * U, a_plain(e->B("hp1"), U), a_plain(dPX + e->oG1, NX), dW("Wgh1"), 2 * U, nullptr))) return rc;
+  if ((rc = dwgemm(e, "dWch1", (int)M, U, U, a_plain(e->B("rh1"), U), a_plain(dPX + e->oC1, NX), dW("Wch1"), U, nullptr))) return rc;
+  if ((rc = dwgemm(e, "dWgh2", (int)M, H, 2 * H, a_plain(e->B("hp2"), H), a_plain(dPX + e->oG2, NX), dW("Wgh2"), 2 * H, nullptr))) return rc;
+  if ((rc = dwgemm(e, "dWch2", (int)M, H, H, a_plain(e->B("rh2"), H), a_plain(dPX + e->oC2, NX), dW("Wch2"), H, nullptr))) return rc;
+  if ((rc = dwgemm(e, "dKm", (int)M, H, 4 * H, a_plain(e->B("mp"), H), a_plain(dPX + e->oL, NX), dW("Km"), 4 * H, nullptr))) return rc;
+
+  // ---- long-term attention ----
+  Mlp& ml = e->mlp_long;
+  float *al = e->B("al"), *ul = e->B("ul"), *h0l = e->B("h0l"), *h1l = e->B("h1l");
+  float *dy1l = e->B("dy1l"), *dy0l = e->B("dy0l");
+  {
+    int wpb = 4;
+    size_t sm = (size_t)(5 * A1 + 3 * A1 + 1 + wpb * (2 * T + D)) * 4;
+    pool_bwd_kernel<<<grid1d(e, cdiv(S, wpb), 1, 8), 128, sm, st>>>(
+        e->B("dafl"), e->B("wl"), X, D, h1l, A1, ml.bn1.scale, ml.bn1.shift, ml.bn1.mean, ml.bn1.rstd, e->P + ml.wo,
+        e->d_len, S, T, 1, dy1l, ml.bn1.stat_b, e->Pg + ml.wo, e->Pg + ml.bo, dX, 1, e->B("dhm"), e->B("dhr"),
+        e->cfg.contrastive_recent_k);
+    POST("pool_bwd_long");
+  }
+  if ((rc = bn_bwd(e, ml.bn1, (double)M))) return rc;
+  {
+    EpiOp ep = e_store(dy0l, A0, nullptr, E_RELUMASK | E_STAT_XHAT);
+    ep.hpre = h0l; ep.ldh = A0; ep.scale = ml.bn0.scale; ep.shift = ml.bn0.shift; ep.mean = ml.bn0.mean;
+    ep.rstd = ml.bn0.rstd; ep.stat = ml.bn0.stat_b;
+    if ((rc = gemm(e, "dy0l", (int)M, A0, A1, a_affine2(dy1l, h1l, A1, ml.bn1), W("W1lT"), A0, ep, true))) return rc;
+  }
+  if ((rc = dwgemm(e, "dW1l", (int)M, A0, A1, a_bnrelu(h0l, A0, ml.bn0), a_affine2(dy1l, h1l, A1, ml.bn1),
+                   e->Pg + ml.w1, A1, nullptr)))
+    return rc;
+  if ((rc = bn_bwd(e, ml.bn0, (double)M))) return rc;
+  {
+    int nx = ((A0 + 31) / 32) * 32;
+    dim3 blk(nx, 4);
+    h0_reduce_kernel<<<S, blk, (size_t)4 * A0 * 4, st>>>(dy0l, h0l, A0, ml.bn0.al, ml.bn0.be, ml.bn0.ga, T, 1, nullptr,
+                                                        e->B("dqbl"));
+    POST("h0_reduce_long");
+  }
+  AOp dh0l = a_affine2(dy0l, h0l, A0, ml.bn0);
+  if ((rc = gemm(e, "dFl", (int)M, 2 * U, A0, dh0l, W("Wl0T"), 2 * U, e_store(e->B("dFl"), 2 * U), false))) return rc;
+  if ((rc = dwgemm(e, "dWl0", (int)M, 2 * U, A0, a_catmul(al, U, U, 0, ul, U, T), dh0l, dW("Wl0"), A0, nullptr))) return rc;
+  {
+    int nx = ((U + 31) / 32) * 32;
+    dim3 blk(nx, 256 / nx > 0 ? 256 / nx : 1);
+    catmul_bwd_kernel<<<S, blk, (size_t)blk.y * U * 4, st>>>(e->B("dFl"), U, U, al, U, ul, U, nullptr, 0, 0, T, e->B("dal"),
+                                                            U, e->B("dul"), U);
+    POST("catmul_bwd_long");
+  }
+  if ((rc = gemm(e, "dul", S, U, A0, a_plain(e->B("dqbl"), A0), W("Wl0qT"), U, e_store(e->B("dul"), U, nullptr, E_ACCUM), false)))
+    return rc;
+  if ((rc = dwgemm(e, "dWl0q", S, U, A0, a_plain(ul, U), a_plain(e->B("dqbl"), A0), dW("Wl0q"), A0, nullptr))) return rc;
+  if ((rc = gemm(e, "dX_al", (int)M, D, U, a_plain(e->B("dal"), U), W("WattlT"), D, e_store(dX, D, nullptr, E_ACCUM), false)))
+    return rc;
+  if ((rc = dwgemm(e, "dWattl", (int)M, D, U, a_plain(X, D), a_plain(e->B("dal"), U), e->Pg + e->p_wattl, U, nullptr)))
+    return rc;
+  (void)Di; (void)Dc; (void)CA;
+  return 0;
+}
+
+// K2 + K13: unique ids per table and scatter-add of every slice gradient into compact rows.
+int sparse_grads(clsr_engine* e, const StepCtx& c) {
+  const int B = c.B, S = c.S, T = c.T, U = e->U, D = e->D, Di = e->Di, Dc = e->Dc;
+  const long long M = (long long)S * T;
+  cudaStream_t st = e->stream;
+  mark_unique_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(c.ih, M, T, c.seq_stride, e->slot[0], e->uniq[0], e->counts + 1);
+  POST("unique_item_hist");
+  mark_unique_kernel<<<grid1d(e, B, 256), 256, 0, st>>>(c.items, B, 1, 1, e->slot[0], e->uniq[0], e->counts + 1);
+  POST("unique_item_tgt");
+  mark_unique_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(c.ch, M, T, c.seq_stride, e->slot[1], e->uniq[1], e->counts + 2);
+  POST("unique_cate_hist");
+  mark_unique_kernel<<<grid1d(e, B, 256), 256, 0, st>>>(c.cates, B, 1, 1, e->slot[1], e->uniq[1], e->counts + 2);
+  POST("unique_cate_tgt");
+  mark_unique_kernel<<<grid1d(e, S, 256), 256, 0, st>>>(c.users, S, 1, c.user_stride, e->slot[2], e->uniq[2], e->counts + 3);
+  POST("unique_users");
+  const int cnt_ix[4] = {1, 2, 3, 3};
+  for (int t = 0; t < 4; ++t) {
+    zero_compact_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->cg[t], e->counts + cnt_ix[t], e->tab_dim[t]);
+    POST("zero_compact");
+  }
+  scatter_hist_kernel<<<e->num_sms * 4, 256, (size_t)D * 4, st>>>(e->B("dX"), c.ih, c.ch, c.seq_stride, T, e->slot[0], e->slot[1],
+                                                                e->cg[0], e->cg[1], Di, Dc, M, e->sumsq);
+  POST("scatter_hist");
+  scatter_rows_kernel<<<grid1d(e, (long long)B * Di / 4, 256), 256, 0, st>>>(e->B("dtgt"), D, 0, Di, c.items, 1, e->slot[0],
+                                                                           e->cg[0], B, e->sumsq + 0);
+  POST("scatter_tgt_item");
+  scatter_rows_kernel<<<grid1d(e, (long long)B * Dc / 4, 256), 256, 0, st>>>(e->B("dtgt"), D, Di, Dc, c.cates, 1, e->slot[1],
+                                                                           e->cg[1], B, e->sumsq + 1);
+  POST("scatter_tgt_cate");
+  scatter_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(e->B("dul"), U, 0, U, c.users, c.user_stride,
+                                                                          e->slot[2], e->cg[2], S, e->sumsq + 2);
+  POST("scatter_ul");
+  scatter_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(e->B("dus"), U, 0, U, c.users, c.user_stride,
+                                                                          e->slot[2], e->cg[3], S, e->sumsq + 3);
+  POST("scatter_us");
+  const float l2 = e->cfg.embed_l2, dw = e->cfg.discrepancy_weight;
+  involved_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[0], nullptr, Di, e->uniq[0], e->counts + 1, e->cg[0], l2, 0.f, 0,
+                                                  e->sumsq + 0, e->acc + 5);
+  POST("involved_item");
+  involved_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[1], nullptr, Dc, e->uniq[1], e->counts + 2, e->cg[1], l2, 0.f, 0,
+                                                  e->sumsq + 1, e->acc + 6);
+  POST("involved_cate");
+  // acc[7] = long rows^2, acc[8] = short rows^2, acc[9] = sum (long-short)^2 (written by the
+  // short-table call only: its acc base is acc+8, its discrepancy slot acc+8+1).
+  involved_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[2], e->tab[3], U, e->uniq[2], e->counts + 3, e->cg[2], l2, dw, 0,
+                                                  e->sumsq + 2, e->acc + 7);
+  POST("involved_ul");
+  involved_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[3], e->tab[2], U, e->uniq[2], e->counts + 3, e->cg[3], l2, dw, 1,
+                                                  e->sumsq + 3, e->acc + 8);
+  POST("involved_us");
+  return 0;
+}
+
+int optimizer_step(clsr_engine* e) {
+  cudaStream_t st = e->stream;
+  const clsr_config& cf = e->cfg;
+  e->adam_step += 1;
+  double t = (double)e->adam_step;
+  float lr_t = (float)(cf.learning_rate * sqrt(1.0 - pow((double)cf.beta2, t)) / (1.0 - pow((double)cf.beta1, t)));
+  AdamDense hd = {lr_t, cf.beta1, cf.beta2, cf.adam_eps, cf.clip_norm ? cf.max_grad_norm : 0.f};
+  dense_adam_kernel<<<(int)e->dense.size(), 256, 0, st>>>(e->d_vars, e->P, e->Pm, e->Pv, e->Pg, e->d_norms, hd);
+  POST("dense_adam");
+  AdamHyper hp = {lr_t, cf.beta1, cf.beta2, cf.adam_eps, cf.clip_norm ? cf.max_grad_norm : 0.f};
+  const int slot_ix[4] = {0, 1, 2, 2}, cnt_ix[4] = {1, 2, 3, 3};
+  for (int tb = 0; tb < 4; ++tb) {
+    if (!e->tab_m[tb] || !e->tab_v[tb]) return fail(e, CLSR_ERR_STATE, "Adam slots of table %d not bound", tb);
+    if (cf.optimizer == 1) {
+      adam_lazy_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[tb], e->tab_m[tb], e->tab_v[tb], e->uniq[slot_ix[tb]],
+                                                       e->counts + cnt_ix[tb], e->cg[tb], e->tab_dim[tb], hp, e->sumsq + tb);
+      POST("adam_lazy");
+    } else {
+      adam_sweep_kernel<<<e->num_sms * 8, 256, 0, st>>>(e->tab[tb], e->tab_m[tb], e->tab_v[tb], e->slot[slot_ix[tb]],
+                                                        e->cg[tb], e->tab_dim[tb], e->tab_rows[tb], hp, e->sumsq + tb);
+      POST("adam_sweep");
+    }
+  }
+  return 0;
+}
+
+int reset_slots(clsr_engine* e) {
+  for (int i = 0; i < 3; ++i) {
+    reset_slots_kernel<<<e->num_sms, 256, 0, e->stream>>>(e->uniq[i], e->counts + 1 + i, e->slot[i]);
+    POST("reset_slots");
+  }
+  return 0;
+}
+
+int zero_step_state(clsr_engine* e) {
+  CK(cudaMemsetAsync(e->counts, 0, 8 * sizeof(int32_t), e->stream));
+  CK(cudaMemsetAsync(e->sumsq, 0, 4 * sizeof(double), e->stream));
+  CK(cudaMemsetAsync(e->acc, 0, 16 * sizeof(double), e->stream));
+  CK(cudaMemsetAsync(e->Pg, 0, (size_t)e->Ptot * 4, e->stream));
+  CK(cudaMemsetAsync(e->dWd, 0, (size_t)e->Wtot * 4, e->stream));
+  Mlp* ms[4] = {&e->mlp_long, &e->mlp_short, &e->mlp_alpha, &e->mlp_logit};
+  for (Mlp* m : ms) {
+    BnLayer* bl[2] = {&m->bn0, &m->bn1};
+    for (BnLayer* b : bl) {
+      CK(cudaMemsetAsync(b->stat_f, 0, 2 * b->N * sizeof(double), e->stream));
+      CK(cudaMemsetAsync(b->stat_b, 0, 2 * b->N * sizeof(double), e->stream));
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* clsr_last_error(const clsr_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int clsr_create(const clsr_config* cfg, clsr_engine** out) {
+  clsr_engine* e = nullptr;
+  if (!cfg || !out) return fail(e, CLSR_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->hidden != cfg->item_dim + cfg->cate_dim)
+    return fail(e, CLSR_ERR_ARG, "hidden (%d) must equal item_dim + cate_dim (%d)", cfg->hidden, cfg->item_dim + cfg->cate_dim);
+  if (cfg->item_dim % 4 || cfg->cate_dim % 4 || cfg->user_dim % 4)
+    return fail(e, CLSR_ERR_ARG, "embedding dims must be multiples of 4 (16-byte rows)");
+  if (cfg->max_rows <= 0 || cfg->seq_len <= 0 || cfg->train_group <= 0) return fail(e, CLSR_ERR_ARG, "bad sizes");
+  if (cfg->att1 > 128) return fail(e, CLSR_ERR_ARG, "att_fcn_layer_sizes[1] > 128 unsupported");
+  if (cfg->contrastive_kind != 0) return fail(e, CLSR_ERR_ARG, "only the triplet contrastive loss is implemented");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(e, CLSR_ERR_CUDA, "no CUDA device: clsr_b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(e, CLSR_ERR_ARG, "bad device %d", cfg->device);
+  e = new clsr_engine();
+  e->cfg = *cfg;
+#define CKC(call)                                                                  \
+  do {                                                                             \
+    int _rc = (call);                                                              \
+    if (_rc) { g_create_error = e->err; clsr_destroy(e); return _rc; }             \
+  } while (0)
+#define CKCU(call)                                                                                       \
+  do {                                                                                                   \
+    cudaError_t _c = (call);                                                                             \
+    if (_c != cudaSuccess) {                                                                             \
+      fail(nullptr, CLSR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_c));                      \
+      clsr_destroy(e);                                                                                   \
+      return CLSR_ERR_CUDA;                                                                              \
+    }                                                                                                    \
+  } while (0)
+  CKCU(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CKCU(cudaGetDeviceProperties(&prop, cfg->device));
+  e->num_sms = prop.multiProcessorCount;
+  CKCU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->own_stream = true;
+
+  e->T = cfg->seq_len; e->Di = cfg->item_dim; e->Dc = cfg->cate_dim; e->D = e->Di + e->Dc; e->U = cfg->user_dim;
+  e->H = cfg->hidden; e->Q = e->U + e->D; e->A0 = cfg->att0; e->A1 = cfg->att1; e->L0 = cfg->fc0; e->L1 = cfg->fc1;
+  e->CA = 2 * e->H + 2 * e->D + 1;
+  const int U = e->U, H = e->H, D = e->D, T = e->T;
+  e->oG1 = 0; e->oC1 = 2 * U; e->oG2 = 3 * U; e->oC2 = 3 * U + 2 * H; e->oL = 3 * U + 3 * H;
+  e->oO = e->oL + 3 * H; e->oTN = e->oL + 4 * H; e->oTL = e->oL + 5 * H; e->NX = e->oL + 6 * H;
+  e->Bmax = cfg->max_rows;
+  e->Smax = cfg->max_rows;  // group = 1 must always fit
+  e->tab_rows[0] = cfg->n_items; e->tab_rows[1] = cfg->n_cates; e->tab_rows[2] = cfg->n_users; e->tab_rows[3] = cfg->n_users;
+  e->tab_dim[0] = e->Di; e->tab_dim[1] = e->Dc; e->tab_dim[2] = U; e->tab_dim[3] = U;
+
+  {
+    size_t sml = (size_t)(H * 4 * H + 6 * H * RNN_LD) * 4;
+    size_t smg = (size_t)(3 * (U > H ? U : H) * (U > H ? U : H) + 5 * (U > H ? U : H) * RNN_LD) * 4;
+    size_t smax = sml > smg ? sml : smg;
+    if (smax > (size_t)prop.sharedMemPerBlockOptin) {
+      fail(nullptr, CLSR_ERR_ARG, "hidden size %d needs %zu B of shared memory for resident recurrent weights (max %zu)",
+           H, smax, (size_t)prop.sharedMemPerBlockOptin);
+      clsr_destroy(e);
+      return CLSR_ERR_ARG;
+    }
+    CKCU(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml));
+    CKCU(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml));
+    CKCU(cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
+    CKCU(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
+    size_t smp = (size_t)(8 * e->A1 + 1 + 4 * (2 * T + D)) * 4;
+    CKCU(cudaFuncSetAttribute(pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smp > 49152 ? smp : 49152)));
+    size_t smf = (size_t)(3 * e->A1 + 4 * T) * 4;
+    CKCU(cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smf > 49152 ? smf : 49152)));
+  }
+
+  build_inventory(e);
+  CKC(dalloc(e, &e->P, e->Ptot));
+  CKC(dalloc(e, &e->Pm, e->Ptot));
+  CKC(dalloc(e, &e->Pv, e->Ptot));
+  CKC(dalloc(e, &e->Pg, e->Ptot));
+  {
+    std::vector<DenseVar> dv;
+    for (auto& d : e->dense) dv.push_back(DenseVar{d.off, (int)d.n, d.trainable});
+    CKC(dalloc(e, &e->d_vars, (long long)dv.size(), false));
+    CKCU(cudaMemcpy(e->d_vars, dv.data(), dv.size() * sizeof(DenseVar), cudaMemcpyHostToDevice));
+    CKC(dalloc(e, &e->d_norms, (long long)dv.size()));
+  }
+  CKC(build_weight_maps(e));
+  Mlp* mls[4] = {&e->mlp_long, &e->mlp_short, &e->mlp_alpha, &e->mlp_logit};
+  for (Mlp* m : mls) { CKC(alloc_bn(e, &m->bn0)); CKC(alloc_bn(e, &m->bn1)); }
+
+  // slot tables and compact gradient rows
+  const long long Bm = e->Bmax, Sm = e->Smax, M = Sm * T, MB = Bm * T;
+  const long long rows3[3] = {cfg->n_items, cfg->n_cates, cfg->n_users};
+  e->uniq_cap[0] = M + Bm; e->uniq_cap[1] = M + Bm; e->uniq_cap[2] = Sm;
+  for (int i = 0; i < 3; ++i) {
+    if (e->uniq_cap[i] > rows3[i]) e->uniq_cap[i] = rows3[i];
+    CKC(dalloc(e, &e->slot[i], rows3[i], false));
+    CKCU(cudaMemset(e->slot[i], 0xFF, (size_t)rows3[i] * 4));
+    CKC(dalloc(e, &e->uniq[i], e->uniq_cap[i]));
+  }
+  CKC(dalloc(e, &e->cg[0], e->uniq_cap[0] * e->Di));
+  CKC(dalloc(e, &e->cg[1], e->uniq_cap[1] * e->Dc));
+  CKC(dalloc(e, &e->cg[2], e->uniq_cap[2] * U));
+  CKC(dalloc(e, &e->cg[3], e->uniq_cap[2] * U));
+  CKC(dalloc(e, &e->counts, 8));
+  CKC(dalloc(e, &e->sumsq, 4));
+  CKC(dalloc(e, &e->acc, 16));
+  CKC(dalloc(e, &e->d_losses, 8));
+  CKCU(cudaMallocHost((void**)&e->h_losses, 8 * sizeof(float)));
+  CKCU(cudaMallocHost((void**)&e->h_out, (size_t)2 * Bm * sizeof(float)));
+
+  // staged inputs: one contiguous block [ih | ch | mask | tfa | ttn | users | items | cates | labels]
+  {
+    size_t bytes = (size_t)5 * M * 4 + (size_t)Sm * 4 + (size_t)Bm * 4 * 3;
+    char* blk = nullptr;
+    CKC(dalloc(e, &blk, (long long)bytes));
+    e->in_ih = (int32_t*)blk;
+    e->h_stage_bytes = bytes;
+    CKCU(cudaMallocHost((void**)&e->h_stage, bytes));
+    CKC(dalloc(e, &e->d_len, Sm));
+  }
+
+  // activations
+  const int A0 = e->A0, A1 = e->A1, Q = e->Q, NX = e->NX, CA = e->CA, L0 = e->L0, L1 = e->L1;
+  struct { const char* n; long long sz; } specs[] = {
+      {"X", M * D}, {"TNL", M * 2 * H}, {"PX", M * NX}, {"dPX", M * NX},
+      {"g1", M * 2 * U}, {"c1", M * U}, {"hp1", M * U}, {"rh1", M * U},
+      {"g2", M * 2 * H}, {"c2", M * H}, {"hp2", M * H}, {"rh2", M * H},
+      {"G4", M * 4 * H}, {"cp", M * H}, {"mp", M * H}, {"R", M * H},
+      {"al", M * U}, {"h0l", M * A0}, {"h1l", M * A1}, {"wl", M}, {"dy1l", M * A1}, {"dy0l", M * A0},
+      {"dFl", M * 2 * U}, {"dal", M * U},
+      {"as", M * Q}, {"invs", M * A0}, {"dinvs", M * A0}, {"dFs", M * (Q + U)}, {"da2", M * D}, {"das", M * Q},
+      {"dR", M * H}, {"dTNL", M * 2 * H}, {"dX", M * D},
+      {"h0s", MB * A0}, {"h1s", MB * A1}, {"dy1s", MB * A1}, {"dy0s", MB * A0}, {"dP", MB * D}, {"ws", MB},
+      {"tgt", Bm * D}, {"ul", Sm * U}, {"us", Sm * U}, {"sti", Sm * U}, {"fs", Sm * H}, {"afl", Sm * D},
+      {"hm", Sm * D}, {"hr", Sm * D}, {"afs", Bm * H}, {"qbl", Sm * A0}, {"qbs", Bm * A0}, {"ca", Bm * CA},
+      {"ha0", Bm * A0}, {"ha1", Bm * A1}, {"alogit", Bm}, {"alpha", Bm}, {"mo", Bm * (H + D)}, {"hl0", Bm * L0},
+      {"hl1", Bm * L1}, {"logit", Bm}, {"pred", Bm}, {"dlogit", Bm}, {"dhl1", Bm * L1}, {"dhl0", Bm * L0},
+      {"dmo", Bm * (H + D)}, {"dalogit", Bm}, {"dha1", Bm * A1}, {"dha0", Bm * A0}, {"dca", Bm * CA},
+      {"dfs", Sm * H}, {"dtgt", Bm * D}, {"dafl", Sm * D}, {"dafs", Bm * H}, {"dhm", Sm * D}, {"dhr", Sm * D},
+      {"dsti", Sm * U}, {"dus", Sm * U}, {"dul", Sm * U}, {"dqbs", Bm * A0}, {"dqs", Bm * Q}, {"dqbl", Sm * A0},
+  };
+  for (auto& s : specs) CKC(fbuf(e, s.n, s.sz));
+  CKCU(cudaDeviceSynchronize());
+  *out = e;
+  return CLSR_OK;
+}
+
+void clsr_destroy(clsr_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->h_losses) cudaFreeHost(e->h_losses);
+  if (e->h_out) cudaFreeHost(e->h_out);
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int clsr_set_stream(clsr_engine* e, void* s) {
+  if (!e) return CLSR_ERR_ARG;
+  if (e->own_stream && e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+  e->stream = (cudaStream_t)s;
+  e->own_stream = false;
+  return CLSR_OK;
+}
+
+int64_t clsr_workspace_bytes(const clsr_engine* e) { return e ? e->ws_bytes : 0; }
+int32_t clsr_dense_count(const clsr_engine* e) { return e ? (int32_t)e->dense.size() : 0; }
+const char* clsr_dense_name(const clsr_engine* e, int32_t i) {
+  return (e && i >= 0 && i < (int)e->dense.size()) ? e->dense[i].name.c_str() : nullptr;
+}
+int64_t clsr_dense_offset(const clsr_engine* e, int32_t i) {
+  return (e && i >= 0 && i < (int)e->dense.size()) ? e->dense[i].off : -1;
+}
+int64_t clsr_dense_numel(const clsr_engine* e, int32_t i) {
+  return (e && i >= 0 && i < (int)e->dense.size()) ? e->dense[i].n : -1;
+}
+int32_t clsr_dense_trainable(const clsr_engine* e, int32_t i) {
+  return (e && i >= 0 && i < (int)e->dense.size()) ? e->dense[i].trainable : 0;
+}
+int64_t clsr_dense_total(const clsr_engine* e) { return e ? e->Ptot : 0; }
+
+static float* dense_which(clsr_engine* e, int which) {
+  switch (which) {
+    case 0: return e->P;
+    case 1: return e->Pm;
+    case 2: return e->Pv;
+    case 3: return e->Pg;
+  }
+  return nullptr;
+}
+int clsr_dense_read(clsr_engine* e, int32_t which, float* host_dst) {
+  if (!e || !host_dst || !dense_which(e, which)) return fail(e, CLSR_ERR_ARG, "bad argument");
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(host_dst, dense_which(e, which), (size_t)e->Ptot * 4, cudaMemcpyDeviceToHost));
+  return CLSR_OK;
+}
+int clsr_dense_write(clsr_engine* e, int32_t which, const float* host_src) {
+  if (!e || !host_src || !dense_which(e, which)) return fail(e, CLSR_ERR_ARG, "bad argument");
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(dense_which(e, which), host_src, (size_t)e->Ptot * 4, cudaMemcpyHostToDevice));
+  return CLSR_OK;
+}
+
+int clsr_bind_table(clsr_engine* e, int32_t t, float* values, float* m, float* v) {
+  if (!e || t < 0 || t >= CLSR_NUM_TABLES || !values) return fail(e, CLSR_ERR_ARG, "bad table binding");
+  if (((uintptr_t)values | (uintptr_t)m | (uintptr_t)v) & 15) return fail(e, CLSR_ERR_ARG, "table pointers must be 16-byte aligned");
+  e->tab[t] = values; e->tab_m[t] = m; e->tab_v[t] = v;
+  return CLSR_OK;
+}
+int clsr_set_adam_step(clsr_engine* e, int64_t s) { if (!e) return CLSR_ERR_ARG; e->adam_step = s; return CLSR_OK; }
+int64_t clsr_get_adam_step(const clsr_engine* e) { return e ? e->adam_step : -1; }
+int clsr_set_debug_sync(clsr_engine* e, int32_t on) { if (!e) return CLSR_ERR_ARG; e->debug_sync = on != 0; return CLSR_OK; }
+int64_t clsr_kernel_launches(const clsr_engine* e) { return e ? e->launches : 0; }
+
+int clsr_synchronize(clsr_engine* e) {
+  if (!e) return CLSR_ERR_ARG;
+  CK(cudaStreamSynchronize(e->stream));
+  return CLSR_OK;
+}
+
+int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, clsr_losses* out) {
+  if (!e) return CLSR_ERR_ARG;
+  int rc;
+  CK(cudaSetDevice(e->cfg.device));
+  if ((rc = check_batch(e, batch, true))) return rc;
+  e->launches = 0;
+  StepCtx c;
+  if ((rc = stage_inputs(e, batch, &c, true))) return rc;
+  if ((rc = zero_step_state(e))) return rc;
+  if ((rc = forward(e, c, 1, (flags & CLSR_STEP_NO_BN_UPDATE) ? 0 : 1))) return rc;
+  if ((rc = backward(e, c))) return rc;
+  if ((rc = sparse_grads(e, c))) return rc;
+  blockop_kernel<<<e->n_unprep, 256, 0, e->stream>>>(e->ops_unprep, e->Pg, e->dWd);
+  POST("unprep_grads");
+  dense_l2_norm_kernel<<<(int)e->dense.size(), 256, 0, e->stream>>>(e->d_vars, e->P, e->Pg, e->cfg.layer_l2, e->d_norms, e->acc);
+  POST("dense_l2_norm");
+  loss_finalize_kernel<<<1, 32, 0, e->stream>>>(e->acc, e->counts, e->counts + 3, c.G, e->U, e->cfg.embed_l2,
+                                                e->cfg.contrastive_weight, e->cfg.discrepancy_weight, e->d_losses);
+  POST("loss_finalize");
+  if (!(flags & CLSR_STEP_NO_OPTIMIZER)) {
+    if ((rc = optimizer_step(e))) return rc;
+  }
+  if ((rc = reset_slots(e))) return rc;
+  CK(cudaMemcpyAsync(e->h_losses, e->d_losses, 5 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  if (out) {
+    CK(cudaStreamSynchronize(e->stream));
+    out->loss = e->h_losses[0]; out->data_loss = e->h_losses[1]; out->regular_loss = e->h_losses[2];
+    out->contrastive_loss = e->h_losses[3]; out->discrepancy_loss = e->h_losses[4];
+  }
+  return CLSR_OK;
+}
+
+int clsr_predict(clsr_engine* e, const clsr_batch* batch, float* pred, float* alpha) {
+  if (!e) return CLSR_ERR_ARG;
+  int rc;
+  CK(cudaSetDevice(e->cfg.device));
+  if ((rc = check_batch(e, batch, false))) return rc;
+  if (!pred) return fail(e, CLSR_ERR_ARG, "null pred buffer");
+  e->launches = 0;
+  StepCtx c;
+  if ((rc = stage_inputs(e, batch, &c, false))) return rc;
+  CK(cudaMemsetAsync(e->counts, 0, 8 * sizeof(int32_t), e->stream));
+  if ((rc = forward(e, c, 0, 0))) return rc;
+  const int B = c.B;
+  sigmoid_kernel<<<grid1d(e, B, 256), 256, 0, e->stream>>>(e->B("logit"), B, e->B("pred"));
+  POST("sigmoid");
+  CK(cudaMemcpyAsync(e->h_out, e->B("pred"), (size_t)B * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (alpha) CK(cudaMemcpyAsync(e->h_out + e->Bmax, e->B("alpha"), (size_t)B * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  memcpy(pred, e->h_out, (size_t)B * 4);
+  if (alpha) memcpy(alpha, e->h_out + e->Bmax, (size_t)B * 4);
+  return CLSR_OK;
+}
+
+int clsr_gather_history(clsr_engine* e, const int32_t* ih, const int32_t* ch, int64_t positions, float* out) {
+  if (!e || !ih || !ch || !out || positions <= 0) return fail(e, CLSR_ERR_ARG, "bad argument");
+  if (!e->tab[0] || !e->tab[1]) return fail(e, CLSR_ERR_STATE, "tables not bound");
+  long long nvec = positions * (e->D / 4);
+  gather_hist_kernel<4><<<grid1d(e, cdiv(nvec, 4), 256, 8), 256, 0, e->stream>>>(
+      ih, ch, e->T, e->T, e->tab[0], e->tab[1], e->Di, e->Dc, out, positions);
+  POST("gather_hist");
+  return CLSR_OK;
+}
+
+int clsr_scatter_history_grad(clsr_engine* e, const int32_t* ih, const int32_t* ch, int64_t positions, const float* d_hist) {
+  if (!e || !ih || !ch || !d_hist || positions <= 0) return fail(e, CLSR_ERR_ARG, "bad argument");
+  if (positions > e->uniq_cap[0] && e->uniq_cap[0] < e->tab_rows[0]) return fail(e, CLSR_ERR_ARG, "too many positions");
+  cudaStream_t st = e->stream;
+  CK(cudaMemsetAsync(e->counts, 0, 8 * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(e->sumsq, 0, 4 * sizeof(double), st));
+  mark_unique_kernel<<<grid1d(e, positions, 256), 256, 0, st>>>(ih, positions, e->T, e->T, e->slot[0], e->uniq[0], e->counts + 1);
+  POST("unique_item_hist");
+  mark_unique_kernel<<<grid1d(e, positions, 256), 256, 0, st>>>(ch, positions, e->T, e->T, e->slot[1], e->uniq[1], e->counts + 2);
+  POST("unique_cate_hist");
+  zero_compact_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->cg[0], e->counts + 1, e->Di);
+  POST("zero_compact");
+  zero_compact_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->cg[1], e->counts + 2, e->Dc);
+  POST("zero_compact");
+  scatter_hist_kernel<<<e->num_sms * 4, 256, (size_t)e->D * 4, st>>>(d_hist, ih, ch, e->T, e->T, e->slot[0], e->slot[1], e->cg[0],
+                                                                  e->cg[1], e->Di, e->Dc, positions, e->sumsq);
+  POST("scatter_hist");
+  for (int i = 0; i < 2; ++i) {
+    reset_slots_kernel<<<e->num_sms, 256, 0, st>>>(e->uniq[i], e->counts + 1 + i, e->slot[i]);
+    POST("reset_slots");
+  }
+  return CLSR_OK;
+}
+
+int clsr_sparse_grad_view(clsr_engine* e, int32_t t, const int32_t** ids, const float** rows, const int32_t** count) {
+  if (!e || t < 0 || t >= CLSR_NUM_TABLES) return fail(e, CLSR_ERR_ARG, "bad table");
+  const int slot_ix[4] = {0, 1, 2, 2}, cnt_ix[4] = {1, 2, 3, 3};
+  if (ids) *ids = e->uniq[slot_ix[t]];
+  if (rows) *rows = e->cg[t];
+  if (count) *count = e->counts + cnt_ix[t];
+  return CLSR_OK;
+}
+
+int clsr_debug_buffer(clsr_engine* e, const char* name, const float** p, int64_t* n) {
+  if (!e || !name) return CLSR_ERR_ARG;
+  auto it = e->bufs.find(name);
+  if (it != e->bufs.end()) {
+    if (p) *p = it->second.first;
+    if (n) *n = it->second.second;
+    return CLSR_OK;
+  }
+  auto wi = e->wd_off.find(name);
+  if (wi != e->wd_off.end()) {
+    if (p) *p = e->Wd + wi->second;
+    if (n) *n = e->Wtot - wi->second;
+    return CLSR_OK;
+  }
+  return fail(e, CLSR_ERR_ARG, "no buffer named %s", name);
+}
+
+int clsr_debug_read(clsr_engine* e, const void* src, void* dst, int64_t bytes) {
+  if (!e || !src || !dst || bytes < 0) return fail(e, CLSR_ERR_ARG, "bad argument");
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+  return CLSR_OK;
+}
+
+int clsr_nccl_unique_id(void* out128) { (void)out128; return CLSR_ERR_NCCL; }
+int clsr_comm_init(clsr_engine* e, int32_t rank, int32_t world, const void* id128) {
+  (void)rank; (void)world; (void)id128;
+  return fail(e, CLSR_ERR_NCCL, "multi-GPU support is not built into this library yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+/* clsr_b200 -- C ABI of the B200-native CLSR training/inference step.
+ *
+ * The reference has no FFI of its own: its one process/device boundary is
+ * `sess.run(fetches, feed_dict)` issued from
+ *   reco_utils/recommender/deeprec/models/sequential/clsr.py:383-408        (train)
+ *   reco_utils/recommender/deeprec/models/base_model.py:366-392             (eval / infer)
+ *   reco_utils/recommender/deeprec/models/sequential/sequential_base_model.py:294-324
+ *                                                       (eval_with_user[_and_alpha])
+ * Each entry point below names the sess.run it replaces.  Conventions: every call
+ * returns 0 on success or a negative clsr_status; the message is available from
+ * clsr_last_error(); no exceptions cross the boundary; all device work is enqueued on
+ * the engine's stream; an engine is used from one host thread at a time.
+ */
+#ifndef CLSR_B200_H
+#define CLSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct clsr_engine clsr_engine;
+
+enum clsr_status {
+  CLSR_OK = 0,
+  CLSR_ERR_ARG = -1,     /* bad argument / unsupported configuration */
+  CLSR_ERR_CUDA = -2,    /* a CUDA runtime call or kernel failed */
+  CLSR_ERR_STATE = -3,   /* call sequence error (e.g. tables not bound) */
+  CLSR_ERR_NCCL = -4
+};
+
+enum clsr_table {
+  CLSR_TABLE_ITEM = 0,        /* sequential/embedding/item_embedding        [n_items, item_dim] */
+  CLSR_TABLE_CATE = 1,        /* sequential/embedding/cate_embedding        [n_cates, cate_dim] */
+  CLSR_TABLE_USER_LONG = 2,   /* sequential/embedding/user_long_embedding   [n_users, user_dim] */
+  CLSR_TABLE_USER_SHORT = 3,  /* sequential/embedding/user_short_embedding  [n_users, user_dim] */
+  CLSR_NUM_TABLES = 4
+};
+
+/* Hyper-parameters: clsr.yaml + the flag overrides of examples/00_quick_start/sequential.py:36-68. */
+typedef struct clsr_config {
+  int32_t device;            /* CUDA device ordinal */
+  int32_t max_rows;          /* capacity in graph rows B (file lines x (1 + train_num_ngs)) */
+  int32_t seq_len;           /* max_seq_length T */
+  int32_t item_dim, cate_dim, user_dim, hidden;   /* hidden must equal item_dim + cate_dim */
+  int32_t att0, att1;        /* att_fcn_layer_sizes */
+  int32_t fc0, fc1;          /* layer_sizes */
+  int64_t n_items, n_cates, n_users;
+  int32_t train_group;       /* 1 + train_num_ngs (grouped softmax width) */
+  float embed_l2, layer_l2;
+  int32_t contrastive_kind;  /* 0 = triplet, 1 = bpr */
+  float triplet_margin, contrastive_weight, discrepancy_weight;
+  int32_t contrastive_len_threshold, contrastive_recent_k;
+  int32_t optimizer;         /* 0 = adam (TF non-lazy sparse sweep), 1 = lazyadam */
+  float learning_rate, beta1, beta2, adam_eps;
+  int32_t clip_norm;         /* is_clip_norm */
+  float max_grad_norm;
+  float bn_momentum, bn_eps; /* 0.95 / 1e-4 (base_model.py:676-677) */
+  int32_t math_mode;         /* 0 = fp32 SIMT everywhere, 1 = bf16 tcgen05 for the large GEMMs */
+} clsr_config;
+
+/* One feed_dict (sequential_iterator.py:718-731), as plain arrays.  `group` declares that
+ * rows s*group .. s*group+group-1 share users / histories / mask / time features (the
+ * iterator replicates each training line 1+num_ngs times, :588-610); the engine then reads
+ * those arrays at row s*group only.  group = 1 makes no assumption. */
+typedef struct clsr_batch {
+  int32_t rows;                 /* B */
+  int32_t group;                /* G, must divide rows */
+  int32_t on_device;            /* 0: host pointers (staged by the call), 1: device pointers */
+  const int32_t* users;         /* [B] */
+  const int32_t* items;         /* [B] */
+  const int32_t* cates;         /* [B] */
+  const int32_t* item_history;  /* [B, T] */
+  const int32_t* cate_history;  /* [B, T] */
+  const int32_t* mask;          /* [B, T] 0/1, left-aligned */
+  const float* time_from_first_action; /* [B, T] */
+  const float* time_to_now;     /* [B, T] */
+  const float* labels;          /* [B] (train only; may be NULL for inference) */
+} clsr_batch;
+
+/* Outputs of one training step = the fetch list of CLSRModel.train (clsr.py:396-406). */
+typedef struct clsr_losses {
+  float loss, data_loss, regular_loss, contrastive_loss, discrepancy_loss;
+} clsr_losses;
+
+#define CLSR_STEP_NO_OPTIMIZER 1u /* stop after gradients (+ scatter-add); do not touch variables */
+#define CLSR_STEP_NO_BN_UPDATE 2u /* do not move the BN moving statistics */
+
+/* ---- lifetime ------------------------------------------------------------------- */
+int clsr_create(const clsr_config* cfg, clsr_engine** out);     /* BaseModel.__init__ (base_model.py:18-71) */
+void clsr_destroy(clsr_engine* e);
+const char* clsr_last_error(const clsr_engine* e);              /* e may be NULL (creation errors) */
+int clsr_set_stream(clsr_engine* e, void* cuda_stream);
+int64_t clsr_workspace_bytes(const clsr_engine* e);
+
+/* ---- variables -------------------------------------------------------------------
+ * Dense (non-table) variables live in one engine-owned fp32 device buffer; entry i has
+ * TF name clsr_dense_name(i), offset and element count in floats. */
+int32_t clsr_dense_count(const clsr_engine* e);
+const char* clsr_dense_name(const clsr_engine* e, int32_t i);
+int64_t clsr_dense_offset(const clsr_engine* e, int32_t i);
+int64_t clsr_dense_numel(const clsr_engine* e, int32_t i);
+int32_t clsr_dense_trainable(const clsr_engine* e, int32_t i);
+int64_t clsr_dense_total(const clsr_engine* e);
+/* which: 0 = values, 1 = Adam m, 2 = Adam v, 3 = last gradient (before clipping) */
+int clsr_dense_read(clsr_engine* e, int32_t which, float* host_dst);
+int clsr_dense_write(clsr_engine* e, int32_t which, const float* host_src);
+/* Tables are caller-owned device memory (fp32, row-major, 16-byte aligned).  m / v are the
+ * Adam slots (may be NULL when the engine is used for inference only). */
+int clsr_bind_table(clsr_engine* e, int32_t table, float* values, float* adam_m, float* adam_v);
+int clsr_set_adam_step(clsr_engine* e, int64_t step);  /* number of completed updates */
+int64_t clsr_get_adam_step(const clsr_engine* e);
+
+/* ---- steps ---------------------------------------------------------------------- */
+/* sess.run([update, update_ops, loss, ...]) of CLSRModel.train (clsr.py:383-408). */
+int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, clsr_losses* out);
+/* sess.run([pred, ...]) of eval / eval_with_user / eval_with_user_and_alpha / infer with
+ * is_train_stage=False.  pred / alpha: host buffers of `rows` floats (alpha may be NULL). */
+int clsr_predict(clsr_engine* e, const clsr_batch* batch, float* pred, float* alpha);
+int clsr_synchronize(clsr_engine* e);
+
+/* ---- standalone hot-path operators (benchmarks / parity tests) -------------------- */
+/* K1+K3: hist_input[r,t,:] = concat(item_table[ih[r,t]], cate_table[ch[r,t]]) (clsr.py:145-147).
+ * All pointers are device pointers; out is [rows, T, item_dim+cate_dim]. */
+int clsr_gather_history(clsr_engine* e, const int32_t* item_hist, const int32_t* cate_hist,
+                        int64_t positions, float* out);
+/* K13: sparse-gradient scatter-add of d_hist [positions, D] into compact per-unique-id rows.
+ * Returns the unique ids / compact rows through device pointers owned by the engine. */
+int clsr_scatter_history_grad(clsr_engine* e, const int32_t* item_hist, const int32_t* cate_hist,
+                              int64_t positions, const float* d_hist);
+int clsr_sparse_grad_view(clsr_engine* e, int32_t table, const int32_t** unique_ids,
+                          const float** rows, const int32_t** count);
+
+/* ---- multi-GPU (data parallel over sequences; NCCL over NVLink) -------------------- */
+int clsr_nccl_unique_id(void* out128);                        /* 128 bytes */
+int clsr_comm_init(clsr_engine* e, int32_t rank, int32_t world, const void* id128);
+
+/* ---- introspection for parity tests ------------------------------------------------ */
+/* Named intermediate buffers of the last step (device pointers, fp32). */
+int clsr_debug_buffer(clsr_engine* e, const char* name, const float** dev_ptr, int64_t* numel);
+/* Synchronise the engine stream, then copy `bytes` from device memory to the host. */
+int clsr_debug_read(clsr_engine* e, const void* dev_src, void* host_dst, int64_t bytes);
+int clsr_set_debug_sync(clsr_engine* e, int32_t on);  /* sync + check after every kernel */
+int64_t clsr_kernel_launches(const clsr_engine* e);   /* kernels launched by the last step */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
