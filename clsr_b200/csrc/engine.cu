@@ -57,6 +57,11 @@ struct clsr_engine {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   bool debug_sync = false;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<const char*> prof_names;
+  size_t prof_used = 0;
+  std::map<std::string, std::pair<double, long long>> prof_agg;
   long long launches = 0;
   long long adam_step = 0;
   int num_sms = 148;
@@ -104,6 +109,7 @@ struct clsr_engine {
   float *in_tfa, *in_ttn, *in_labels;
   char* h_stage = nullptr;  // pinned staging
   size_t h_stage_bytes = 0;
+  cudaEvent_t h2d_done = nullptr;  // the staging buffer may be rewritten once this has fired
   float* h_out = nullptr;  // pinned [2*Bmax]
 
   // workspace
@@ -134,10 +140,26 @@ int fail(clsr_engine* e, int code, const char* fmt, ...) {
                   __LINE__);                                                                       \
   } while (0)
 
+// Per-kernel device timing: one event after every launch on the engine stream; the interval
+// between consecutive events is the kernel's duration (the stream serialises them).
+void prof_mark(clsr_engine* e, const char* name) {
+  if (e->prof_used == e->prof_events.size()) {
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    e->prof_events.push_back(ev);
+    e->prof_names.push_back(name);
+  }
+  e->prof_names[e->prof_used] = name;
+  cudaEventRecord(e->prof_events[e->prof_used], e->stream);
+  e->prof_used++;
+}
+#define MARK(name) do { if (e->profiling) prof_mark(e, name); } while (0)
+
 // Launch bookkeeping: count, optional sync-and-check per kernel (debug).
 #define POST(name)                                                                                 \
   do {                                                                                             \
     e->launches++;                                                                                 \
+    if (e->profiling) prof_mark(e, name);                                                          \
     cudaError_t _c = cudaGetLastError();                                                           \
     if (_c == cudaSuccess && e->debug_sync) _c = cudaStreamSynchronize(e->stream);                 \
     if (_c != cudaSuccess)                                                                         \
@@ -576,6 +598,7 @@ int stage_inputs(clsr_engine* e, const clsr_batch* b, StepCtx* c, bool need_labe
   size_t seq_i = (size_t)S * T * 4;
   size_t need = 5 * seq_i + (size_t)S * 4 + (size_t)B * 4 * 3;
   if (need > e->h_stage_bytes) return fail(e, CLSR_ERR_ARG, "batch exceeds staging capacity");
+  CK(cudaEventSynchronize(e->h2d_done));
   char* hp = e->h_stage;
   auto pack_rows = [&](const void* src, size_t row_bytes) {
     const char* s = (const char*)src;
@@ -599,6 +622,7 @@ int stage_inputs(clsr_engine* e, const clsr_batch* b, StepCtx* c, bool need_labe
   hp += (size_t)B * 4;
   // device layout mirrors the staging layout inside one contiguous block starting at in_ih
   CK(cudaMemcpyAsync(e->in_ih, base, (size_t)(hp - base), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaEventRecord(e->h2d_done, e->stream));
   char* d = (char*)e->in_ih;
   c->ih = (const int32_t*)d; d += seq_i;
   c->ch = (const int32_t*)d; d += seq_i;
@@ -851,6 +875,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
   // ---- BPTT through the three recurrences ----
   float *PX = e->B("PX"), *dPX = e->B("dPX");
   CK(cudaMemsetAsync(dPX, 0, (size_t)M * NX * 4, st));
+  MARK("memset_dPX");
   const int nblk = cdiv(S, RNN_NSEQ);
   {
     size_t sml = (size_t)(H * 4 * H + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
@@ -1039,6 +1064,7 @@ int zero_step_state(clsr_engine* e) {
       CK(cudaMemsetAsync(b->stat_b, 0, 2 * b->N * sizeof(double), e->stream));
     }
   }
+  MARK("zero_state");
   return 0;
 }
 
@@ -1163,6 +1189,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
     e->in_ih = (int32_t*)blk;
     e->h_stage_bytes = bytes;
     CKCU(cudaMallocHost((void**)&e->h_stage, bytes));
+    CKCU(cudaEventCreateWithFlags(&e->h2d_done, cudaEventDisableTiming));
     CKC(dalloc(e, &e->d_len, Sm));
   }
 
@@ -1196,10 +1223,12 @@ void clsr_destroy(clsr_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_losses) cudaFreeHost(e->h_losses);
   if (e->h_out) cudaFreeHost(e->h_out);
   if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->h2d_done) cudaEventDestroy(e->h2d_done);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1274,7 +1303,9 @@ int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, cls
   if ((rc = check_batch(e, batch, true))) return rc;
   e->launches = 0;
   StepCtx c;
+  MARK("(step begin)");
   if ((rc = stage_inputs(e, batch, &c, true))) return rc;
+  MARK("h2d_inputs");
   if ((rc = zero_step_state(e))) return rc;
   if ((rc = forward(e, c, 1, (flags & CLSR_STEP_NO_BN_UPDATE) ? 0 : 1))) return rc;
   if ((rc = backward(e, c))) return rc;
@@ -1385,6 +1416,41 @@ int clsr_debug_read(clsr_engine* e, const void* src, void* dst, int64_t bytes) {
   if (!e || !src || !dst || bytes < 0) return fail(e, CLSR_ERR_ARG, "bad argument");
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+  return CLSR_OK;
+}
+
+int clsr_set_profiling(clsr_engine* e, int32_t on) {
+  if (!e) return CLSR_ERR_ARG;
+  CK(cudaStreamSynchronize(e->stream));
+  e->profiling = on != 0;
+  e->prof_used = 0;
+  e->prof_agg.clear();
+  return CLSR_OK;
+}
+
+// Fold the recorded events into per-kernel totals; returns the number of distinct names.
+int clsr_profile_collect(clsr_engine* e) {
+  if (!e) return CLSR_ERR_ARG;
+  CK(cudaStreamSynchronize(e->stream));
+  for (size_t i = 1; i < e->prof_used; ++i) {
+    if (!strcmp(e->prof_names[i], "(step begin)")) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->prof_events[i - 1], e->prof_events[i]) != cudaSuccess) continue;
+    auto& a = e->prof_agg[e->prof_names[i]];
+    a.first += ms;
+    a.second += 1;
+  }
+  e->prof_used = 0;
+  return (int)e->prof_agg.size();
+}
+
+int clsr_profile_entry(clsr_engine* e, int32_t i, char* name, int32_t name_cap, double* total_ms, int64_t* calls) {
+  if (!e || i < 0 || i >= (int)e->prof_agg.size() || !name || name_cap <= 0) return CLSR_ERR_ARG;
+  auto it = e->prof_agg.begin();
+  std::advance(it, i);
+  snprintf(name, (size_t)name_cap, "%s", it->first.c_str());
+  if (total_ms) *total_ms = it->second.first;
+  if (calls) *calls = it->second.second;
   return CLSR_OK;
 }
 

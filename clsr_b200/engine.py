@@ -56,6 +56,7 @@ EXPORTS = [
     "clsr_get_adam_step", "clsr_train_step", "clsr_predict", "clsr_synchronize", "clsr_gather_history",
     "clsr_scatter_history_grad", "clsr_sparse_grad_view", "clsr_nccl_unique_id", "clsr_comm_init",
     "clsr_debug_buffer", "clsr_debug_read", "clsr_set_debug_sync", "clsr_kernel_launches",
+    "clsr_set_profiling", "clsr_profile_collect", "clsr_profile_entry",
 ]
 
 _lib = None
@@ -101,6 +102,9 @@ def load_library(path=None):
         "clsr_debug_read": (C.c_int, [P, P, P, I64]),
         "clsr_set_debug_sync": (C.c_int, [P, I32]),
         "clsr_kernel_launches": (I64, [P]),
+        "clsr_set_profiling": (C.c_int, [P, I32]),
+        "clsr_profile_collect": (C.c_int, [P]),
+        "clsr_profile_entry": (C.c_int, [P, I32, C.c_char_p, I32, C.POINTER(C.c_double), C.POINTER(I64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -338,6 +342,26 @@ class Engine:
 
     def set_debug_sync(self, on=True):
         self._check(self.lib.clsr_set_debug_sync(self.h, 1 if on else 0))
+
+    def set_stream(self, cuda_stream):
+        """Run all engine work on the given CUDA stream (e.g. torch.cuda.Stream().cuda_stream)."""
+        self._check(self.lib.clsr_set_stream(self.h, cuda_stream))
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.clsr_set_profiling(self.h, 1 if on else 0))
+
+    def profile(self):
+        """{kernel name: (total device ms, calls)} since profiling was switched on."""
+        n = self.lib.clsr_profile_collect(self.h)
+        if n < 0:
+            self._check(n)
+        out = {}
+        buf = C.create_string_buffer(128)
+        ms, calls = C.c_double(), C.c_int64()
+        for i in range(n):
+            self._check(self.lib.clsr_profile_entry(self.h, i, buf, 128, C.byref(ms), C.byref(calls)))
+            out[buf.value.decode()] = (ms.value, calls.value)
+        return out
 
     # -- introspection --
     def debug(self, name, shape):

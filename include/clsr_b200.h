@@ -143,6 +143,12 @@ int clsr_debug_buffer(clsr_engine* e, const char* name, const float** dev_ptr, i
 int clsr_debug_read(clsr_engine* e, const void* dev_src, void* host_dst, int64_t bytes);
 int clsr_set_debug_sync(clsr_engine* e, int32_t on);  /* sync + check after every kernel */
 int64_t clsr_kernel_launches(const clsr_engine* e);   /* kernels launched by the last step */
+/* Per-kernel device time: with profiling on, a CUDA event is recorded on the engine stream after
+ * every launch; collect() folds the intervals into per-kernel totals (ms, calls) by name. */
+int clsr_set_profiling(clsr_engine* e, int32_t on);
+int clsr_profile_collect(clsr_engine* e);
+int clsr_profile_entry(clsr_engine* e, int32_t i, char* name, int32_t name_cap, double* total_ms,
+                       int64_t* calls);
 
 #ifdef __cplusplus
 }
