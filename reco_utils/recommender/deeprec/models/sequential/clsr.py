@@ -1,0 +1,137 @@
+"""CLSRModel on the B200 engine.
+
+Reference: reco_utils/recommender/deeprec/models/sequential/clsr.py.  The whole of
+``_build_seq_graph`` (:137-277), ``_attention_fcn`` (:343-381), the losses (:22-82) and the
+optimizer step (base_model.py:281-297) execute inside libclsr_b200.so; this class keeps the
+reference's constructor, ``train`` / ``eval`` / ``eval_with_user`` / ``eval_with_user_and_alpha`` /
+``infer`` signatures and return shapes (:383-408; base_model.py:366-392;
+sequential_base_model.py:294-324).
+"""
+import numpy as np
+
+from clsr_b200 import params as P
+from clsr_b200.engine import Engine, detect_group, normalize_feed
+from reco_utils.recommender.deeprec.deeprec_utils import load_dict
+from reco_utils.recommender.deeprec.io.sequential_iterator import GROUP_KEY
+from reco_utils.recommender.deeprec.models.sequential.sequential_base_model import SequentialBaseModel
+
+__all__ = ["CLSRModel"]
+
+
+class CLSRModel(SequentialBaseModel):
+    def _build_seq_graph(self):
+        hp = self.hparams
+        unsupported = []
+        if hp.sequential_model != "time4lstm": unsupported.append("sequential_model=%s" % hp.sequential_model)
+        if not hp.interest_evolve: unsupported.append("interest_evolve=False")
+        if not hp.predict_long_short: unsupported.append("predict_long_short=False")
+        if hp.manual_alpha: unsupported.append("manual_alpha=True")
+        if hp.loss != "softmax": unsupported.append("loss=%s" % hp.loss)
+        if hp.enable_BN is not True: unsupported.append("enable_BN=%s" % hp.enable_BN)
+        if list(hp.activation) != ["relu", "relu"]: unsupported.append("activation=%s" % hp.activation)
+        if hp.user_dropout or hp.embedding_dropout or any(hp.dropout): unsupported.append("dropout")
+        if hp.embed_l1 or hp.layer_l1 or hp.cross_l1 or hp.cross_l2: unsupported.append("l1 / cross regularisers")
+        if hp.method != "classification": unsupported.append("method=%s" % hp.method)
+        if len(hp.att_fcn_layer_sizes) != 2 or len(hp.layer_sizes) != 2: unsupported.append("MLP depth != 2")
+        if unsupported:
+            raise NotImplementedError("not available on the B200 CLSR path: " + ", ".join(unsupported))
+        self.user_vocab_length = len(load_dict(hp.user_vocab))
+        self.item_vocab_length = len(load_dict(hp.item_vocab))
+        self.cate_vocab_length = len(load_dict(hp.cate_vocab))
+        self.user_embedding_dim = hp.user_embedding_dim
+        self.item_embedding_dim = hp.item_embedding_dim
+        self.cate_embedding_dim = hp.cate_embedding_dim
+        G = self.train_num_ngs + 1
+        self.engine = Engine(
+            self.item_vocab_length, self.cate_vocab_length, self.user_vocab_length,
+            max_rows=hp.batch_size * G, seq_len=hp.max_seq_length, item_dim=hp.item_embedding_dim,
+            cate_dim=hp.cate_embedding_dim, user_dim=hp.user_embedding_dim, hidden=hp.hidden_size,
+            att_sizes=tuple(hp.att_fcn_layer_sizes), layer_sizes=tuple(hp.layer_sizes), train_group=G,
+            embed_l2=hp.embed_l2, layer_l2=hp.layer_l2, contrastive_loss=hp.contrastive_loss,
+            triplet_margin=hp.triplet_margin, contrastive_weight=hp.contrastive_loss_weight,
+            discrepancy_weight=hp.discrepancy_loss_weight,
+            contrastive_len_threshold=hp.contrastive_length_threshold,
+            contrastive_recent_k=hp.contrastive_recent_k, optimizer=hp.optimizer,
+            learning_rate=hp.learning_rate, clip_norm=bool(hp.is_clip_norm), max_grad_norm=float(hp.max_grad_norm))
+        if hp.init_method != "tnormal":
+            raise NotImplementedError("init_method=%s (only tnormal) on the B200 CLSR path" % hp.init_method)
+        self.engine.set_params(P.init_params(
+            self.item_vocab_length, self.cate_vocab_length, self.user_vocab_length, hp.item_embedding_dim,
+            hp.cate_embedding_dim, hp.user_embedding_dim, hp.hidden_size, hp.att_fcn_layer_sizes, hp.layer_sizes,
+            seed=self.seed, init_value=hp.init_value))
+
+    # ---- variables <-> checkpoints ---------------------------------------------------------------
+    def _export_variables(self):
+        shapes = self.engine.shapes()
+        out = {}
+        for name, arr in self.engine.get_params().items():
+            out[name] = arr.reshape(shapes[name]) if name in shapes else arr
+        return out
+
+    def _import_variables(self, tensors):
+        self.engine.set_params(tensors, strict=True)
+
+    # ---- feed handling ---------------------------------------------------------------------------
+    def _arrays(self, feed_dict, need_labels):
+        it = self.iterator
+        raw = {"users": feed_dict[it.users], "items": feed_dict[it.items], "cates": feed_dict[it.cates],
+               "item_history": feed_dict[it.item_history], "item_cate_history": feed_dict[it.item_cate_history],
+               "mask": feed_dict[it.mask], "time_from_first_action": feed_dict[it.time_from_first_action],
+               "time_to_now": feed_dict[it.time_to_now], "labels": feed_dict.get(it.labels)}
+        feed = normalize_feed(raw, need_labels)
+        group = feed_dict.get(GROUP_KEY)
+        if group is None:  # foreign feed: share work only if the rows of a group really are identical
+            group = detect_group(feed, self.train_num_ngs + 1)
+        return feed, int(group)
+
+    def train(self, sess, feed_dict):
+        """One optimisation step.  Returns the reference's 8-item fetch list
+        [update, update_ops, loss, data_loss, regular_loss, contrastive_loss, discrepancy_loss, summary]."""
+        feed_dict[self.layer_keeps] = self.keep_prob_train
+        feed_dict[self.embedding_keeps] = self.embedding_keep_prob_train
+        feed_dict[self.is_train_stage] = True
+        feed, group = self._arrays(feed_dict, True)
+        out = self.engine.train_step(feed, group=group, normalized=True)
+        summary = dict(out) if self.hparams.write_tfevents else None
+        return [None, [], out["loss"], out["data_loss"], out["regular_loss"], out["contrastive_loss"],
+                out["discrepancy_loss"], summary]
+
+    def batch_train(self, file_iterator, train_sess):
+        step = 0
+        epoch_loss = 0
+        for batch_data_input in file_iterator:
+            if batch_data_input:
+                (_, _, step_loss, step_data_loss, _, _, _, summary) = self.train(train_sess, batch_data_input)
+                if self.hparams.write_tfevents and self.hparams.SUMMARIES_DIR:
+                    self.writer.add_summary(summary, step)
+                epoch_loss += step_loss
+                step += 1
+                if step % self.hparams.show_step == 0:
+                    print("step {0:d} , total_loss: {1:.4f}, data_loss: {2:.4f}".format(step, step_loss, step_data_loss))
+        return epoch_loss
+
+    def _predict(self, feed_dict, with_alpha=False):
+        feed_dict[self.layer_keeps] = self.keep_prob_test
+        feed_dict[self.embedding_keeps] = self.embedding_keep_prob_test
+        feed_dict[self.is_train_stage] = False
+        feed, group = self._arrays(feed_dict, False)
+        if GROUP_KEY in feed_dict and feed_dict[GROUP_KEY] == 1:
+            group = 1
+        pred, alpha = self.engine.predict(feed, group=group, normalized=True, with_alpha=with_alpha)
+        return feed, pred.reshape(-1, 1), (alpha.reshape(-1, 1) if with_alpha else None)
+
+    def eval(self, sess, feed_dict):
+        _, pred, _ = self._predict(feed_dict)
+        return [pred, np.asarray(feed_dict[self.iterator.labels])]
+
+    def eval_with_user(self, sess, feed_dict):
+        feed, pred, _ = self._predict(feed_dict)
+        return [feed["users"], pred, np.asarray(feed_dict[self.iterator.labels])]
+
+    def eval_with_user_and_alpha(self, sess, feed_dict):
+        feed, pred, alpha = self._predict(feed_dict, with_alpha=True)
+        return [feed["users"], pred, np.asarray(feed_dict[self.iterator.labels]), alpha]
+
+    def infer(self, sess, feed_dict):
+        _, pred, _ = self._predict(feed_dict)
+        return [pred]

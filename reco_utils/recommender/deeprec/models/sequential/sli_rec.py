@@ -1,0 +1,11 @@
+"""Import-only placeholder: SLI_RECModel is one of the comparison baselines of the reference
+(reco_utils/recommender/deeprec/models/sequential/sli_rec.py); it is outside the CLSR hot path this
+repository accelerates, but examples/00_quick_start/sequential.py imports it unconditionally."""
+from reco_utils.recommender.deeprec.models.sequential.sequential_base_model import SequentialBaseModel
+
+__all__ = ["SLI_RECModel"]
+
+
+class SLI_RECModel(SequentialBaseModel):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("SLI_RECModel is not part of the B200 CLSR build; use --model CLSR")
