@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--seqs", type=int, default=0, help="user-sequences per step per GPU (default: workload's)")
     ap.add_argument("--optimizer", default="adam", choices=["adam", "lazyadam"])
     ap.add_argument("--ref-seqs", type=int, default=256, help="bounded CPU sample: sequences per CPU step")
+    ap.add_argument("--math", default="tc", choices=["tc", "simt"],
+                    help="tc: large GEMMs on tcgen05 (split-bf16, fp32 accumulate); simt: fp32 CUDA cores everywhere")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default="")
     return ap.parse_args()
@@ -154,7 +156,7 @@ def run_b200(a):
     S = a.seqs or w["seqs"]
     B, T = S * G, w["T"]
     eng = Engine(w["n_items"], w["n_cates"], w["n_users"], max_rows=B, seq_len=T, train_group=G,
-                 optimizer=a.optimizer, device=local)
+                 optimizer=a.optimizer, device=local, math_mode=1 if a.math == "tc" else 0)
     dense = P.init_params(1, 1, 1, seed=42, tables=False)
     eng.set_dense(dense)
     tabs = make_tables(w, 42)
@@ -251,7 +253,8 @@ def run_b200(a):
         "metric": "user-sequences/sec (CLSR training step, seq_len=%d, emb_dim=40)" % T,
         "value": S * world * a.steps / (ms / 1e3), "unit": "user-sequences/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (split-bf16 tcgen05 MMA, fp32 accumulate) + f32" if a.math == "tc" else "f32", "data": "synthetic",
         "config": {"workload": "Taobao-shaped synthetic: seq_len=%d emb_dim=40 (32+8) batch=%d user-sequences "
                                "(%d rows) per GPU, %d items / %d cates / %d users, zipf ids, optimizer=%s"
                                % (T, S, B, w["n_items"], w["n_cates"], w["n_users"], a.optimizer),

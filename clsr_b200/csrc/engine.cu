@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -20,6 +21,7 @@
 #include "gemm.cuh"
 #include "head.cuh"
 #include "rnn.cuh"
+#include "tc_gemm.cuh"
 
 using namespace clsr;
 
@@ -65,6 +67,9 @@ struct clsr_engine {
   long long launches = 0;
   long long adam_step = 0;
   int num_sms = 148;
+  int smem_optin = 49152;
+  int tc_smem_max = 49152;
+  int tc_dw_smem_max = 49152;
 
   int T, Di, Dc, D, U, H, Q, A0, A1, L0, L1, CA, NX;
   int oG1, oC1, oG2, oC2, oL, oO, oTN, oTL;
@@ -447,9 +452,68 @@ int alloc_bn(clsr_engine* e, BnLayer* b) {
 }
 
 // ---- launch helpers --------------------------------------------------------------------------------
+inline int round16(int x) { return (x + 15) & ~15; }
+
+// One tcgen05 launch: K <= 160 (W resident in shared memory), N <= 256 (one UMMA, one TMEM accumulator).
+int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, const float* W, int ldw,
+                const EpiOp& ep, bool stats) {
+  const int kpad = round16(K), npad = round16(N);
+  int nstages = 2;
+  tc::Smem L = tc::smem_layout(kpad, npad, nstages);
+  if (L.total > e->tc_smem_max) {
+    nstages = 1;
+    L = tc::smem_layout(kpad, npad, nstages);
+  }
+  if (L.total > e->tc_smem_max) return fail(e, CLSR_ERR_ARG, "tc_gemm %s: K=%d N=%d does not fit shared memory", name, K, N);
+  uint32_t cols = 32;
+  while ((int)cols < 2 * npad) cols <<= 1;
+  int per_sm = e->smem_optin / (L.total + 6 * 1024);
+  if (per_sm > 1) per_sm = 1;  // 416 threads x 128 registers: one resident CTA per SM
+  if (per_sm * (int)cols > 512) per_sm = 512 / (int)cols;
+  if (per_sm < 1) per_sm = 1;
+  int tiles = cdiv(M, tc::kTileM);
+  int grid = tiles < e->num_sms * per_sm ? tiles : e->num_sms * per_sm;
+  if (stats) tc::tc_gemm_kernel<true><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, a, W, ldw, ep);
+  else tc::tc_gemm_kernel<false><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, a, W, ldw, ep);
+  POST(name);
+  return 0;
+}
+
+bool tc_eligible(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, bool stats) {
+  if (e->cfg.math_mode != 1 || M < 1024) return false;
+  if (const char* only = getenv("CLSR_TC_ONLY")) {  // developer bisection aid: comma-separated GEMM names
+    std::string list = std::string(",") + only + ",";
+    if (list.find(std::string(",") + name + ",") == std::string::npos) return false;
+  }
+  if (N > 256 && stats) return false;
+  if (K > 160 && a.mode != A_PLAIN) return false;
+  return true;
+}
+
+int tc_gemm(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, const float* W, int ldw,
+            const EpiOp& ep, bool stats) {
+  int rc;
+  for (int n0 = 0; n0 < N; n0 += 240) {          // column slabs (one UMMA is at most 256 wide)
+    int nn = N - n0 < 240 ? N - n0 : 240;
+    if (N <= 256) nn = N;
+    for (int k0 = 0; k0 < K; k0 += 160) {        // K slabs accumulate through the epilogue
+      int kk = K - k0 < 160 ? K - k0 : 160;
+      AOp a2 = a;
+      EpiOp p2 = ep;
+      if (k0) { a2.A = a.A + k0; p2.flags |= E_ACCUM; p2.bias = nullptr; }
+      p2.C = ep.C + n0;
+      if (ep.bias && !k0) p2.bias = ep.bias + n0;
+      if ((rc = tc_gemm_one(e, name, M, nn, kk, a2, W + (size_t)k0 * ldw + n0, ldw, p2, stats))) return rc;
+    }
+    if (N <= 256) break;
+  }
+  return 0;
+}
+
 int gemm(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, const float* W, int ldw,
          const EpiOp& ep, bool stats) {
   if (M <= 0) return 0;
+  if (tc_eligible(e, name, M, N, K, a, stats)) return tc_gemm(e, name, M, N, K, a, W, ldw, ep, stats);
   auto launch = [&](auto kern, int BM, int BN) {
     int tiles = cdiv(M, BM);
     int gx = tiles < e->num_sms * 4 ? tiles : e->num_sms * 4;
@@ -469,9 +533,39 @@ int gemm(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, co
   return 0;
 }
 
+// dW on tensor cores; N is cut into column slabs of at most 240.
+int tc_dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& a, const AOp& b, float* dW,
+              int lddw, float* colsum) {
+  const int nslab = cdiv(N, 240);
+  const int per = ((cdiv(N, nslab) + 7) / 8) * 8;
+  for (int n0 = 0; n0 < N; n0 += per) {
+    int nn = N - n0 < per ? N - n0 : per;
+    int npad = round16(nn);
+    int nstages = 2;
+    tc::DwSmem L = tc::dw_smem_layout(npad, nstages);
+    if (L.total > e->tc_dw_smem_max) { nstages = 1; L = tc::dw_smem_layout(npad, nstages); }
+    if (L.total > e->tc_dw_smem_max) return fail(e, CLSR_ERR_ARG, "tc_dwgemm %s: N slab %d does not fit", name, nn);
+    uint32_t cols = 32;
+    while ((int)cols < npad) cols <<= 1;
+    AOp b2 = b;
+    if (n0) {
+      if (b.mode != A_PLAIN) return fail(e, CLSR_ERR_ARG, "tc_dwgemm %s: column slabs need a plain B operand", name);
+      b2.A = b.A + n0;
+    }
+    int tiles = cdiv(M, tc::kTileM);
+    int grid = tiles < e->num_sms ? tiles : e->num_sms;
+    tc::tc_dw_kernel<<<grid, tc::kDwThreads, L.total, e->stream>>>(M, K, nn, npad, nstages, cols, a, b2, dW + n0, lddw,
+                                                                 colsum ? colsum + n0 : nullptr);
+    POST(name);
+  }
+  return 0;
+}
+
 int dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& a, const AOp& b, float* dW,
            int lddw, float* colsum) {
   if (M <= 0) return 0;
+  if (tc_eligible(e, name, M, N, K, a, false) && K + (colsum ? 1 : 0) <= 128 && (N <= 240 || b.mode == A_PLAIN))
+    return tc_dwgemm(e, name, M, K, N, a, b, dW, lddw, colsum);
   int ty = cdiv(K, 64), tz = cdiv(N, 64);
   int want = (e->num_sms * 4) / (ty * tz);
   if (want < 1) want = 1;
@@ -1110,6 +1204,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
   cudaDeviceProp prop;
   CKCU(cudaGetDeviceProperties(&prop, cfg->device));
   e->num_sms = prop.multiProcessorCount;
+  e->smem_optin = (int)prop.sharedMemPerBlockOptin;
   CKCU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   e->own_stream = true;
 
@@ -1144,6 +1239,16 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
     CKCU(cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smf > 49152 ? smf : 49152)));
   }
 
+  {
+    cudaFuncAttributes fa;
+    CKCU(cudaFuncGetAttributes(&fa, tc::tc_gemm_kernel<true>));
+    e->tc_smem_max = e->smem_optin - (int)fa.sharedSizeBytes - 256;
+    CKCU(cudaFuncSetAttribute(tc::tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tc_smem_max));
+    CKCU(cudaFuncSetAttribute(tc::tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tc_smem_max));
+    CKCU(cudaFuncGetAttributes(&fa, tc::tc_dw_kernel));
+    e->tc_dw_smem_max = e->smem_optin - (int)fa.sharedSizeBytes - 256;
+    CKCU(cudaFuncSetAttribute(tc::tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tc_dw_smem_max));
+  }
   build_inventory(e);
   CKC(dalloc(e, &e->P, e->Ptot));
   CKC(dalloc(e, &e->Pm, e->Ptot));
@@ -1417,6 +1522,29 @@ int clsr_debug_read(clsr_engine* e, const void* src, void* dst, int64_t bytes) {
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
   return CLSR_OK;
+}
+
+// Standalone linear layer C = A.W + bias on device pointers (mode 0: fp32 SIMT, 1: tcgen05 split-bf16).
+int clsr_debug_gemm(clsr_engine* e, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* W,
+                    int32_t ldw, const float* bias, float* C, int32_t ldc, int32_t mode) {
+  if (!e || !A || !W || !C) return fail(e, CLSR_ERR_ARG, "bad argument");
+  int saved = e->cfg.math_mode;
+  e->cfg.math_mode = mode;
+  int rc = mode == 1 ? tc_gemm(e, "debug_tc_gemm", M, N, K, a_plain(A, lda), W, ldw, e_store(C, ldc, bias), false)
+                     : gemm(e, "debug_gemm", M, N, K, a_plain(A, lda), W, ldw, e_store(C, ldc, bias), false);
+  e->cfg.math_mode = saved;
+  return rc;
+}
+
+// Standalone weight-gradient product dW[K,N] += A[M,K]^T . B[M,N] (+ column sums of B) on device pointers.
+int clsr_debug_dwgemm(clsr_engine* e, int32_t M, int32_t K, int32_t N, const float* A, int32_t lda, const float* B,
+                      int32_t ldb, float* dW, int32_t lddw, float* colsum, int32_t mode) {
+  if (!e || !A || !B || !dW) return fail(e, CLSR_ERR_ARG, "bad argument");
+  int saved = e->cfg.math_mode;
+  e->cfg.math_mode = mode;
+  int rc = dwgemm(e, "debug_dwgemm", M, K, N, a_plain(A, lda), a_plain(B, ldb), dW, lddw, colsum);
+  e->cfg.math_mode = saved;
+  return rc;
 }
 
 int clsr_set_profiling(clsr_engine* e, int32_t on) {

@@ -56,7 +56,7 @@ EXPORTS = [
     "clsr_get_adam_step", "clsr_train_step", "clsr_predict", "clsr_synchronize", "clsr_gather_history",
     "clsr_scatter_history_grad", "clsr_sparse_grad_view", "clsr_nccl_unique_id", "clsr_comm_init",
     "clsr_debug_buffer", "clsr_debug_read", "clsr_set_debug_sync", "clsr_kernel_launches",
-    "clsr_set_profiling", "clsr_profile_collect", "clsr_profile_entry",
+    "clsr_set_profiling", "clsr_profile_collect", "clsr_profile_entry", "clsr_debug_gemm", "clsr_debug_dwgemm",
 ]
 
 _lib = None
@@ -102,6 +102,8 @@ def load_library(path=None):
         "clsr_debug_read": (C.c_int, [P, P, P, I64]),
         "clsr_set_debug_sync": (C.c_int, [P, I32]),
         "clsr_kernel_launches": (I64, [P]),
+        "clsr_debug_gemm": (C.c_int, [P, I32, I32, I32, P, I32, P, I32, P, P, I32, I32]),
+        "clsr_debug_dwgemm": (C.c_int, [P, I32, I32, I32, P, I32, P, I32, P, I32, P, I32]),
         "clsr_set_profiling": (C.c_int, [P, I32]),
         "clsr_profile_collect": (C.c_int, [P]),
         "clsr_profile_entry": (C.c_int, [P, I32, C.c_char_p, I32, C.POINTER(C.c_double), C.POINTER(I64)]),
@@ -201,6 +203,9 @@ class Engine:
                 self.table_v[t] = torch.zeros(shp, dtype=torch.float32, device=self.device)
             self._bind(t)
         self.user_table = None  # sequential/embedding/user_embedding: gathered but unused by CLSR
+        # Share torch's current stream so engine kernels are ordered with the torch ops that fill or read
+        # the tables and device-resident feeds (the engine's own stream is non-blocking).
+        self._check(self.lib.clsr_set_stream(self.h, torch.cuda.current_stream(self.device).cuda_stream))
 
     # -- plumbing --
     def _check(self, rc):

@@ -143,6 +143,13 @@ int clsr_debug_buffer(clsr_engine* e, const char* name, const float** dev_ptr, i
 int clsr_debug_read(clsr_engine* e, const void* dev_src, void* host_dst, int64_t bytes);
 int clsr_set_debug_sync(clsr_engine* e, int32_t on);  /* sync + check after every kernel */
 int64_t clsr_kernel_launches(const clsr_engine* e);   /* kernels launched by the last step */
+/* Standalone linear layer C[M,N] = A[M,K].W[K,N] + bias on device pointers; mode 0 = fp32 SIMT kernel,
+ * 1 = tcgen05 split-bf16 kernel.  Used by the kernel-level parity tests. */
+int clsr_debug_gemm(clsr_engine* e, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* W,
+                    int32_t ldw, const float* bias, float* C, int32_t ldc, int32_t mode);
+/* Standalone weight-gradient product dW[K,N] += A[M,K]^T . B[M,N], colsum[n] += sum_m B[m,n] (may be NULL). */
+int clsr_debug_dwgemm(clsr_engine* e, int32_t M, int32_t K, int32_t N, const float* A, int32_t lda, const float* B,
+                      int32_t ldb, float* dW, int32_t lddw, float* colsum, int32_t mode);
 /* Per-kernel device time: with profiling on, a CUDA event is recorded on the engine stream after
  * every launch; collect() folds the intervals into per-kernel totals (ms, calls) by name. */
 int clsr_set_profiling(clsr_engine* e, int32_t on);

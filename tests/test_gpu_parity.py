@@ -40,6 +40,18 @@ def test_step_matches_oracle(cuda_lib, group):
     assert res["fwd/X"] == 0.0 and res["fwd/tgt"] == 0.0, "gathered rows must be bit-exact"
 
 
+@pytest.mark.parametrize("group", [5, 1])
+def test_step_matches_oracle_tensor_core_path(cuda_lib, group):
+    """math_mode=1: the large GEMMs run on tcgen05 (split-bf16, fp32 accumulate in TMEM)."""
+    G, S = 5, 48
+    feed, prm = PU.small_problem(S=S, G=G, seed=21)
+    feed = PU.set_lengths(feed, [1, 50, 3, 5, 6, 2], G)
+    eng = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, G=G, math_mode=1)
+    eng.set_debug_sync(True)
+    res, _ = PU.compare_step(eng, feed, prm, G, group)
+    _check(res)
+
+
 def test_ragged_batch_and_long_window(cuda_lib):
     """Row count not a multiple of any tile size, T = 250 (Kuaishou window)."""
     G, S, T = 5, 13, 250

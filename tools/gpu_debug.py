@@ -12,9 +12,9 @@ def main():
     G = int(os.environ.get("G", 5))
     group = int(os.environ.get("GROUP", G))
     S = int(os.environ.get("S", 24))
-    feed, prm = PU.small_problem(S=S, G=G)
+    feed, prm = PU.small_problem(S=S, G=G, seed=int(os.environ.get('SEED', 3)))
     feed = PU.set_lengths(feed, [1, 50, 3, 5, 6, 2], G)
-    eng = PU.make_engine(prm, 3000, 40, 200, max_rows=S * G, G=G)
+    eng = PU.make_engine(prm, 3000, 40, 200, max_rows=S * G, G=G, math_mode=int(os.environ.get('MATH', 0)))
     eng.set_debug_sync(True)
     res, losses = PU.compare_step(eng, feed, prm, G, group)
     print("losses", losses)
