@@ -70,6 +70,16 @@ __global__ void gather_rows_kernel(const int32_t* __restrict__ idx, int idx_stri
   }
 }
 
+// dst[i] = src[(i / T) * seq_stride + i % T]: contiguous copy of a strided id array (all-gather staging)
+__global__ void compact_ids_kernel(const int32_t* __restrict__ src, int T, int seq_stride, long long n,
+                                   int32_t* __restrict__ dst) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long s = i / T;
+    dst[i] = src[s * seq_stride + (i - s * T)];
+  }
+}
+
 // tf.unique through a direct-address table: slot[id] = compact row (or -1).  The first thread to
 // claim an id appends it to uniq[]; later kernels translate ids through slot[].
 __global__ void mark_unique_kernel(const int32_t* __restrict__ ids, long long n, int T, int seq_stride,

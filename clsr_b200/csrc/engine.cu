@@ -5,6 +5,7 @@
 // The step is a fixed sequence of kernel launches on one stream over a workspace allocated at
 // creation; no allocation, no host synchronisation until the scalar losses are read back.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -117,6 +118,18 @@ struct clsr_engine {
   cudaEvent_t h2d_done = nullptr;  // the staging buffer may be rewritten once this has fired
   float* h_out = nullptr;  // pinned [2*Bmax]
 
+  // data-parallel state (NCCL is dlopen'ed by clsr_comm_init)
+  int world = 1, rank = 0;
+  void* nccl_lib = nullptr;
+  void* comm = nullptr;
+  int (*ncclAllReduce_)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*ncclAllGather_)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*ncclCommDestroy_)(void*) = nullptr;
+  const char* (*ncclGetErrorString_)(int) = nullptr;
+  int32_t *g_ih = nullptr, *g_ch = nullptr, *g_items = nullptr, *g_cates = nullptr, *g_users = nullptr;
+  int32_t *l_ih = nullptr, *l_ch = nullptr, *l_users = nullptr;
+  float *g_dX = nullptr, *g_dtgt = nullptr, *g_dul = nullptr, *g_dus = nullptr;
+
   // workspace
   std::vector<void*> allocs;
   std::map<std::string, std::pair<float*, long long>> bufs;
@@ -171,6 +184,22 @@ void prof_mark(clsr_engine* e, const char* name) {
       return fail(e, CLSR_ERR_CUDA, "kernel %s failed: %s (%s:%d)", name, cudaGetErrorString(_c),  \
                   __FILE__, __LINE__);                                                             \
   } while (0)
+
+enum { kNcclInt32 = 2, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
+
+int allreduce(clsr_engine* e, void* buf, size_t count, int dtype) {
+  if (e->world <= 1) return 0;
+  int r = e->ncclAllReduce_(buf, buf, count, dtype, kNcclSum, e->comm, e->stream);
+  if (r != 0) return fail(e, CLSR_ERR_NCCL, "ncclAllReduce failed: %s", e->ncclGetErrorString_(r));
+  MARK("nccl_allreduce");
+  return 0;
+}
+int allgather(clsr_engine* e, const void* src, void* dst, size_t count, int dtype) {
+  int r = e->ncclAllGather_(src, dst, count, dtype, e->comm, e->stream);
+  if (r != 0) return fail(e, CLSR_ERR_NCCL, "ncclAllGather failed: %s", e->ncclGetErrorString_(r));
+  MARK("nccl_allgather");
+  return 0;
+}
 
 template <typename Tp>
 int dalloc(clsr_engine* e, Tp** p, long long n, bool zero = true) {
@@ -604,6 +633,11 @@ EpiOp e_store(float* C, int ldc, const float* bias = nullptr, int flags = 0) {
 }
 
 int bn_fwd(clsr_engine* e, BnLayer& b, double count, int train, int update) {
+  if (train && e->world > 1) {  // single-device semantics: statistics over the global batch
+    int rc = allreduce(e, b.stat_f, 2 * b.N, kNcclFloat64);
+    if (rc) return rc;
+    count *= e->world;
+  }
   bn_fwd_finalize_kernel<<<cdiv(b.N, 128), 128, 0, e->stream>>>(
       b.stat_f, b.N, count, e->P + b.gamma, e->P + b.beta, e->cfg.bn_eps, e->cfg.bn_momentum,
       e->P + b.mmean, e->P + b.mvar, train, update, b.scale, b.shift, b.mean, b.rstd);
@@ -611,8 +645,16 @@ int bn_fwd(clsr_engine* e, BnLayer& b, double count, int train, int update) {
   return 0;
 }
 int bn_bwd(clsr_engine* e, BnLayer& b, double count) {
+  if (e->world > 1) {
+    int rc = allreduce(e, b.stat_b, 2 * b.N, kNcclFloat64);
+    if (rc) return rc;
+    count *= e->world;
+  }
+  // gamma/beta gradients come from the already global sums: only rank 0 contributes them to the
+  // dense-gradient all-reduce
   bn_bwd_finalize_kernel<<<cdiv(b.N, 128), 128, 0, e->stream>>>(
-      b.stat_b, b.N, count, e->P + b.gamma, b.mean, b.rstd, b.al, b.be, b.ga, e->Pg + b.gamma, e->Pg + b.beta);
+      b.stat_b, b.N, count, e->P + b.gamma, b.mean, b.rstd, b.al, b.be, b.ga, e->Pg + b.gamma, e->Pg + b.beta,
+      e->rank == 0 ? 1.f : 0.f);
   POST("bn_bwd_finalize");
   return 0;
 }
@@ -760,6 +802,7 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
   seq_prep_kernel<<<grid1d(e, S, 128), 128, 0, st>>>(c.mask, c.seq_stride, T, S, e->cfg.contrastive_len_threshold,
                                                      e->d_len, e->counts);
   POST("seq_prep");
+  if (train && (rc = allreduce(e, e->counts, 1, kNcclInt32))) return rc;
   blockop_kernel<<<e->n_prep, 256, 0, st>>>(e->ops_prep, e->Wd, e->P);
   POST("prep_weights");
 
@@ -887,7 +930,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
 
   // ---- data loss + prediction MLP ----
   softmax_loss_kernel<<<grid1d(e, B / e->cfg.train_group, 128), 128, 0, st>>>(
-      e->B("logit"), c.labels, e->cfg.train_group, B, e->B("dlogit"), e->B("pred"), e->acc);
+      e->B("logit"), c.labels, e->cfg.train_group, B, B * e->world, e->B("dlogit"), e->B("pred"), e->acc);
   POST("softmax_loss");
   if ((rc = mlp_bwd(e, e->mlp_logit, e->B("mo"), B, e->B("hl0"), e->B("hl1"), e->B("dlogit"), e->B("dhl1"), e->B("dhl0"),
                     W("Wg0T"), W("Wg1T"), e->B("dmo"))))
@@ -1058,38 +1101,66 @@ int backward(clsr_engine* e, const StepCtx& c) {
 }
 
 // K2 + K13: unique ids per table and scatter-add of every slice gradient into compact rows.
+// Data-parallel runs first all-gather the raw ids and per-position gradients of every rank, so each
+// replica builds the identical global (unique ids, summed rows) set and applies the identical update.
 int sparse_grads(clsr_engine* e, const StepCtx& c) {
-  const int B = c.B, S = c.S, T = c.T, U = e->U, D = e->D, Di = e->Di, Dc = e->Dc;
-  const long long M = (long long)S * T;
+  const int T = c.T, U = e->U, D = e->D, Di = e->Di, Dc = e->Dc;
+  int B = c.B, S = c.S;
+  long long M = (long long)S * T;
   cudaStream_t st = e->stream;
-  mark_unique_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(c.ih, M, T, c.seq_stride, e->slot[0], e->uniq[0], e->counts + 1);
+  const int32_t *ih = c.ih, *ch = c.ch, *items = c.items, *cates = c.cates, *users = c.users;
+  int seq_stride = c.seq_stride, user_stride = c.user_stride;
+  const float *dX = e->B("dX"), *dtgt = e->B("dtgt"), *dul = e->B("dul"), *dus = e->B("dus");
+  int rc;
+  if (e->world > 1) {
+    compact_ids_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(c.ih, T, c.seq_stride, M, e->l_ih);
+    POST("compact_ids");
+    compact_ids_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(c.ch, T, c.seq_stride, M, e->l_ch);
+    POST("compact_ids");
+    compact_ids_kernel<<<grid1d(e, S, 256), 256, 0, st>>>(c.users, 1, c.user_stride, S, e->l_users);
+    POST("compact_ids");
+    if ((rc = allgather(e, e->l_ih, e->g_ih, (size_t)M, kNcclInt32))) return rc;
+    if ((rc = allgather(e, e->l_ch, e->g_ch, (size_t)M, kNcclInt32))) return rc;
+    if ((rc = allgather(e, e->l_users, e->g_users, (size_t)S, kNcclInt32))) return rc;
+    if ((rc = allgather(e, c.items, e->g_items, (size_t)B, kNcclInt32))) return rc;
+    if ((rc = allgather(e, c.cates, e->g_cates, (size_t)B, kNcclInt32))) return rc;
+    if ((rc = allgather(e, dX, e->g_dX, (size_t)M * D, kNcclFloat32))) return rc;
+    if ((rc = allgather(e, dtgt, e->g_dtgt, (size_t)B * D, kNcclFloat32))) return rc;
+    if ((rc = allgather(e, dul, e->g_dul, (size_t)S * U, kNcclFloat32))) return rc;
+    if ((rc = allgather(e, dus, e->g_dus, (size_t)S * U, kNcclFloat32))) return rc;
+    ih = e->g_ih; ch = e->g_ch; items = e->g_items; cates = e->g_cates; users = e->g_users;
+    dX = e->g_dX; dtgt = e->g_dtgt; dul = e->g_dul; dus = e->g_dus;
+    seq_stride = T; user_stride = 1;
+    B *= e->world; S *= e->world; M *= e->world;
+  }
+  mark_unique_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(ih, M, T, seq_stride, e->slot[0], e->uniq[0], e->counts + 1);
   POST("unique_item_hist");
-  mark_unique_kernel<<<grid1d(e, B, 256), 256, 0, st>>>(c.items, B, 1, 1, e->slot[0], e->uniq[0], e->counts + 1);
+  mark_unique_kernel<<<grid1d(e, B, 256), 256, 0, st>>>(items, B, 1, 1, e->slot[0], e->uniq[0], e->counts + 1);
   POST("unique_item_tgt");
-  mark_unique_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(c.ch, M, T, c.seq_stride, e->slot[1], e->uniq[1], e->counts + 2);
+  mark_unique_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(ch, M, T, seq_stride, e->slot[1], e->uniq[1], e->counts + 2);
   POST("unique_cate_hist");
-  mark_unique_kernel<<<grid1d(e, B, 256), 256, 0, st>>>(c.cates, B, 1, 1, e->slot[1], e->uniq[1], e->counts + 2);
+  mark_unique_kernel<<<grid1d(e, B, 256), 256, 0, st>>>(cates, B, 1, 1, e->slot[1], e->uniq[1], e->counts + 2);
   POST("unique_cate_tgt");
-  mark_unique_kernel<<<grid1d(e, S, 256), 256, 0, st>>>(c.users, S, 1, c.user_stride, e->slot[2], e->uniq[2], e->counts + 3);
+  mark_unique_kernel<<<grid1d(e, S, 256), 256, 0, st>>>(users, S, 1, user_stride, e->slot[2], e->uniq[2], e->counts + 3);
   POST("unique_users");
   const int cnt_ix[4] = {1, 2, 3, 3};
   for (int t = 0; t < 4; ++t) {
     zero_compact_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->cg[t], e->counts + cnt_ix[t], e->tab_dim[t]);
     POST("zero_compact");
   }
-  scatter_hist_kernel<<<e->num_sms * 4, 256, (size_t)D * 4, st>>>(e->B("dX"), c.ih, c.ch, c.seq_stride, T, e->slot[0], e->slot[1],
+  scatter_hist_kernel<<<e->num_sms * 4, 256, (size_t)D * 4, st>>>(dX, ih, ch, seq_stride, T, e->slot[0], e->slot[1],
                                                                 e->cg[0], e->cg[1], Di, Dc, M, e->sumsq);
   POST("scatter_hist");
-  scatter_rows_kernel<<<grid1d(e, (long long)B * Di / 4, 256), 256, 0, st>>>(e->B("dtgt"), D, 0, Di, c.items, 1, e->slot[0],
+  scatter_rows_kernel<<<grid1d(e, (long long)B * Di / 4, 256), 256, 0, st>>>(dtgt, D, 0, Di, items, 1, e->slot[0],
                                                                            e->cg[0], B, e->sumsq + 0);
   POST("scatter_tgt_item");
-  scatter_rows_kernel<<<grid1d(e, (long long)B * Dc / 4, 256), 256, 0, st>>>(e->B("dtgt"), D, Di, Dc, c.cates, 1, e->slot[1],
+  scatter_rows_kernel<<<grid1d(e, (long long)B * Dc / 4, 256), 256, 0, st>>>(dtgt, D, Di, Dc, cates, 1, e->slot[1],
                                                                            e->cg[1], B, e->sumsq + 1);
   POST("scatter_tgt_cate");
-  scatter_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(e->B("dul"), U, 0, U, c.users, c.user_stride,
+  scatter_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(dul, U, 0, U, users, user_stride,
                                                                           e->slot[2], e->cg[2], S, e->sumsq + 2);
   POST("scatter_ul");
-  scatter_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(e->B("dus"), U, 0, U, c.users, c.user_stride,
+  scatter_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(dus, U, 0, U, users, user_stride,
                                                                           e->slot[2], e->cg[3], S, e->sumsq + 3);
   POST("scatter_us");
   const float l2 = e->cfg.embed_l2, dw = e->cfg.discrepancy_weight;
@@ -1328,6 +1399,7 @@ void clsr_destroy(clsr_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->comm && e->ncclCommDestroy_) e->ncclCommDestroy_(e->comm);
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_losses) cudaFreeHost(e->h_losses);
@@ -1414,6 +1486,11 @@ int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, cls
   if ((rc = zero_step_state(e))) return rc;
   if ((rc = forward(e, c, 1, (flags & CLSR_STEP_NO_BN_UPDATE) ? 0 : 1))) return rc;
   if ((rc = backward(e, c))) return rc;
+  if (e->world > 1) {
+    if ((rc = allreduce(e, e->Pg, (size_t)e->Ptot, kNcclFloat32))) return rc;
+    if ((rc = allreduce(e, e->dWd, (size_t)e->Wtot, kNcclFloat32))) return rc;
+    if ((rc = allreduce(e, e->acc, 5, kNcclFloat64))) return rc;  // data + contrastive partial sums
+  }
   if ((rc = sparse_grads(e, c))) return rc;
   blockop_kernel<<<e->n_unprep, 256, 0, e->stream>>>(e->ops_unprep, e->Pg, e->dWd);
   POST("unprep_grads");
@@ -1582,10 +1659,71 @@ int clsr_profile_entry(clsr_engine* e, int32_t i, char* name, int32_t name_cap, 
   return CLSR_OK;
 }
 
-int clsr_nccl_unique_id(void* out128) { (void)out128; return CLSR_ERR_NCCL; }
+static void* open_nccl() {
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  return h;
+}
+
+int clsr_nccl_unique_id(void* out128) {
+  void* h = open_nccl();
+  if (!h || !out128) return CLSR_ERR_NCCL;
+  typedef int (*fn_t)(void*);
+  fn_t f = (fn_t)dlsym(h, "ncclGetUniqueId");
+  if (!f) return CLSR_ERR_NCCL;
+  return f(out128) == 0 ? CLSR_OK : CLSR_ERR_NCCL;
+}
+
+// Data-parallel training over `world` ranks (one process per GPU): replicated variables, the batch
+// sharded by user-sequences.  Collectives (all on the engine stream): BatchNorm statistics in both
+// directions, the contrastive row count, dense gradients + loss partial sums, and an all-gather of the
+// sparse-gradient inputs.  Every rank must feed the same number of rows per step.
 int clsr_comm_init(clsr_engine* e, int32_t rank, int32_t world, const void* id128) {
-  (void)rank; (void)world; (void)id128;
-  return fail(e, CLSR_ERR_NCCL, "multi-GPU support is not built into this library yet");
+  if (!e || !id128 || world < 1 || rank < 0 || rank >= world) return fail(e, CLSR_ERR_ARG, "bad argument");
+  if (world == 1) return CLSR_OK;
+  if (e->comm) return fail(e, CLSR_ERR_STATE, "communicator already initialised");
+  e->nccl_lib = open_nccl();
+  if (!e->nccl_lib) return fail(e, CLSR_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+  struct Id { char b[128]; };
+  typedef int (*init_t)(void**, int, Id, int);
+  init_t init = (init_t)dlsym(e->nccl_lib, "ncclCommInitRank");
+  *(void**)(&e->ncclAllReduce_) = dlsym(e->nccl_lib, "ncclAllReduce");
+  *(void**)(&e->ncclAllGather_) = dlsym(e->nccl_lib, "ncclAllGather");
+  *(void**)(&e->ncclCommDestroy_) = dlsym(e->nccl_lib, "ncclCommDestroy");
+  *(void**)(&e->ncclGetErrorString_) = dlsym(e->nccl_lib, "ncclGetErrorString");
+  if (!init || !e->ncclAllReduce_ || !e->ncclAllGather_ || !e->ncclGetErrorString_)
+    return fail(e, CLSR_ERR_NCCL, "libnccl is missing required symbols");
+  CK(cudaSetDevice(e->cfg.device));
+  Id id;
+  memcpy(id.b, id128, 128);
+  int r = init(&e->comm, world, id, rank);
+  if (r != 0) return fail(e, CLSR_ERR_NCCL, "ncclCommInitRank failed: %s", e->ncclGetErrorString_(r));
+  e->world = world;
+  e->rank = rank;
+  // staging for the all-gathered sparse-gradient inputs and room for the global unique sets
+  const long long W = world, Bm = e->Bmax, Sm = e->Smax, T = e->T, M = Sm * T;
+  int rc;
+  if ((rc = dalloc(e, &e->l_ih, M)) || (rc = dalloc(e, &e->l_ch, M)) || (rc = dalloc(e, &e->l_users, Sm))) return rc;
+  if ((rc = dalloc(e, &e->g_ih, W * M)) || (rc = dalloc(e, &e->g_ch, W * M)) || (rc = dalloc(e, &e->g_users, W * Sm)) ||
+      (rc = dalloc(e, &e->g_items, W * Bm)) || (rc = dalloc(e, &e->g_cates, W * Bm)))
+    return rc;
+  if ((rc = dalloc(e, &e->g_dX, W * M * e->D)) || (rc = dalloc(e, &e->g_dtgt, W * Bm * e->D)) ||
+      (rc = dalloc(e, &e->g_dul, W * Sm * e->U)) || (rc = dalloc(e, &e->g_dus, W * Sm * e->U)))
+    return rc;
+  const long long rows3[3] = {e->cfg.n_items, e->cfg.n_cates, e->cfg.n_users};
+  const long long want[3] = {W * (M + Bm), W * (M + Bm), W * Sm};
+  for (int i = 0; i < 3; ++i) {
+    long long cap = want[i] < rows3[i] ? want[i] : rows3[i];
+    if (cap > e->uniq_cap[i]) {
+      e->uniq_cap[i] = cap;
+      if ((rc = dalloc(e, &e->uniq[i], cap))) return rc;
+    }
+  }
+  if ((rc = dalloc(e, &e->cg[0], e->uniq_cap[0] * e->Di)) || (rc = dalloc(e, &e->cg[1], e->uniq_cap[1] * e->Dc)) ||
+      (rc = dalloc(e, &e->cg[2], e->uniq_cap[2] * e->U)) || (rc = dalloc(e, &e->cg[3], e->uniq_cap[2] * e->U)))
+    return rc;
+  CK(cudaDeviceSynchronize());
+  return CLSR_OK;
 }
 
 }  // extern "C"

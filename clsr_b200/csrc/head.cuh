@@ -82,7 +82,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stat, int N, d
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ rstd, float* __restrict__ al,
                                        float* __restrict__ be, float* __restrict__ ga,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float add_scale) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   double s1 = stat[n], s2 = stat[N + n];
@@ -91,8 +91,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stat, int N, d
   al[n] = g * r;
   be[n] = -g * r * r * m2;
   ga[n] = -g * r * m1 + g * r * r * m2 * mu;
-  dgamma[n] += (float)s2;
-  dbeta[n] += (float)s1;
+  dgamma[n] += add_scale * (float)s2;
+  dbeta[n] += add_scale * (float)s1;
 }
 
 // ---- output units -------------------------------------------------------------------------------
@@ -200,11 +200,11 @@ __global__ void head_mid_bwd_kernel(const float* __restrict__ dmo, int ldmo, con
 // Grouped softmax loss (base_model.py:215-235) over groups of Gs consecutive rows, its gradient,
 // and pred = sigmoid(logit).  acc[0] += -(Gs/B) * sum_{label==1} log softmax.
 __global__ void softmax_loss_kernel(const float* __restrict__ logit, const float* __restrict__ labels, int Gs,
-                                    int B, float* __restrict__ dlogit, float* __restrict__ pred,
+                                    int B, int Btot, float* __restrict__ dlogit, float* __restrict__ pred,
                                     double* __restrict__ acc) {
   const int ng = B / Gs;
   float part = 0.f;
-  const float coef = (float)Gs / (float)B;
+  const float coef = (float)Gs / (float)Btot;  // Btot: rows of the global (all-rank) batch
   for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < ng; gi += gridDim.x * blockDim.x) {
     const float* lp = logit + (size_t)gi * Gs;
     float mx = -INFINITY;

@@ -331,6 +331,23 @@ class Engine:
                                           alpha.ctypes.data if with_alpha else None))
         return pred, alpha
 
+    def comm_init(self, rank, world, dist=None):
+        """Join a data-parallel group of ``world`` engines (one process per GPU).  The NCCL unique id is
+        created on rank 0 and broadcast through ``torch.distributed`` (any backend)."""
+        if world <= 1:
+            return
+        import torch.distributed as td
+        dist = dist or td
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            rc = self.lib.clsr_nccl_unique_id(buf)
+            if rc != 0:
+                raise EngineError("ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0)
+        self._check(self.lib.clsr_comm_init(self.h, rank, world, C.create_string_buffer(box[0], 128)))
+        self.world, self.rank = world, rank
+
     def synchronize(self):
         self._check(self.lib.clsr_synchronize(self.h))
 

@@ -73,11 +73,37 @@ def _t(x, dtype):
     return torch.as_tensor(np.asarray(x)).to(dtype)
 
 
+_DIST = None  # set by data_parallel(): object with .all_reduce(t) (autograd-aware sum) and .world
+
+
+class data_parallel:
+    """Context manager for the sharded-batch tests: inside it, BatchNorm statistics and the loss
+    normalisers are taken over the batch of ALL ranks (single-device semantics), which is the set of
+    exchanges the multi-GPU engine performs."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def __enter__(self):
+        global _DIST
+        _DIST = self.ctx
+
+    def __exit__(self, *a):
+        global _DIST
+        _DIST = None
+
+
 def _bn(x, p, prefix, train, cfg, stats):
     """tf.layers.batch_normalization, non-fused (base_model.py:673-679).  Statistics run
     over every axis but the last, padded positions included."""
     gamma, beta = p[prefix + "gamma"], p[prefix + "beta"]
-    if train:
+    if train and _DIST is not None:
+        flat = x.reshape(-1, x.shape[-1])
+        n = flat.shape[0] * _DIST.world
+        mean = _DIST.all_reduce(flat.sum(0)) / n
+        var = _DIST.all_reduce((flat ** 2).sum(0)) / n - mean ** 2
+        stats[prefix] = (mean.detach(), var.detach())
+    elif train:
         flat = x.reshape(-1, x.shape[-1])
         mean = flat.mean(0)
         var = ((flat - mean) ** 2).mean(0)          # biased (tf.nn.moments)
@@ -249,7 +275,10 @@ def losses(out, params, batch, cfg, dtype=torch.float64):
     labels = _t(batch["labels"], dtype).reshape(-1, G)
     sm = torch.softmax(logits, -1)
     pos = torch.where(labels == 1, sm, torch.ones_like(sm))
-    data_loss = -G * torch.log(pos).mean()
+    if _DIST is not None:   # mean over the rows of all ranks
+        data_loss = -G * torch.log(pos).sum() / (pos.numel() * _DIST.world)
+    else:
+        data_loss = -G * torch.log(pos).mean()
 
     reg = torch.zeros((), dtype=dtype)
     for e in out["embed_params"]:
@@ -262,6 +291,8 @@ def losses(out, params, batch, cfg, dtype=torch.float64):
     cm = (I["length"] > cfg.contrastive_length_threshold).to(dtype)
     afl, afs, hm, hr = I["afl"], I["afs"], I["hist_mean"], I["hist_recent"]
     den = cm.sum()
+    if _DIST is not None:
+        den = _DIST.all_reduce(den.clone()).detach()
     if cfg.contrastive_loss == "bpr":
         sp = torch.nn.functional.softplus
         l1 = (cm * sp((afl * (-hm + hr)).sum(-1))).sum() / den

@@ -71,13 +71,21 @@ def relerr(got, ref):
     return float(np.abs(got - ref).max() / scale)
 
 
+def relerr_l2(got, ref):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
 def oracle_config(G, **kw):
     from oracle.clsr_oracle import OracleConfig
     return OracleConfig(train_num_ngs=G - 1, **kw)
 
 
-def compare_step(eng, feed, prm, G, group, shapes_only=False):
-    """Run one gradient-only step on the engine and the oracle; return {name: relative error}."""
+def compare_step(eng, feed, prm, G, group, shapes_only=False, metric=None):
+    """Run one gradient-only step on the engine and the oracle; return {name: relative error}
+    (max-norm by default; ``metric=relerr_l2`` for the backward / gradient entries)."""
+    bw_err = metric or relerr
     import torch
     from oracle import clsr_oracle as O
     from clsr_b200.engine import STEP_NO_OPTIMIZER, STEP_NO_BN_UPDATE
@@ -113,10 +121,10 @@ def compare_step(eng, feed, prm, G, group, shapes_only=False):
           ("dR", (S, T, H), gs(ig["rnn_out"])), ("dX", (S, T, D), gs(ig["hist"])),
           ("dtgt", (B, D), ig["target"].numpy()), ("dul", (S, U), gs(ig["ul"])), ("dus", (S, U), gs(ig["us"]))]
     for name, shp, ref in bw:
-        res["bwd/" + name] = relerr(eng.debug(name, shp), ref)
+        res["bwd/" + name] = bw_err(eng.debug(name, shp), ref)
     dg = eng.get_dense(3)
     for name, gref in dense.items():
-        res["grad/" + name.replace("sequential/", "")] = relerr(dg[name], gref.numpy().reshape(-1))
+        res["grad/" + name.replace("sequential/", "")] = bw_err(dg[name], gref.numpy().reshape(-1))
     from clsr_b200.engine import TABLE_VARS
     for t, name in TABLE_VARS.items():
         ids, rows = eng.sparse_grad(t)
@@ -126,6 +134,6 @@ def compare_step(eng, feed, prm, G, group, shapes_only=False):
         np.add.at(dense_ref, idx.numpy(), val.numpy())
         got = np.zeros(prm[name].shape, np.float64)
         got[ids] = rows
-        res["grad/" + tab] = relerr(got, dense_ref)
+        res["grad/" + tab] = bw_err(got, dense_ref)
         res["uniq/" + tab] = float(len(ids) != len(np.unique(idx.numpy())))
     return res, losses

@@ -16,7 +16,7 @@ def main():
     feed = PU.set_lengths(feed, [1, 50, 3, 5, 6, 2], G)
     eng = PU.make_engine(prm, 3000, 40, 200, max_rows=S * G, G=G, math_mode=int(os.environ.get('MATH', 0)))
     eng.set_debug_sync(True)
-    res, losses = PU.compare_step(eng, feed, prm, G, group)
+    res, losses = PU.compare_step(eng, feed, prm, G, group, metric=PU.relerr_l2 if os.environ.get('L2') else None)
     print("losses", losses)
     bad = 0
     for k, v in res.items():
