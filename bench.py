@@ -329,6 +329,8 @@ def run_reference(a):
 
 
 if __name__ == "__main__":
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
     args = parse()
     if args.impl == "reference":
         run_reference(args)

@@ -488,10 +488,23 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
                 const EpiOp& ep, bool stats) {
   const int kpad = round16(K), npad = round16(N);
   int nstages = 2;
-  tc::Smem L = tc::smem_layout(kpad, npad, nstages);
+  // per-element epilogue operand prefetched by the producers (needs 16-byte aligned rows)
+  int eop = 0;
+  auto al16p = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if ((N & 3) == 0) {
+    if ((ep.flags & (E_RELUMASK | E_STAT_XHAT)) && (ep.ldh & 3) == 0 && al16p(ep.hpre)) eop = 1;
+    else if ((ep.flags & E_GROUPADD) && (ep.ldga & 3) == 0 && al16p(ep.ga)) eop = 2;
+    else if ((ep.flags & E_ACCUM) && (ep.ldc & 3) == 0 && al16p(ep.C)) eop = 3;
+  }
+  tc::Smem L = tc::smem_layout(kpad, npad, nstages, eop);
   if (L.total > e->tc_smem_max) {
     nstages = 1;
-    L = tc::smem_layout(kpad, npad, nstages);
+    L = tc::smem_layout(kpad, npad, nstages, eop);
+  }
+  if (L.total > e->tc_smem_max && eop) {
+    eop = 0; nstages = 2;
+    L = tc::smem_layout(kpad, npad, nstages, eop);
+    if (L.total > e->tc_smem_max) { nstages = 1; L = tc::smem_layout(kpad, npad, nstages, eop); }
   }
   if (L.total > e->tc_smem_max) return fail(e, CLSR_ERR_ARG, "tc_gemm %s: K=%d N=%d does not fit shared memory", name, K, N);
   uint32_t cols = 32;
@@ -502,8 +515,8 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   if (per_sm < 1) per_sm = 1;
   int tiles = cdiv(M, tc::kTileM);
   int grid = tiles < e->num_sms * per_sm ? tiles : e->num_sms * per_sm;
-  if (stats) tc::tc_gemm_kernel<true><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, a, W, ldw, ep);
-  else tc::tc_gemm_kernel<false><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, a, W, ldw, ep);
+  if (stats) tc::tc_gemm_kernel<true><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, a, W, ldw, ep);
+  else tc::tc_gemm_kernel<false><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, a, W, ldw, ep);
   POST(name);
   return 0;
 }

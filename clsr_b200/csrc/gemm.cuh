@@ -97,7 +97,7 @@ gemm_kernel(int M, int N, int K, AOp a, const float* __restrict__ W, int ldw, Ep
   static_assert(TM % 4 == 0, "TM must be a multiple of 4");
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ float Ws[BK][BN];
-  __shared__ float sst[STATS ? 2 : 1][STATS ? BN : 1];
+  __shared__ float part[STATS ? 2 : 1][STATS ? NTY : 1][STATS ? BN : 1];  // per row-group column partials
   __shared__ double dacc[STATS ? 2 : 1][STATS ? BN : 1];
 
   const int tid = threadIdx.x;
@@ -106,9 +106,7 @@ gemm_kernel(int M, int N, int K, AOp a, const float* __restrict__ W, int ldw, Ep
   const int ntiles = (M + BM - 1) / BM;
 
   if (STATS) {
-    for (int c = tid; c < BN; c += 256) {
-      sst[0][c] = 0.f; sst[1][c] = 0.f; dacc[0][c] = 0.0; dacc[1][c] = 0.0;
-    }
+    for (int c = tid; c < BN; c += 256) { dacc[0][c] = 0.0; dacc[1][c] = 0.0; }
     __syncthreads();
   }
 
@@ -185,15 +183,19 @@ gemm_kernel(int M, int N, int K, AOp a, const float* __restrict__ W, int ldw, Ep
       }
     }
     if (STATS) {
+      // plain stores of the per-thread partials, then one thread per column sums the NTY row groups
+      // (shared-memory fp32 atomics are CAS loops and serialise badly here)
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
-        atomicAdd(&sst[0][tx + j * NTX], s1[j]);
-        atomicAdd(&sst[1][tx + j * NTX], s2[j]);
+        part[0][ty][tx + j * NTX] = s1[j];
+        part[1][ty][tx + j * NTX] = s2[j];
       }
       __syncthreads();
       for (int c = tid; c < BN; c += 256) {
-        dacc[0][c] += (double)sst[0][c]; dacc[1][c] += (double)sst[1][c];
-        sst[0][c] = 0.f; sst[1][c] = 0.f;
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll 8
+        for (int y = 0; y < NTY; ++y) { a1 += part[0][y][c]; a2 += part[1][y][c]; }
+        dacc[0][c] += (double)a1; dacc[1][c] += (double)a2;
       }
       __syncthreads();
     }

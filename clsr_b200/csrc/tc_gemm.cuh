@@ -212,9 +212,10 @@ CLSR_DEVINL void finish8(const AOp& a, int m, int k0, int K, const Raw8& r, floa
 
 struct Smem {
   // byte offsets into dynamic shared memory
-  int w_hi, w_lo, a_stage0, a_stage_bytes, epi, bars, total;
+  int w_hi, w_lo, a_stage0, a_stage_bytes, epi, eop, eop_bytes, bars, total;
 };
-__host__ __device__ inline Smem smem_layout(int kpad, int npad, int nstages) {
+// eop != 0 reserves two [128 x npad] fp32 tiles for the prefetched epilogue operand.
+__host__ __device__ inline Smem smem_layout(int kpad, int npad, int nstages, int eop = 0) {
   Smem s;
   int wbytes = kpad * npad * 2;
   s.w_hi = 0;
@@ -222,18 +223,28 @@ __host__ __device__ inline Smem smem_layout(int kpad, int npad, int nstages) {
   s.a_stage0 = 2 * wbytes;
   s.a_stage_bytes = 2 * kTileM * kpad * 2;  // hi + lo
   s.epi = s.a_stage0 + nstages * s.a_stage_bytes;
-  s.bars = s.epi + kTileM * (kEpiCols + 1) * 4;
+  s.eop = s.epi + kTileM * (kEpiCols + 1) * 4;
+  s.eop_bytes = eop ? kTileM * npad * 4 : 0;
+  s.bars = s.eop + 2 * s.eop_bytes;
   s.total = s.bars + 128;
   return s;
 }
 
+CLSR_DEVINL void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+CLSR_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // STATS: accumulate per-column statistics into ep.stat (see gemm.cuh).
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tmem_cols, AOp a,
+tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tmem_cols, int eop_kind, AOp a,
                const float* __restrict__ W, int ldw, EpiOp ep) {
+  // eop_kind: which per-element epilogue operand the producers prefetch into shared memory with
+  // cp.async two tiles ahead (0 none, 1 hpre, 2 group-add rows, 3 old C for accumulation), so the
+  // epilogue itself issues no dependent global loads.
   extern __shared__ __align__(128) uint8_t smem[];
-  const Smem L = smem_layout(kpad, npad, nstages);
+  const Smem L = smem_layout(kpad, npad, nstages, eop_kind);
   uint8_t* w_hi = smem + L.w_hi;
   uint8_t* w_lo = smem + L.w_lo;
   float* epi = reinterpret_cast<float*>(smem + L.epi);
@@ -243,7 +254,7 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
   uint64_t* tfull = bars + 4;     // [2]
   uint64_t* tempty = bars + 6;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  __shared__ float sst[2][kEpiCols];
+  __shared__ float sst[4][2][kEpiCols];  // per epilogue warp: column partial sums of the current slab
   __shared__ double dacc[STATS ? 2 : 1][STATS ? 256 : 1];  // per-CTA column statistics across tiles
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -293,6 +304,24 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
       uint8_t* a_hi = smem + L.a_stage0 + s * L.a_stage_bytes;
       uint8_t* a_lo = a_hi + kTileM * kpad * 2;
       const int m0 = tile * kTileM;
+      if (eop_kind) {
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);  // the epilogue of tile it-2 has released this tile
+        float* dst = reinterpret_cast<float*>(smem + L.eop + acc * L.eop_bytes);
+        const int nq = N >> 2;                          // 16-byte pieces per row (N % 4 == 0 checked on the host)
+        for (int i = tid; i < kTileM * nq; i += kProducers) {
+          const int r = i / nq, q4 = (i - r * nq) * 4;
+          const int m = m0 + r;
+          if (m >= M) continue;
+          const float* src;
+          if (eop_kind == 1) src = ep.hpre + (size_t)m * ep.ldh + q4;
+          else if (eop_kind == 2) {
+            int b = m / ep.T, t = m - b * ep.T;
+            src = ep.ga + ((size_t)(b / ep.G) * ep.T + t) * ep.ldga + q4;
+          } else src = ep.C + (size_t)m * ep.ldc + q4;
+          cp_async16(dst + r * npad + q4, src);
+        }
+      }
       constexpr int UN = 4;
       for (int task0 = tid; task0 < ntask; task0 += kProducers * UN) {
         // consecutive threads take consecutive 8-element chunks of one row (coalesced 32-byte pieces);
@@ -317,6 +346,7 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
           split_store8(x, a_hi + off, a_lo + off);
         }
       }
+      if (eop_kind) cp_async_wait_all();
       fence_proxy_async();
       mbar_arrive(&full[s]);
     }
@@ -364,6 +394,7 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
       const int m0 = tile * kTileM;
       mbar_wait(&tfull[acc], pa);
       tc_fence_after();
+      const float* eop_tile = reinterpret_cast<const float*>(smem + L.eop + acc * L.eop_bytes);
       for (int c0 = 0; c0 < npad; c0 += kEpiCols) {
         float v[16];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * npad + c0);
@@ -375,7 +406,6 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
 #pragma unroll
           for (int i = 0; i < 16; ++i) epi[row * (kEpiCols + 1) + 16 + i] = v[i];
         }
-        if (STATS && et < kEpiCols) { sst[0][et] = 0.f; sst[1][et] = 0.f; }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         // cooperative finish + store with 16-byte vectors: thread -> (row er0 + 16*j, columns 4*eq..4*eq+3);
         // a warp covers four 128-byte row segments per access, EB accesses are in flight per thread
@@ -417,14 +447,20 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
                   float4 t4 = __ldg(reinterpret_cast<const float4*>(ep.rb + (size_t)(m / ep.rbT) * ep.ldrb + n));
                   x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
                 }
+                const float4* eo = reinterpret_cast<const float4*>(eop_tile + r * npad + n);
                 if (ep.flags & E_GROUPADD) {
-                  int b = m / ep.T, t = m - b * ep.T;
-                  float4 t4 = __ldg(reinterpret_cast<const float4*>(ep.ga + ((size_t)(b / ep.G) * ep.T + t) * ep.ldga + n));
+                  float4 t4;
+                  if (eop_kind == 2) t4 = *eo;
+                  else {
+                    int b = m / ep.T, t = m - b * ep.T;
+                    t4 = __ldg(reinterpret_cast<const float4*>(ep.ga + ((size_t)(b / ep.G) * ep.T + t) * ep.ldga + n));
+                  }
                   x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
                 }
                 if (ep.flags & (E_RELUMASK | E_STAT_XHAT))
-                  hp[u] = __ldg(reinterpret_cast<const float4*>(ep.hpre + (size_t)m * ep.ldh + n));
-                if (ep.flags & E_ACCUM) old[u] = *reinterpret_cast<const float4*>(ep.C + (size_t)m * ep.ldc + n);
+                  hp[u] = (eop_kind == 1) ? *eo : __ldg(reinterpret_cast<const float4*>(ep.hpre + (size_t)m * ep.ldh + n));
+                if (ep.flags & E_ACCUM)
+                  old[u] = (eop_kind == 3) ? *eo : *reinterpret_cast<const float4*>(ep.C + (size_t)m * ep.ldc + n);
               } else {
                 float* xp = &x.x; float* hpp = &hp[u].x; float* op = &old[u].x;
                 for (int i = 0; i < 4 && n + i < N; ++i) {
@@ -466,16 +502,24 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
           }
         }
         if (STATS) {
+          // the four row lanes of a warp that share a column quad are 8 lanes apart: two shuffles,
+          // then one plain store per column and warp (shared fp32 atomics are CAS loops)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            atomicAdd(&sst[0][eq * 4 + i], s1[i]);
-            atomicAdd(&sst[1][eq * 4 + i], s2[i]);
+            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 8);
+            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 16);
+            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], 8);
+            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], 16);
+          }
+          if (lane < 8) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sst[q][0][lane * 4 + i] = s1[i]; sst[q][1][lane * 4 + i] = s2[i]; }
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (STATS && et < kEpiCols && c0 + et < N) {
-          dacc[0][c0 + et] += (double)sst[0][et];
-          dacc[1][c0 + et] += (double)sst[1][et];
+          dacc[0][c0 + et] += (double)(sst[0][0][et] + sst[1][0][et] + sst[2][0][et] + sst[3][0][et]);
+          dacc[1][c0 + et] += (double)(sst[0][1][et] + sst[1][1][et] + sst[2][1][et] + sst[3][1][et]);
         }
       }
       tc_fence_before();
