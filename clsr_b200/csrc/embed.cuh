@@ -245,27 +245,42 @@ adam_sweep_kernel(float* __restrict__ var, float* __restrict__ m, float* __restr
     scale = hp.clip / fmaxf(nrm, hp.clip);
   }
   const long long nvec = rows * V;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / V;
-    int q = (int)(i - r * V);
-    int c = __ldg(slot + r);
-    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c >= 0) {
-      gv = *reinterpret_cast<const float4*>(g + (size_t)c * dim + q * 4);
-      gv.x *= scale; gv.y *= scale; gv.z *= scale; gv.w *= scale;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int UN = 4;  // 4 x 3 independent 16-byte loads in flight per thread
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * UN) {
+    float4 mv[UN], vv[UN], xv[UN];
+    int c[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long i = i0 + u * stride;
+      c[u] = -1;
+      if (i < nvec) {
+        mv[u] = ldg_stream(reinterpret_cast<const float4*>(m) + i);
+        vv[u] = ldg_stream(reinterpret_cast<const float4*>(v) + i);
+        xv[u] = ldg_stream(reinterpret_cast<const float4*>(var) + i);
+        c[u] = __ldg(slot + i / V);
+      }
     }
-    float4 mv = ldg_stream(reinterpret_cast<const float4*>(m) + i);
-    float4 vv = ldg_stream(reinterpret_cast<const float4*>(v) + i);
-    float4 xv = ldg_stream(reinterpret_cast<const float4*>(var) + i);
-#define CLSR_ADAM1(c_)                                          \
-  mv.c_ = hp.beta1 * mv.c_ + (1.f - hp.beta1) * gv.c_;          \
-  vv.c_ = hp.beta2 * vv.c_ + (1.f - hp.beta2) * gv.c_ * gv.c_;  \
-  xv.c_ -= hp.lr_t * mv.c_ / (sqrtf(vv.c_) + hp.eps);
-    CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
-    stg_stream(reinterpret_cast<float4*>(m) + i, mv);
-    stg_stream(reinterpret_cast<float4*>(v) + i, vv);
-    stg_stream(reinterpret_cast<float4*>(var) + i, xv);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) continue;
+      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c[u] >= 0) {
+        const int q = (int)(i - (i / V) * V);
+        gv = *reinterpret_cast<const float4*>(g + (size_t)c[u] * dim + q * 4);
+        gv.x *= scale; gv.y *= scale; gv.z *= scale; gv.w *= scale;
+      }
+#define CLSR_ADAM1(c_)                                                      \
+  mv[u].c_ = hp.beta1 * mv[u].c_ + (1.f - hp.beta1) * gv.c_;                \
+  vv[u].c_ = hp.beta2 * vv[u].c_ + (1.f - hp.beta2) * gv.c_ * gv.c_;        \
+  xv[u].c_ -= hp.lr_t * mv[u].c_ / (sqrtf(vv[u].c_) + hp.eps);
+      CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
+#undef CLSR_ADAM1
+      stg_stream(reinterpret_cast<float4*>(m) + i, mv[u]);
+      stg_stream(reinterpret_cast<float4*>(v) + i, vv[u]);
+      stg_stream(reinterpret_cast<float4*>(var) + i, xv[u]);
+    }
   }
 }
 
@@ -291,6 +306,10 @@ __global__ void adam_lazy_kernel(float* __restrict__ var, float* __restrict__ m,
     float4 mv = *reinterpret_cast<const float4*>(m + off);
     float4 vv = *reinterpret_cast<const float4*>(v + off);
     float4 xv = *reinterpret_cast<const float4*>(var + off);
+#define CLSR_ADAM1(c_)                                          \
+  mv.c_ = hp.beta1 * mv.c_ + (1.f - hp.beta1) * gv.c_;          \
+  vv.c_ = hp.beta2 * vv.c_ + (1.f - hp.beta2) * gv.c_ * gv.c_;  \
+  xv.c_ -= hp.lr_t * mv.c_ / (sqrtf(vv.c_) + hp.eps);
     CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
     *reinterpret_cast<float4*>(m + off) = mv;
     *reinterpret_cast<float4*>(v + off) = vv;

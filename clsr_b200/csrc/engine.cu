@@ -59,6 +59,8 @@ struct clsr_engine {
   std::string err;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t aux[2] = {nullptr, nullptr};   // side streams: the three recurrences run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   bool debug_sync = false;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -184,6 +186,28 @@ void prof_mark(clsr_engine* e, const char* name) {
       return fail(e, CLSR_ERR_CUDA, "kernel %s failed: %s (%s:%d)", name, cudaGetErrorString(_c),  \
                   __FILE__, __LINE__);                                                             \
   } while (0)
+
+// Fork the two side streams off the engine stream / join them back (the recurrent kernels are
+// latency-bound with few resident warps; running the three of them side by side fills the SMs).
+int fork_aux(clsr_engine* e) {
+  CK(cudaEventRecord(e->ev_fork, e->stream));
+  for (int i = 0; i < 2; ++i) CK(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
+  return 0;
+}
+int join_aux(clsr_engine* e, const char* name) {
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventRecord(e->ev_join[i], e->aux[i]));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_join[i], 0));
+  }
+  cudaError_t c = cudaGetLastError();
+  if (c == cudaSuccess && e->debug_sync) {
+    for (int i = 0; i < 2 && c == cudaSuccess; ++i) c = cudaStreamSynchronize(e->aux[i]);
+    if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+  }
+  if (c != cudaSuccess) return fail(e, CLSR_ERR_CUDA, "%s failed: %s", name, cudaGetErrorString(c));
+  MARK(name);
+  return 0;
+}
 
 enum { kNcclInt32 = 2, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
 
@@ -848,21 +872,23 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
                  e_store(PX + e->oO, NX, nullptr, E_ACCUM), false)))
     return rc;
 
-  // ---- recurrences ----
+  // ---- recurrences: three independent kernels, one per stream ----
   const int nblk = cdiv(S, RNN_NSEQ);
   {
+    if ((rc = fork_aux(e))) return rc;
     size_t smg = (size_t)(U * 2 * U + U * U + 3 * U * RNN_LD) * 4;
-    gru_fwd_kernel<<<nblk, RNN_THREADS, smg, st>>>(PX, NX, e->oG1, e->oC1, us, W("Wgh1"), W("Wch1"), e->d_len, S, T, U,
-                                                   e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"));
-    POST("gru_fwd_sti");
+    gru_fwd_kernel<<<nblk, RNN_THREADS, smg, e->aux[0]>>>(PX, NX, e->oG1, e->oC1, us, W("Wgh1"), W("Wch1"), e->d_len, S, T, U,
+                                                       e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"));
+    e->launches++;
     size_t smg2 = (size_t)(H * 2 * H + H * H + 3 * H * RNN_LD) * 4;
-    gru_fwd_kernel<<<nblk, RNN_THREADS, smg2, st>>>(PX, NX, e->oG2, e->oC2, nullptr, W("Wgh2"), W("Wch2"), e->d_len, S, T, H,
-                                                    e->B("g2"), e->B("c2"), e->B("hp2"), e->B("rh2"), e->B("fs"));
-    POST("gru_fwd_causal2");
+    gru_fwd_kernel<<<nblk, RNN_THREADS, smg2, e->aux[1]>>>(PX, NX, e->oG2, e->oC2, nullptr, W("Wgh2"), W("Wch2"), e->d_len, S, T, H,
+                                                        e->B("g2"), e->B("c2"), e->B("hp2"), e->B("rh2"), e->B("fs"));
+    e->launches++;
     size_t sml = (size_t)(H * 4 * H + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
     lstm_fwd_kernel<<<nblk, RNN_THREADS, sml, st>>>(PX, NX, e->oL, e->oTN, e->oTL, W("Km"), e->d_len, S, T, H,
                                                     e->B("G4"), e->B("cp"), e->B("mp"), e->B("R"));
-    POST("lstm_fwd");
+    e->launches++;
+    if ((rc = join_aux(e, "rnn_fwd(gru_sti|gru_causal2|time4lstm)"))) return rc;
   }
 
   // ---- long-term attention (all per sequence) ----
@@ -1028,18 +1054,21 @@ int backward(clsr_engine* e, const StepCtx& c) {
   MARK("memset_dPX");
   const int nblk = cdiv(S, RNN_NSEQ);
   {
+    // the three BPTT kernels write disjoint column ranges of dPX: run them side by side
+    if ((rc = fork_aux(e))) return rc;
     size_t sml = (size_t)(H * 4 * H + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
     lstm_bwd_kernel<<<nblk, RNN_THREADS, sml, st>>>(PX, NX, e->oL, e->oTN, e->oTL, e->B("G4"), e->B("cp"), W("KmT"), dR,
                                                     e->d_len, S, T, H, dPX);
-    POST("lstm_bwd");
+    e->launches++;
     size_t smg = (size_t)(2 * U * U + U * U + 5 * U * RNN_LD) * 4;
-    gru_bwd_kernel<<<nblk, RNN_THREADS, smg, st>>>(e->B("g1"), e->B("c1"), e->B("hp1"), W("Wgh1T"), W("Wch1T"), e->B("dsti"),
-                                                   e->d_len, S, T, U, dPX, NX, e->oG1, e->oC1, e->B("dus"));
-    POST("gru_bwd_sti");
+    gru_bwd_kernel<<<nblk, RNN_THREADS, smg, e->aux[0]>>>(e->B("g1"), e->B("c1"), e->B("hp1"), W("Wgh1T"), W("Wch1T"), e->B("dsti"),
+                                                       e->d_len, S, T, U, dPX, NX, e->oG1, e->oC1, e->B("dus"));
+    e->launches++;
     size_t smg2 = (size_t)(2 * H * H + H * H + 5 * H * RNN_LD) * 4;
-    gru_bwd_kernel<<<nblk, RNN_THREADS, smg2, st>>>(e->B("g2"), e->B("c2"), e->B("hp2"), W("Wgh2T"), W("Wch2T"), e->B("dfs"),
-                                                    e->d_len, S, T, H, dPX, NX, e->oG2, e->oC2, nullptr);
-    POST("gru_bwd_causal2");
+    gru_bwd_kernel<<<nblk, RNN_THREADS, smg2, e->aux[1]>>>(e->B("g2"), e->B("c2"), e->B("hp2"), W("Wgh2T"), W("Wch2T"), e->B("dfs"),
+                                                        e->d_len, S, T, H, dPX, NX, e->oG2, e->oC2, nullptr);
+    e->launches++;
+    if ((rc = join_aux(e, "rnn_bwd(time4lstm|gru_sti|gru_causal2)"))) return rc;
   }
   float *dX = e->B("dX"), *TNL = e->B("TNL"), *dTNL = e->B("dTNL");
   if ((rc = gemm(e, "dX", (int)M, D, NX, a_plain(dPX, NX), W("Wx_allT"), D, e_store(dX, D), false))) return rc;
@@ -1291,6 +1320,11 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
   e->smem_optin = (int)prop.sharedMemPerBlockOptin;
   CKCU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   e->own_stream = true;
+  for (int i = 0; i < 2; ++i) {
+    CKCU(cudaStreamCreateWithFlags(&e->aux[i], cudaStreamNonBlocking));
+    CKCU(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
+  }
+  CKCU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
 
   e->T = cfg->seq_len; e->Di = cfg->item_dim; e->Dc = cfg->cate_dim; e->D = e->Di + e->Dc; e->U = cfg->user_dim;
   e->H = cfg->hidden; e->Q = e->U + e->D; e->A0 = cfg->att0; e->A1 = cfg->att1; e->L0 = cfg->fc0; e->L1 = cfg->fc1;
@@ -1420,6 +1454,11 @@ void clsr_destroy(clsr_engine* e) {
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->h2d_done) cudaEventDestroy(e->h2d_done);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  for (int i = 0; i < 2; ++i) {
+    if (e->aux[i]) { cudaStreamSynchronize(e->aux[i]); cudaStreamDestroy(e->aux[i]); }
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   delete e;
 }
 

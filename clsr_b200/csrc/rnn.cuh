@@ -18,6 +18,17 @@ constexpr int RNN_NSEQ = 16;
 constexpr int RNN_LD = 20;  // padded row stride of the [k][seq] state tiles (16-byte aligned rows)
 constexpr int RNN_THREADS = 256;
 
+CLSR_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Software prefetch for the serial loops: the rows a CTA will read `two steps from now` are pulled
+// into L2 while the current step computes, so the per-step global loads hit L2 instead of HBM.
+// Thread `idx` (0 .. 16*lines-1) touches 128-byte line `idx % lines` of sequence `idx / lines`.
+CLSR_DEVINL void prefetch_row_lines(const float* base, size_t ld, int col0, int lines, int idx, int s0, int T,
+                                    int tt, const int* slen) {
+  const int q = idx / lines, l = idx - q * lines;
+  if (q < RNN_NSEQ && tt >= 0 && tt < slen[q]) prefetch_l2(base + ((size_t)(s0 + q) * T + tt) * ld + col0 + l * 32);
+}
+
 CLSR_DEVINL int rnn_setup_len(const int* __restrict__ len, int s0, int S, int* slen) {
   __shared__ int s_tmax;
   if (threadIdx.x == 0) s_tmax = 0;
@@ -57,7 +68,9 @@ gru_fwd_kernel(const float* __restrict__ PX, int ldpx, int colg, int colc,
   const int tmax = rnn_setup_len(len, s0, S, slen);
   const int nt1 = (RNN_NSEQ / 4) * U2, nt2 = (RNN_NSEQ / 4) * U;
 
+  const int pf_lines = (3 * U + 31) / 32 + 1;  // gates + candidate columns are contiguous in PX
   for (int t = 0; t < tmax; ++t) {
+    if (tid < RNN_NSEQ * pf_lines) prefetch_row_lines(PX, ldpx, colg, pf_lines, tid, s0, T, t + 2, slen);
     for (int task = tid; task < nt1; task += RNN_THREADS) {
       const int qg = task / U2, j = task - qg * U2;
       float px[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -158,7 +171,14 @@ gru_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ cand,
   const int tmax = rnn_setup_len(len, s0, S, slen);
   const int ntm = (RNN_NSEQ / 4) * U;
 
+  const int lg = (U2 + 31) / 32 + 1, lc = (U + 31) / 32 + 1;
   for (int t = tmax - 1; t >= 0; --t) {
+    {
+      int idx = tid;
+      if (idx < RNN_NSEQ * lg) prefetch_row_lines(gates, U2, 0, lg, idx, s0, T, t - 2, slen);
+      else if ((idx -= RNN_NSEQ * lg) < RNN_NSEQ * lc) prefetch_row_lines(cand, U, 0, lc, idx, s0, T, t - 2, slen);
+      else if ((idx -= RNN_NSEQ * lc) < RNN_NSEQ * lc) prefetch_row_lines(hprev, U, 0, lc, idx, s0, T, t - 2, slen);
+    }
     for (int e = tid; e < RNN_NSEQ * U; e += RNN_THREADS) {
       const int q = e / U, j = e - q * U;
       const float dhn = dhT[j * RNN_LD + q];
@@ -253,7 +273,9 @@ lstm_fwd_kernel(const float* __restrict__ PX, int ldpx, int colL, int colTN, int
   const int tmax = rnn_setup_len(len, s0, S, slen);
   const int nt1 = (RNN_NSEQ / 4) * H4;
 
+  const int pf_lines = (6 * H + 31) / 32 + 1;  // lstm gates + both time gates are contiguous in PX
   for (int t = 0; t < tmax; ++t) {
+    if (tid < RNN_NSEQ * pf_lines) prefetch_row_lines(PX, ldpx, colL, pf_lines, tid, s0, T, t + 2, slen);
     for (int task = tid; task < nt1; task += RNN_THREADS) {
       const int qg = task / H4, j = task - qg * H4;
       float px[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -326,7 +348,15 @@ lstm_bwd_kernel(const float* __restrict__ PX, int ldpx, int colL, int colTN, int
   const int tmax = rnn_setup_len(len, s0, S, slen);
   const int ntm = (RNN_NSEQ / 4) * H;
 
+  const int l4 = (H4 + 31) / 32 + 1, l1 = (H + 31) / 32 + 1, l2 = (2 * H + 31) / 32 + 1;
   for (int t = tmax - 1; t >= 0; --t) {
+    {
+      int idx = tid;
+      if (idx < RNN_NSEQ * l4) prefetch_row_lines(gates4, H4, 0, l4, idx, s0, T, t - 2, slen);
+      else if ((idx -= RNN_NSEQ * l4) < RNN_NSEQ * l1) prefetch_row_lines(cprev, H, 0, l1, idx, s0, T, t - 2, slen);
+      else if ((idx -= RNN_NSEQ * l1) < RNN_NSEQ * l1) prefetch_row_lines(dR, H, 0, l1, idx, s0, T, t - 2, slen);
+      else if ((idx -= RNN_NSEQ * l1) < RNN_NSEQ * l2) prefetch_row_lines(PX, ldpx, colTN, l2, idx, s0, T, t - 2, slen);
+    }
     for (int e = tid; e < RNN_NSEQ * H; e += RNN_THREADS) {
       const int q = e / H, j = e - q * H;
       float dpi = 0.f, dpj = 0.f, dpf = 0.f, dpo = 0.f;
