@@ -115,6 +115,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/r01_ncu_top_kernels.json; Taobao workload only), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_top_kernels.json")) as f:
+            t = json.load(f)["traffic"]
+    except Exception:
+        return None
+    key = {"adam_sweep": "adam_sweep (4 tables, one step)", "gather_hist": "gather_hist_kernel<4>",
+           "scatter_hist": "scatter_hist_kernel"}.get(name)
+    if key not in t:
+        return None
+    return t[key].get("dram_bytes", t[key].get("dram_bytes_per_launch_mean"))
+
+
 def algorithmic_bytes(name, S, B, T, w):
     """Algorithmic HBM bytes of one launch of the named kernel (kernel table)."""
     M, MB, D, A0, A1, NX, Q, U = S * T, B * T, 40, 80, 40, 480, 80, 40
@@ -241,14 +256,16 @@ def run_b200(a):
                    (w["n_items"] + w["n_cates"] + 2 * w["n_users"]) * 4
             gbs = rows / 1e9 / (k["ms"] * k["calls_per_step"] / 1e3)
             return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                    "traffic": None, "kernel": name, "peak_source": peak_src, "note": "all four tables, per step"}
+                    "traffic": ncu_traffic(name) if a.workload == "taobao" else None, "kernel": name,
+                    "peak_source": peak_src, "algorithmic_bytes": rows, "ms": k["ms"] * k["calls_per_step"],
+                    "note": "TF non-lazy Adam sweep, the four table launches of one step taken together"}
         if nbytes is None:
             return {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
                     "traffic": None, "kernel": name, "peak_source": peak_src}
         gbs = nbytes / 1e9 / (k["ms"] / 1e3)
         return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                "traffic": None, "kernel": name, "peak_source": peak_src, "algorithmic_bytes": nbytes,
-                "ms": k["ms"]}
+                "traffic": ncu_traffic(name) if a.workload == "taobao" else None, "kernel": name,
+                "peak_source": peak_src, "algorithmic_bytes": nbytes, "ms": k["ms"]}
     out = {
         "metric": "user-sequences/sec (CLSR training step, seq_len=%d, emb_dim=40)" % T,
         "value": S * world * a.steps / (ms / 1e3), "unit": "user-sequences/s", "n_gpus": world,

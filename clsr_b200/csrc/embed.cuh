@@ -245,9 +245,12 @@ adam_sweep_kernel(float* __restrict__ var, float* __restrict__ m, float* __restr
     scale = hp.clip / fmaxf(nrm, hp.clip);
   }
   const long long nvec = rows * V;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  constexpr int UN = 4;  // 4 x 3 independent 16-byte loads in flight per thread
-  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * UN) {
+  // each CTA walks contiguous slabs of UN*blockDim vectors: UN x 3 independent 16-byte loads in flight
+  // per thread, every warp access still one fully coalesced 512-byte piece
+  constexpr int UN = 4;
+  const long long stride = blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x * UN + threadIdx.x; i0 < nvec;
+       i0 += (long long)gridDim.x * blockDim.x * UN) {
     float4 mv[UN], vv[UN], xv[UN];
     int c[UN];
 #pragma unroll
