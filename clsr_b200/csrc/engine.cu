@@ -980,9 +980,17 @@ int backward(clsr_engine* e, const StepCtx& c) {
   if ((rc = mlp_bwd(e, e->mlp_alpha, e->B("ca"), B, e->B("ha0"), e->B("ha1"), e->B("dalogit"), e->B("dha1"), e->B("dha0"),
                     W("Wa0T"), W("Wa1T"), e->B("dca"))))
     return rc;
+  const float* bpr_gs = nullptr;
+  if (e->cfg.contrastive_kind == 1) {
+    bpr_dots_kernel<<<grid1d(e, (long long)B * 32, 256), 256, 0, st>>>(e->B("afl"), e->B("afs"), e->B("hm"), e->B("hr"), e->d_len,
+                                                                     e->cfg.contrastive_len_threshold, D, G, B, e->B("bpr_gs"),
+                                                                     e->acc);
+    POST("bpr_dots");
+    bpr_gs = e->B("bpr_gs");
+  }
   head_final_bwd_kernel<<<grid1d(e, (long long)S * D, 128), 128, 0, st>>>(
       e->B("dmo"), e->B("dca"), e->B("alpha"), e->B("afl"), e->B("afs"), e->B("hm"), e->B("hr"), e->d_len, e->counts,
-      e->cfg.contrastive_len_threshold, e->cfg.triplet_margin, e->cfg.contrastive_weight, H, D, G, S, e->B("dfs"),
+      e->cfg.contrastive_len_threshold, e->cfg.triplet_margin, e->cfg.contrastive_weight, bpr_gs, H, D, G, S, e->B("dfs"),
       e->B("dtgt"), e->B("dafl"), e->B("dafs"), e->B("dhm"), e->B("dhr"), e->acc);
   POST("head_final_bwd");
 
@@ -1292,7 +1300,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
     return fail(e, CLSR_ERR_ARG, "embedding dims must be multiples of 4 (16-byte rows)");
   if (cfg->max_rows <= 0 || cfg->seq_len <= 0 || cfg->train_group <= 0) return fail(e, CLSR_ERR_ARG, "bad sizes");
   if (cfg->att1 > 128) return fail(e, CLSR_ERR_ARG, "att_fcn_layer_sizes[1] > 128 unsupported");
-  if (cfg->contrastive_kind != 0) return fail(e, CLSR_ERR_ARG, "only the triplet contrastive loss is implemented");
+  if (cfg->contrastive_kind != 0 && cfg->contrastive_kind != 1) return fail(e, CLSR_ERR_ARG, "contrastive_kind must be 0 (triplet) or 1 (bpr)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail(e, CLSR_ERR_CUDA, "no CUDA device: clsr_b200 has no CPU fallback");
@@ -1435,6 +1443,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
       {"dmo", Bm * (H + D)}, {"dalogit", Bm}, {"dha1", Bm * A1}, {"dha0", Bm * A0}, {"dca", Bm * CA},
       {"dfs", Sm * H}, {"dtgt", Bm * D}, {"dafl", Sm * D}, {"dafs", Bm * H}, {"dhm", Sm * D}, {"dhr", Sm * D},
       {"dsti", Sm * U}, {"dus", Sm * U}, {"dul", Sm * U}, {"dqbs", Bm * A0}, {"dqs", Bm * Q}, {"dqbl", Sm * A0},
+      {"bpr_gs", Bm * 4},
   };
   for (auto& s : specs) CKC(fbuf(e, s.n, s.sz));
   CKCU(cudaDeviceSynchronize());

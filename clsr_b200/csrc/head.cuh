@@ -230,6 +230,43 @@ __global__ void sigmoid_kernel(const float* __restrict__ x, int n, float* __rest
     y[i] = sigmoid_acc(x[i]);
 }
 
+// BPR contrastive loss (clsr.py:53-57), per row: x1 = afl.(hr-hm), x2 = afs.(hm-hr), x3 = hm.(afs-afl),
+// x4 = hr.(afl-afs); loss terms softplus(x_i); gs[b,i] = sigmoid(x_i) (the derivative) for the backward.
+// One warp per row; acc[1..4] += sum over rows of mask*softplus(x_i).
+__global__ void bpr_dots_kernel(const float* __restrict__ afl, const float* __restrict__ afs,
+                                const float* __restrict__ hm, const float* __restrict__ hr,
+                                const int32_t* __restrict__ len, int thr, int D, int G, int B,
+                                float* __restrict__ gs, double* __restrict__ acc) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f;
+  for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += gridDim.x * wpb) {
+    const int s = b / G;
+    float x1 = 0.f, x2 = 0.f, x3 = 0.f, x4 = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      float l = afl[(size_t)s * D + d], sh = afs[(size_t)b * D + d], m = hm[(size_t)s * D + d], r = hr[(size_t)s * D + d];
+      x1 = fmaf(l, r - m, x1); x2 = fmaf(sh, m - r, x2); x3 = fmaf(m, sh - l, x3); x4 = fmaf(r, l - sh, x4);
+    }
+    x1 = warp_sum(x1); x2 = warp_sum(x2); x3 = warp_sum(x3); x4 = warp_sum(x4);
+    if (lane == 0) {
+      const float cm = (len[s] > thr) ? 1.f : 0.f;
+      const float xs[4] = {x1, x2, x3, x4};
+      float sp[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sp[i] = fmaxf(xs[i], 0.f) + log1pf(expf(-fabsf(xs[i])));
+        gs[(size_t)b * 4 + i] = sigmoid_acc(xs[i]);
+      }
+      l1 += cm * sp[0]; l2 += cm * sp[1]; l3 += cm * sp[2]; l4 += cm * sp[3];
+    }
+  }
+  if (lane == 0) {
+    if (l1 != 0.f) atomicAdd(acc + 1, (double)l1);
+    if (l2 != 0.f) atomicAdd(acc + 2, (double)l2);
+    if (l3 != 0.f) atomicAdd(acc + 3, (double)l3);
+    if (l4 != 0.f) atomicAdd(acc + 4, (double)l4);
+  }
+}
+
 // Everything that fans out of the head, one thread per (sequence, channel), looping the G rows of
 // the group: gradients of the fusion, of concat_all / model_output, and of the triplet contrastive
 // loss (clsr.py:58-71) whose value is accumulated in acc[1..4].
@@ -239,7 +276,8 @@ __global__ void head_final_bwd_kernel(const float* __restrict__ dmo, const float
                                       const float* __restrict__ afs, const float* __restrict__ hm,
                                       const float* __restrict__ hr, const int32_t* __restrict__ len,
                                       const int32_t* __restrict__ counts, int thr, float margin, float cw,
-                                      int H, int D, int G, int S, float* __restrict__ dfs,
+                                      const float* __restrict__ bpr_gs, int H, int D, int G, int S,
+                                      float* __restrict__ dfs,
                                       float* __restrict__ dtgt, float* __restrict__ dafl,
                                       float* __restrict__ dafs, float* __restrict__ dhm,
                                       float* __restrict__ dhr, double* __restrict__ acc) {
@@ -261,6 +299,17 @@ __global__ void head_final_bwd_kernel(const float* __restrict__ dmo, const float
       dtgt[b * D + d] = dmo[b * W + H + d] + dca[b * CA + H + d];
       float dl = dca[b * CA + H + D + d] + due * a;
       float ds = dca[b * CA + H + 2 * D + d] + due * (1.f - a);
+      if (bpr_gs) {  // BPR: gradients through the four inner products, derivative = sigmoid(x_i)
+        const float g1 = c * bpr_gs[b * 4 + 0], g2 = c * bpr_gs[b * 4 + 1], g3 = c * bpr_gs[b * 4 + 2],
+                    g4 = c * bpr_gs[b * 4 + 3];
+        dl += g1 * (r - m) - g3 * m + g4 * r;
+        ds += g2 * (m - r) + g3 * m - g4 * r;
+        sm += -g1 * l + g2 * sh + g3 * (sh - l);
+        sr += g1 * l - g2 * sh + g4 * (l - sh);
+        sl += dl;
+        dafs[b * H + d] = ds;
+        continue;
+      }
       const float elm = l - m, elr = l - r, esm = sh - m, esr = sh - r;
       const float dlm = elm * elm, dlr = elr * elr, dsm = esm * esm, dsr = esr * esr;
       const float v1 = dlm - dlr + margin, v2 = dsr - dsm + margin, v3 = dlm - dsm + margin,
@@ -280,7 +329,7 @@ __global__ void head_final_bwd_kernel(const float* __restrict__ dmo, const float
     dfs[i] = sfs; dafl[i] = sl; dhm[i] = sm; dhr[i] = sr;
   }
   l1 = warp_sum(l1); l2 = warp_sum(l2); l3 = warp_sum(l3); l4 = warp_sum(l4);
-  if ((threadIdx.x & 31) == 0) {
+  if ((threadIdx.x & 31) == 0 && !bpr_gs) {
     atomicAdd(acc + 1, (double)l1); atomicAdd(acc + 2, (double)l2);
     atomicAdd(acc + 3, (double)l3); atomicAdd(acc + 4, (double)l4);
   }

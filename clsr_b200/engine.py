@@ -170,13 +170,13 @@ class Engine:
         self.lib = load_library()
         if optimizer not in ("adam", "lazyadam"):
             raise EngineError("optimizer %r is not implemented on the B200 path (adam, lazyadam)" % optimizer)
-        if contrastive_loss not in ("triplet",):
-            raise EngineError("contrastive_loss %r is not implemented on the B200 path" % contrastive_loss)
+        if contrastive_loss not in ("triplet", "bpr"):
+            raise EngineError("contrastive_loss %r is not defined (triplet, bpr)" % contrastive_loss)
         self.cfg = Config(
             device=device, max_rows=max_rows, seq_len=seq_len, item_dim=item_dim, cate_dim=cate_dim,
             user_dim=user_dim, hidden=hidden, att0=att_sizes[0], att1=att_sizes[1], fc0=layer_sizes[0],
             fc1=layer_sizes[1], n_items=n_items, n_cates=n_cates, n_users=n_users, train_group=train_group,
-            embed_l2=embed_l2, layer_l2=layer_l2, contrastive_kind=0, triplet_margin=triplet_margin,
+            embed_l2=embed_l2, layer_l2=layer_l2, contrastive_kind=1 if contrastive_loss == "bpr" else 0, triplet_margin=triplet_margin,
             contrastive_weight=contrastive_weight, discrepancy_weight=discrepancy_weight,
             contrastive_len_threshold=contrastive_len_threshold, contrastive_recent_k=contrastive_recent_k,
             optimizer=0 if optimizer == "adam" else 1, learning_rate=learning_rate, beta1=0.9, beta2=0.999,

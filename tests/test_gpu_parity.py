@@ -59,6 +59,29 @@ def test_step_matches_oracle_tensor_core_path(cuda_lib, group):
     assert not bad, bad
 
 
+def test_bpr_contrastive_loss(cuda_lib):
+    """contrastive_loss='bpr' (clsr.py:53-57), the create_hparams default."""
+    import torch
+    from oracle import clsr_oracle as O
+    from clsr_b200.engine import STEP_NO_OPTIMIZER, STEP_NO_BN_UPDATE
+    G, S = 5, 20
+    feed, prm = PU.small_problem(S=S, G=G, seed=8)
+    eng = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, G=G, contrastive_loss="bpr")
+    got = eng.train_step(feed, group=G, flags=STEP_NO_OPTIMIZER | STEP_NO_BN_UPDATE)
+    cfg = PU.oracle_config(G, contrastive_loss="bpr")
+    out, L, dense, slices, ig = O.compute_gradients(prm, feed, cfg, torch.float64, retain=["afl", "afs", "hist_mean"])
+    for k in ("loss", "contrastive_loss", "data_loss"):
+        assert abs(got[k] - float(L[k])) < 2e-5 * max(abs(float(L[k])), 1e-3), (k, got[k], float(L[k]))
+    D = 40
+    gs = lambda a: a.numpy().reshape(S, G, *a.shape[1:]).sum(1)
+    assert PU.relerr(eng.debug("dafs", (S * G, D)), ig["afs"].numpy()) < BWD_TOL
+    assert PU.relerr(eng.debug("dafl", (S, D)), gs(ig["afl"])) < BWD_TOL
+    assert PU.relerr(eng.debug("dhm", (S, D)), gs(ig["hist_mean"])) < BWD_TOL
+    dg = eng.get_dense(3)
+    for name in ("sequential/clsr/long_term/attention_fcn/attention_mat", "sequential/logit_fcn/nn_part/w_nn_layer0"):
+        assert PU.relerr(dg[name], dense[name].numpy().reshape(-1)) < BWD_TOL, name
+
+
 def test_ragged_batch_and_long_window(cuda_lib):
     """Row count not a multiple of any tile size, T = 250 (Kuaishou window)."""
     G, S, T = 5, 13, 250
