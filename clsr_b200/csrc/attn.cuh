@@ -81,10 +81,12 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
                 int Dv, const float* __restrict__ h1, int A1, const float* __restrict__ scale,
                 const float* __restrict__ shift, const float* __restrict__ mean,
                 const float* __restrict__ rstd, const float* __restrict__ wout,
-                const int* __restrict__ len, int nseq, int T, int G, float* __restrict__ dy1,
+                const int* __restrict__ len, int nseq, int T, int G, int vdiv, float* __restrict__ dy1,
                 double* __restrict__ stat, float* __restrict__ dwout, float* __restrict__ dbout,
                 float* __restrict__ dV, int dV_accum, const float* __restrict__ dhm,
                 const float* __restrict__ dhr, int recent_k) {
+  // vdiv > 1: every "sequence" index here is a single row (G == 1) whose values / length belong to
+  // sequence s / vdiv; dV is then produced by pool_dv_kernel (dV == nullptr here).
   extern __shared__ float sm[];
   const int wpb = blockDim.x >> 5;
   float* s_scale = sm;
@@ -109,7 +111,8 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
   for (int i = 0; i < MAXSLOT; ++i) { st1[i] = 0.f; st2[i] = 0.f; dwo[i] = 0.f; }
 
   for (int s = blockIdx.x * wpb + wid; s < nseq; s += gridDim.x * wpb) {
-    const int L = len[s];
+    const int sv = s / vdiv;
+    const int L = len[sv];
     const int kk = min(L, recent_k);
     for (int g = 0; g < G; ++g) {
       const size_t row = (size_t)s * G + g;
@@ -119,7 +122,7 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
       for (int t = lane; t < T; t += 32) {
         float dwt = 0.f, wt = 0.f;
         if (t < L) {
-          const float* vp = V + ((size_t)s * T + t) * Dv;
+          const float* vp = V + ((size_t)sv * T + t) * Dv;
           for (int d = 0; d < Dv; ++d) dwt = fmaf(dat[d], vp[d], dwt);
           wt = w[row * T + t];
           dot = fmaf(wt, dwt, dot);
@@ -153,7 +156,7 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
           }
         }
       }
-      for (int d = lane; d < Dv; d += 32) {
+      for (int d = lane; dV && d < Dv; d += 32) {
         const float da = dat[d];
         const float pm = dhm ? dhm[(size_t)s * Dv + d] / (float)L : 0.f;
         const float pr = dhr ? dhr[(size_t)s * Dv + d] / (float)kk : 0.f;
@@ -187,6 +190,27 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
     atomicAdd(dwout + i, s_acc[2 * A1 + i]);
   }
   if (threadIdx.x == 0) atomicAdd(dbout, s_acc[3 * A1]);
+}
+
+// dV[s,t,:] = sum_g w[(s*G+g), t] * datt[(s*G+g), :]  for t < len[s], zero beyond (values gradient of
+// the short-term attention, summed over the rows of a group).  One thread per (s, t, d).
+__global__ void pool_dv_kernel(const float* __restrict__ w, const float* __restrict__ datt,
+                               const int* __restrict__ len, int S, int T, int G, int Dv, float* __restrict__ dV) {
+  long long n = (long long)S * T * Dv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int d = (int)(i % Dv);
+    long long st = i / Dv;
+    int t = (int)(st % T), s = (int)(st / T);
+    float acc = 0.f;
+    if (t < len[s]) {
+      for (int g = 0; g < G; ++g) {
+        size_t b = (size_t)s * G + g;
+        acc = fmaf(w[b * T + t], datt[b * Dv + d], acc);
+      }
+    }
+    dV[i] = acc;
+  }
 }
 
 // dh0 = al*dy0 + be*h0 + ga (BatchNorm backward of the first attention layer), reduced two ways:

@@ -1001,11 +1001,15 @@ int backward(clsr_engine* e, const StepCtx& c) {
   {
     int wpb = 4;
     size_t sm = (size_t)(5 * A1 + 3 * A1 + 1 + wpb * (2 * T + H)) * 4;
-    pool_bwd_kernel<<<grid1d(e, cdiv(S, wpb), 1, 8), 128, sm, st>>>(
+    // one warp per ROW (5x the parallelism of one warp per group); the group sum of the values
+    // gradient is a separate small kernel
+    pool_bwd_kernel<<<grid1d(e, cdiv(B, wpb), 1, 16), 128, sm, st>>>(
         e->B("dafs"), e->B("ws"), R, H, h1s, A1, ms.bn1.scale, ms.bn1.shift, ms.bn1.mean, ms.bn1.rstd, e->P + ms.wo,
-        e->d_len, S, T, G, dy1s, ms.bn1.stat_b, e->Pg + ms.wo, e->Pg + ms.bo, dR, 0, nullptr, nullptr,
+        e->d_len, B, T, 1, G, dy1s, ms.bn1.stat_b, e->Pg + ms.wo, e->Pg + ms.bo, nullptr, 0, nullptr, nullptr,
         e->cfg.contrastive_recent_k);
     POST("pool_bwd_short");
+    pool_dv_kernel<<<grid1d(e, M * H, 256), 256, 0, st>>>(e->B("ws"), e->B("dafs"), e->d_len, S, T, G, H, dR);
+    POST("pool_dv_short");
   }
   if ((rc = bn_bwd(e, ms.bn1, (double)MB))) return rc;
   {
@@ -1087,7 +1091,8 @@ int backward(clsr_engine* e, const StepCtx& c) {
     return rc;
   {
     int ppc = cdiv(M, (long long)e->num_sms * 4);
-    time_feat_bwd_kernel<<<cdiv(M, ppc), ((2 * H + 31) / 32) * 32, 0, st>>>(
+    int nx = ((2 * H + 31) / 32) * 32, ny = 1024 / nx > 8 ? 8 : (1024 / nx > 0 ? 1024 / nx : 1);
+    time_feat_bwd_kernel<<<cdiv(M, ppc), dim3(nx, ny), (size_t)2 * ny * 2 * H * 4, st>>>(
         dTNL, TNL, c.ttn, c.tfa, c.seq_stride, T, H, M, ppc, e->Pg + e->p_tw1, e->Pg + e->p_tb1, e->Pg + e->p_tw2,
         e->Pg + e->p_tb2);
     POST("time_feat_bwd");
@@ -1107,7 +1112,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
     size_t sm = (size_t)(5 * A1 + 3 * A1 + 1 + wpb * (2 * T + D)) * 4;
     pool_bwd_kernel<<<grid1d(e, cdiv(S, wpb), 1, 8), 128, sm, st>>>(
         e->B("dafl"), e->B("wl"), X, D, h1l, A1, ml.bn1.scale, ml.bn1.shift, ml.bn1.mean, ml.bn1.rstd, e->P + ml.wo,
-        e->d_len, S, T, 1, dy1l, ml.bn1.stat_b, e->Pg + ml.wo, e->Pg + ml.bo, dX, 1, e->B("dhm"), e->B("dhr"),
+        e->d_len, S, T, 1, 1, dy1l, ml.bn1.stat_b, e->Pg + ml.wo, e->Pg + ml.bo, dX, 1, e->B("dhm"), e->B("dhr"),
         e->cfg.contrastive_recent_k);
     POST("pool_bwd_long");
   }

@@ -426,29 +426,39 @@ __global__ void time_feat_kernel(const float* __restrict__ ttn, const float* __r
 }
 
 // Gradients of the four time-input vectors: dpre = dTNL*(1-TNL^2); dw += sum dpre*time, db += sum dpre.
-// blockDim.x = 2H (one column per thread), each CTA reduces a slab of positions.
+// blockDim = (NX >= 2H channels, NY row lanes); each CTA reduces a slab of positions: the NY row lanes
+// stride through the slab (coalesced 2H-wide rows), then combine through shared memory.
 __global__ void time_feat_bwd_kernel(const float* __restrict__ dTNL, const float* __restrict__ TNL,
                                      const float* __restrict__ ttn, const float* __restrict__ tfa,
                                      int seq_stride, int T, int H, long long npos, int pos_per_cta,
                                      float* __restrict__ dw1, float* __restrict__ db1,
                                      float* __restrict__ dw2, float* __restrict__ db2) {
+  extern __shared__ float red[];  // [2][NY][2H]
   const int H2 = 2 * H;
-  const int j = threadIdx.x;
-  if (j >= H2) return;
+  const int j = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
   long long p0 = (long long)blockIdx.x * pos_per_cta;
   long long p1 = min(npos, p0 + pos_per_cta);
   float aw = 0.f, ab = 0.f;
-  for (long long p = p0; p < p1; ++p) {
-    long long s = p / T;
-    long long io = s * seq_stride + (p - s * T);
-    float y = TNL[p * H2 + j];
-    float d = dTNL[p * H2 + j] * (1.f - y * y);
-    float tm = (j < H) ? ttn[io] : tfa[io];
-    aw = fmaf(d, tm, aw);
-    ab += d;
+  if (j < H2) {
+    for (long long p = p0 + ty; p < p1; p += ny) {
+      long long s = p / T;
+      long long io = s * seq_stride + (p - s * T);
+      float y = TNL[p * H2 + j];
+      float d = dTNL[p * H2 + j] * (1.f - y * y);
+      float tm = (j < H) ? ttn[io] : tfa[io];
+      aw = fmaf(d, tm, aw);
+      ab += d;
+    }
+    red[(0 * ny + ty) * H2 + j] = aw;
+    red[(1 * ny + ty) * H2 + j] = ab;
   }
-  if (j < H) { atomicAdd(dw1 + j, aw); atomicAdd(db1 + j, ab); }
-  else { atomicAdd(dw2 + j - H, aw); atomicAdd(db2 + j - H, ab); }
+  __syncthreads();
+  if (j < H2 && ty == 0) {
+    float sw = 0.f, sb = 0.f;
+    for (int y = 0; y < ny; ++y) { sw += red[(0 * ny + y) * H2 + j]; sb += red[(1 * ny + y) * H2 + j]; }
+    if (j < H) { atomicAdd(dw1 + j, sw); atomicAdd(db1 + j, sb); }
+    else { atomicAdd(dw2 + j - H, sw); atomicAdd(db2 + j - H, sb); }
+  }
 }
 
 }  // namespace clsr
