@@ -512,29 +512,30 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
                 const EpiOp& ep, bool stats) {
   const int kpad = round16(K), npad = round16(N);
   int nstages = 2;
-  // per-element epilogue operand prefetched by the producers (needs 16-byte aligned rows)
+  // per-element epilogue operand prefetched by bulk copy: needs contiguous, 16-byte aligned rows
   int eop = 0;
   auto al16p = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
   if ((N & 3) == 0) {
-    if ((ep.flags & (E_RELUMASK | E_STAT_XHAT)) && (ep.ldh & 3) == 0 && al16p(ep.hpre)) eop = 1;
-    else if ((ep.flags & E_GROUPADD) && (ep.ldga & 3) == 0 && al16p(ep.ga)) eop = 2;
-    else if ((ep.flags & E_ACCUM) && (ep.ldc & 3) == 0 && al16p(ep.C)) eop = 3;
+    if ((ep.flags & (E_RELUMASK | E_STAT_XHAT)) && ep.ldh == N && al16p(ep.hpre)) eop = 1;
+    else if ((ep.flags & E_GROUPADD) && ep.ldga == N && al16p(ep.ga)) eop = 2;
+    else if ((ep.flags & E_ACCUM) && ep.ldc == N && al16p(ep.C)) eop = 3;
   }
-  tc::Smem L = tc::smem_layout(kpad, npad, nstages, eop);
+  const int st = stats ? 1 : 0;
+  tc::Smem L = tc::smem_layout(kpad, npad, N, nstages, eop, st);
   if (L.total > e->tc_smem_max) {
     nstages = 1;
-    L = tc::smem_layout(kpad, npad, nstages, eop);
+    L = tc::smem_layout(kpad, npad, N, nstages, eop, st);
   }
   if (L.total > e->tc_smem_max && eop) {
     eop = 0; nstages = 2;
-    L = tc::smem_layout(kpad, npad, nstages, eop);
-    if (L.total > e->tc_smem_max) { nstages = 1; L = tc::smem_layout(kpad, npad, nstages, eop); }
+    L = tc::smem_layout(kpad, npad, N, nstages, eop, st);
+    if (L.total > e->tc_smem_max) { nstages = 1; L = tc::smem_layout(kpad, npad, N, nstages, eop, st); }
   }
   if (L.total > e->tc_smem_max) return fail(e, CLSR_ERR_ARG, "tc_gemm %s: K=%d N=%d does not fit shared memory", name, K, N);
   uint32_t cols = 32;
   while ((int)cols < 2 * npad) cols <<= 1;
   int per_sm = e->smem_optin / (L.total + 6 * 1024);
-  if (per_sm > 1) per_sm = 1;  // 416 threads x 128 registers: one resident CTA per SM
+  if (per_sm > 1) per_sm = 1;  // 544 threads: one resident CTA per SM
   if (per_sm * (int)cols > 512) per_sm = 512 / (int)cols;
   if (per_sm < 1) per_sm = 1;
   int tiles = cdiv(M, tc::kTileM);
