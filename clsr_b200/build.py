@@ -26,6 +26,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
         [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd += os.environ.get("CLSR_NVCC_EXTRA", "").split()   # developer knobs (-DCLSR_TC_UN1=8 ...)
     if os.environ.get("CLSR_NCCL", "1") != "0" and os.path.exists("/usr/include/nccl.h"):
         cmd += ["-DCLSR_WITH_NCCL"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -533,7 +533,7 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   }
   if (L.total > e->tc_smem_max) return fail(e, CLSR_ERR_ARG, "tc_gemm %s: K=%d N=%d does not fit shared memory", name, K, N);
   uint32_t cols = 32;
-  while ((int)cols < 2 * npad) cols <<= 1;
+  while ((int)cols < (stats ? 4 : 2) * npad) cols <<= 1;   // two accumulators (+ two statistic regions)
   int per_sm = e->smem_optin / (L.total + 6 * 1024);
   if (per_sm > 1) per_sm = 1;  // 544 threads: one resident CTA per SM
   if (per_sm * (int)cols > 512) per_sm = 512 / (int)cols;
@@ -552,7 +552,7 @@ bool tc_eligible(clsr_engine* e, const char* name, int M, int N, int K, const AO
     std::string list = std::string(",") + only + ",";
     if (list.find(std::string(",") + name + ",") == std::string::npos) return false;
   }
-  if (N > 256 && stats) return false;
+  if (N > 128 && stats) return false;   // accumulators + per-row statistics must fit 512 TMEM columns
   if (K > 160 && a.mode != A_PLAIN) return false;
   return true;
 }

@@ -30,10 +30,22 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "gemm.cuh"
 
 namespace clsr {
 namespace tc {
+
+#ifndef CLSR_TC_UN1
+#define CLSR_TC_UN1 8   // pieces in flight per producer thread, one-stream operands (32 bytes each)
+#endif
+#ifndef CLSR_TC_UN2
+#define CLSR_TC_UN2 4   // two-stream operands (64 bytes each)
+#endif
+#ifndef CLSR_TC_PREFETCH
+#define CLSR_TC_PREFETCH 3   // tiles of L2 prefetch distance (0 = off)
+#endif
 
 constexpr int kTileM = 128;
 constexpr int kProducers = 224;                         // warps 0-6
@@ -57,12 +69,12 @@ CLSR_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "CLSR_WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra CLSR_WAIT_DONE;\n"
       "bra CLSR_WAIT_LOOP;\n"
       "CLSR_WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)   // suspend-time hint: park the warp instead of spinning on issue slots
       : "memory");
 }
 // 1-D bulk copy global -> shared; completion is counted in bytes on an mbarrier.
@@ -71,6 +83,10 @@ CLSR_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// L2 prefetch of a contiguous byte range (no shared-memory destination, no completion tracking)
+CLSR_DEVINL void l2_prefetch(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 CLSR_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 CLSR_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -110,6 +126,36 @@ CLSR_DEVINL void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// Three 16-column loads (accumulator chunk + the two per-thread statistic accumulators) and one wait.
+CLSR_DEVINL void tmem_ld16x3(uint32_t t0, uint32_t t1, uint32_t t2, float* a, float* b, float* c) {
+  uint32_t r[48];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%48];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%49];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47}, [%50];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
+      : "r"(t0), "r"(t1), "r"(t2)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[16 + i]); c[i] = __uint_as_float(r[32 + i]); }
+}
+CLSR_DEVINL void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+CLSR_DEVINL void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4, [16,30) leading (K-direction) byte offset >> 4,
@@ -206,118 +252,106 @@ CLSR_DEVINL Fast fast_eligible(const AOp& a) {
   return f;
 }
 
-struct Raw8 {
-  F8 a, b;
-};
-
+// Loads of one piece (row m, columns k0..k0+7).  `second` selects the second half of a concatenated
+// operand (thread-constant: every thread keeps one plane for the whole tile).
 template <int MODE, bool V256>
-CLSR_DEVINL void issue8(const AOp& a, int m, int k0, Raw8& r) {
+CLSR_DEVINL void load_piece(const AOp& a, int m, int k0, bool second, F8& ra, F8& rb) {
   if (MODE == A_PLAIN || MODE == A_BNRELU) {
-    r.a = ld8<V256>(a.A + (size_t)m * a.lda + k0);
+    ra = ld8<V256>(a.A + (size_t)m * a.lda + k0);
   } else if (MODE == A_AFFINE2) {
-    r.a = ld8<V256>(a.A + (size_t)m * a.lda + k0);
-    r.b = ld8<V256>(a.A2 + (size_t)m * a.lda2 + k0);
+    ra = ld8<V256>(a.A + (size_t)m * a.lda + k0);
+    rb = ld8<V256>(a.A2 + (size_t)m * a.lda2 + k0);
   } else if (MODE == A_CATMUL) {
-    if (k0 < a.W1) {
-      r.a = ld8<V256>(a.A + (size_t)m * a.lda + k0);
+    if (!second) {
+      ra = ld8<V256>(a.A + (size_t)m * a.lda + k0);
+      rb = ra;
     } else {
       const int kk = k0 - a.W1;
-      r.a = ld8<V256>(a.A + (size_t)m * a.lda + a.off + kk);
-      r.b = ld8<V256>(a.A2 + (size_t)(m / a.T) * a.lda2 + kk);
+      ra = ld8<V256>(a.A + (size_t)m * a.lda + a.off + kk);
+      rb = ld8<V256>(a.A2 + (size_t)(m / a.T) * a.lda2 + kk);
     }
   } else if (MODE == A_MULROW) {
     const int b = m / a.T, t = m - b * a.T, sq = b / a.G;
-    r.a = ld8<V256>(a.A + ((size_t)sq * a.T + t) * a.lda + a.off + k0);
-    r.b = ld8<V256>(a.A2 + (size_t)b * a.lda2 + k0);
+    ra = ld8<V256>(a.A + ((size_t)sq * a.T + t) * a.lda + a.off + k0);
+    rb = ld8<V256>(a.A2 + (size_t)b * a.lda2 + k0);
   } else {  // A_CAT2ROW
-    if (k0 < a.W1) r.a = ld8<V256>(a.A + (size_t)(m / a.G) * a.lda + k0);
-    else r.a = ld8<V256>(a.A2 + (size_t)m * a.lda2 + (k0 - a.W1));
+    if (!second) ra = ld8<V256>(a.A + (size_t)(m / a.G) * a.lda + k0);
+    else ra = ld8<V256>(a.A2 + (size_t)m * a.lda2 + (k0 - a.W1));
   }
 }
 
-// sv: shared-memory copy of the per-column prologue vectors, sv[j * svld + k] = a.vj[k]
-template <int MODE>
-CLSR_DEVINL void finish8(const AOp& a, const float* sv, int svld, int k0, const Raw8& r, float* x) {
-  const float v[8] = {r.a.lo.x, r.a.lo.y, r.a.lo.z, r.a.lo.w, r.a.hi.x, r.a.hi.y, r.a.hi.z, r.a.hi.w};
-  if (MODE == A_PLAIN || MODE == A_CAT2ROW) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = v[i];
-  } else if (MODE == A_BNRELU) {
-    const float4 s0 = *reinterpret_cast<const float4*>(sv + k0), s1 = *reinterpret_cast<const float4*>(sv + k0 + 4);
-    const float4 t0 = *reinterpret_cast<const float4*>(sv + svld + k0), t1 = *reinterpret_cast<const float4*>(sv + svld + k0 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = fmaxf(0.f, fmaf(v[i], sc[i], sh[i]));
-  } else if (MODE == A_AFFINE2) {
-    const float h[8] = {r.b.lo.x, r.b.lo.y, r.b.lo.z, r.b.lo.w, r.b.hi.x, r.b.hi.y, r.b.hi.z, r.b.hi.w};
-    const float4 s0 = *reinterpret_cast<const float4*>(sv + k0), s1 = *reinterpret_cast<const float4*>(sv + k0 + 4);
-    const float4 t0 = *reinterpret_cast<const float4*>(sv + svld + k0), t1 = *reinterpret_cast<const float4*>(sv + svld + k0 + 4);
-    const float4 u0 = *reinterpret_cast<const float4*>(sv + 2 * svld + k0), u1 = *reinterpret_cast<const float4*>(sv + 2 * svld + k0 + 4);
-    const float c0[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float c1[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-    const float c2[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = fmaf(c0[i], v[i], fmaf(c1[i], h[i], c2[i]));
-  } else if (MODE == A_CATMUL) {
-    if (k0 < a.W1) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = v[i];
-    } else {
-      const float h[8] = {r.b.lo.x, r.b.lo.y, r.b.lo.z, r.b.lo.w, r.b.hi.x, r.b.hi.y, r.b.hi.z, r.b.hi.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = v[i] * h[i];
-    }
-  } else {  // A_MULROW
-    const float h[8] = {r.b.lo.x, r.b.lo.y, r.b.lo.z, r.b.lo.w, r.b.hi.x, r.b.hi.y, r.b.hi.z, r.b.hi.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = v[i] * h[i];
-  }
-}
-
-// Fast pieces of one 128-row tile: 16 row-octets x nfull planes of "octet tasks"; an octet of eight
-// consecutive threads takes eight consecutive rows of one plane (conflict-free 128-byte store), the
-// four octets of a warp take neighbouring planes of the same rows (contiguous 128 bytes per row).
+// Fast pieces of one 128-row tile.  Octet o of eight consecutive threads owns plane o % nfull and the
+// row octets o / nfull, + per, + 2 per, ... (per = octets per plane): the plane, its prologue vectors
+// and the address strides are loop constants, eight consecutive threads write eight consecutive rows
+// of one plane (conflict-free 128-byte store) and the four octets of a warp read neighbouring
+// 32-byte pieces of the same rows.  Loads are always issued from a clamped row (a predicated load
+// would keep its destination registers live across the whole kernel).
 template <int MODE, bool V256>
 CLSR_DEVINL void produce_fast(const AOp& a, const float* sv, int svld, int m0, int M, int nfull, int ptid, int nprod,
                               uint32_t hi, uint32_t lo) {
-  if (nfull <= 0) return;
-  const int rl = ptid & 7, o = ptid >> 3, noct = nprod >> 3;
-  const int ntask = 16 * nfull;
-  int cc = o % nfull, ro = o / nfull;
-  const int dcc = noct % nfull, dro = noct / nfull;
-  // pieces in flight per thread: 4 x 32 bytes (one stream) or 2 x 64 bytes (two streams)
-  constexpr int UN = (MODE == A_AFFINE2 || MODE == A_CATMUL || MODE == A_MULROW) ? 2 : 4;
+  const int noct = nprod >> 3;
+  const int per = noct / nfull;
+  const int o = ptid >> 3, rl = ptid & 7;
+  const int cc = o % nfull, ro0 = o / nfull;
+  if (ro0 >= per) return;
+  const int k0 = cc * 8;
+  const bool full = m0 + kTileM <= M;
+  const bool second = (MODE == A_CATMUL || MODE == A_CAT2ROW) ? (k0 >= a.W1) : false;
+  float c0[8], c1[8], c2[8];
+  if (MODE == A_BNRELU || MODE == A_AFFINE2) {
+    const float4 p0 = *reinterpret_cast<const float4*>(sv + k0), p1 = *reinterpret_cast<const float4*>(sv + k0 + 4);
+    const float4 q0 = *reinterpret_cast<const float4*>(sv + svld + k0), q1 = *reinterpret_cast<const float4*>(sv + svld + k0 + 4);
+    c0[0] = p0.x; c0[1] = p0.y; c0[2] = p0.z; c0[3] = p0.w; c0[4] = p1.x; c0[5] = p1.y; c0[6] = p1.z; c0[7] = p1.w;
+    c1[0] = q0.x; c1[1] = q0.y; c1[2] = q0.z; c1[3] = q0.w; c1[4] = q1.x; c1[5] = q1.y; c1[6] = q1.z; c1[7] = q1.w;
+  }
+  if (MODE == A_AFFINE2) {
+    const float4 u0 = *reinterpret_cast<const float4*>(sv + 2 * svld + k0), u1 = *reinterpret_cast<const float4*>(sv + 2 * svld + k0 + 4);
+    c2[0] = u0.x; c2[1] = u0.y; c2[2] = u0.z; c2[3] = u0.w; c2[4] = u1.x; c2[5] = u1.y; c2[6] = u1.z; c2[7] = u1.w;
+  }
+  const int rstep = per * 8;
+  const uint32_t sstep = (uint32_t)rstep * 16;
+  uint32_t soff = (uint32_t)(cc * (kTileM * 16) + (ro0 * 8 + rl) * 16);
+  // pieces in flight per thread: UN1 x 32 bytes (one stream) or UN2 x 64 bytes (two streams)
+  constexpr int UN = (MODE == A_AFFINE2 || MODE == A_CATMUL || MODE == A_MULROW) ? CLSR_TC_UN2 : CLSR_TC_UN1;
 #pragma unroll 1
-  for (int ot = o; ot < ntask; ot += noct * UN) {
-    Raw8 raw[UN];
-    int st[UN];  // bit 31: row in bounds; bits 0..30: byte offset of the piece in the canonical tile, or -1 if no task
+  for (int r = ro0 * 8 + rl; r < kTileM; r += rstep * UN, soff += sstep * UN) {
+    F8 ra[UN], rb[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      // loads are issued unconditionally from a clamped row (a predicated load would keep the
-      // destination registers live across the whole kernel); out-of-range pieces are zeroed below
-      const int r = ro * 8 + rl;
-      const bool has = ot + u * noct < ntask;
-      int m = m0 + r;
-      const bool in = has && m < M;
+      int m = m0 + r + u * rstep;
       m = m < M ? m : M - 1;
-      issue8<MODE, V256>(a, m, cc * 8, raw[u]);
-      st[u] = has ? (cc * (kTileM * 16) + r * 16) | (in ? 0x40000000 : 0) : -1;
-      cc += dcc; ro += dro;
-      if (cc >= nfull) { cc -= nfull; ++ro; }
+      load_piece<MODE, V256>(a, m, k0, second, ra[u], rb[u]);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      if (st[u] < 0) continue;
-      const uint32_t off = (uint32_t)st[u] & 0x3fffffffu;
+      const int rr = r + u * rstep;
+      if (rr >= kTileM) continue;
+      const float v[8] = {ra[u].lo.x, ra[u].lo.y, ra[u].lo.z, ra[u].lo.w, ra[u].hi.x, ra[u].hi.y, ra[u].hi.z, ra[u].hi.w};
       float x[8];
-      if (st[u] & 0x40000000) {
-        finish8<MODE>(a, sv, svld, (int)(off / (kTileM * 16)) * 8, raw[u], x);
+      if (MODE == A_PLAIN || MODE == A_CAT2ROW) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = v[i];
+      } else if (MODE == A_BNRELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaxf(0.f, fmaf(v[i], c0[i], c1[i]));
       } else {
+        const float h[8] = {rb[u].lo.x, rb[u].lo.y, rb[u].lo.z, rb[u].lo.w, rb[u].hi.x, rb[u].hi.y, rb[u].hi.z, rb[u].hi.w};
+        if (MODE == A_AFFINE2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = fmaf(c0[i], v[i], fmaf(c1[i], h[i], c2[i]));
+        } else if (MODE == A_CATMUL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = second ? v[i] * h[i] : v[i];
+        } else {  // A_MULROW
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = v[i] * h[i];
+        }
+      }
+      if (!full && m0 + rr >= M) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = 0.f;
       }
-      split_store8(x, hi + off, lo + off);
+      split_store8(x, hi + soff + u * sstep, lo + soff + u * sstep);
     }
   }
 }
@@ -351,10 +385,11 @@ CLSR_DEVINL void produce_fast_v(const AOp& a, bool v256, const float* sv, int sv
 }
 CLSR_DEVINL void produce_tile(const AOp& a, Fast f, const float* sv, int svld, int m0, int M, int K, int one_col,
                               int ptid, int nprod, uint32_t hi, uint32_t lo) {
-  const int nfull = f.ok ? (K >> 3) : 0;
+  int nfull = f.ok ? (K >> 3) : 0;
+  if (nfull > (nprod >> 3)) nfull = 0;   // more planes than thread octets: element-wise path
   const int kall = one_col >= K ? one_col + 1 : K;
   const int nall = (kall + 7) >> 3;
-  switch (a.mode) {
+  if (nfull > 0) switch (a.mode) {
     case A_PLAIN: produce_fast_v<A_PLAIN>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, hi, lo); break;
     case A_BNRELU: produce_fast_v<A_BNRELU>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, hi, lo); break;
     case A_AFFINE2: produce_fast_v<A_AFFINE2>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, hi, lo); break;
@@ -363,6 +398,35 @@ CLSR_DEVINL void produce_tile(const AOp& a, Fast f, const float* sv, int svld, i
     default: produce_fast_v<A_CAT2ROW>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, hi, lo); break;
   }
   if (nall > nfull) produce_slow(a, m0, M, K, nfull, nall, one_col, ptid, nprod, hi, lo);
+}
+
+// L2 prefetch of the HBM-streamed rows of one operand tile, issued by one warp a few tiles ahead of the
+// producers so that their register loads see L2 latency instead of HBM latency.
+CLSR_DEVINL void prefetch_rows(const float* base, int ld, int m0, int rows, int kfloats, int lane) {
+  if (ld == kfloats) {
+    if (lane == 0) l2_prefetch(base + (size_t)m0 * ld, (uint32_t)rows * kfloats * 4);
+  } else {
+    for (int r = lane; r < rows; r += 32) l2_prefetch(base + (size_t)(m0 + r) * ld, (uint32_t)kfloats * 4);
+  }
+}
+CLSR_DEVINL void prefetch_operand(const AOp& a, int m0, int M, int K, int lane) {
+  if (m0 >= M || (K & 3)) return;
+  const int rows = M - m0 < kTileM ? M - m0 : kTileM;
+  const bool a4 = (a.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0;
+  switch (a.mode) {
+    case A_PLAIN:
+    case A_BNRELU:
+      if (a4) prefetch_rows(a.A, a.lda, m0, rows, K, lane);
+      break;
+    case A_AFFINE2:
+      if (a4) prefetch_rows(a.A, a.lda, m0, rows, K, lane);
+      if ((a.lda2 & 3) == 0 && (reinterpret_cast<uintptr_t>(a.A2) & 15) == 0) prefetch_rows(a.A2, a.lda2, m0, rows, K, lane);
+      break;
+    case A_CATMUL:
+      if (a4) prefetch_rows(a.A, a.lda, m0, rows, a.lda, lane);
+      break;
+    default: break;  // A_MULROW / A_CAT2ROW read small, L2-resident operands
+  }
 }
 
 // copy the per-column prologue vectors of an operand into shared memory (sv[j*svld + k])
@@ -440,8 +504,8 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
   float* sbias = sv + 3 * kpad;                           // [npad] each
   float* sscale = sbias + npad;
   float* sshift = sscale + npad;
-  float* smean = sshift + npad;
-  float* srstd = smean + npad;
+  float* smr = sshift + npad;                             // -mean * rstd
+  float* srstd = smr + npad;
   double* dstat = reinterpret_cast<double*>(smem + L.dstat);  // [4 quadrants][2][npad]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full = bars;          // [2]
@@ -477,8 +541,9 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
     sbias[n] = (in && ep.bias) ? ep.bias[n] : 0.f;
     sscale[n] = (in && (ep.flags & E_RELUMASK)) ? ep.scale[n] : 0.f;
     sshift[n] = (in && (ep.flags & E_RELUMASK)) ? ep.shift[n] : 0.f;
-    smean[n] = (in && (ep.flags & E_STAT_XHAT)) ? ep.mean[n] : 0.f;
-    srstd[n] = (in && (ep.flags & E_STAT_XHAT)) ? ep.rstd[n] : 0.f;
+    const float rs = (in && (ep.flags & E_STAT_XHAT)) ? ep.rstd[n] : 0.f;
+    srstd[n] = rs;
+    smr[n] = (in && (ep.flags & E_STAT_XHAT)) ? -ep.mean[n] * rs : 0.f;
   }
   if (STATS) {
     for (int i = tid; i < 4 * 2 * npad; i += kThreads) dstat[i] = 0.0;
@@ -525,6 +590,7 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
       const uint32_t ph = (it / nstages) & 1;
       const int acc = it & 1;
       const uint32_t pa = (it >> 1) & 1;
+      if (CLSR_TC_PREFETCH) prefetch_operand(a, (tile + CLSR_TC_PREFETCH * (int)gridDim.x) * kTileM, M, K, lane);
       mbar_wait(&tempty[acc], pa ^ 1);   // the epilogue of tile it-2 has released accumulator and operand tile
       if (eop_kind && lane == 0) {
         const int m0 = tile * kTileM;
@@ -574,19 +640,32 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
     const int row = q * 32 + lane;         // accumulator row owned by this thread
     const int flags = ep.flags;
     const bool need_h = flags & (E_RELUMASK | E_STAT_XHAT);
+    const bool has_bias = ep.bias != nullptr;
     const bool vec_ok = (N & 3) == 0 && (ep.ldc & 3) == 0 && al16(ep.C) &&
                         (!need_h || eop_kind == 1 || ((ep.ldh & 3) == 0 && al16(ep.hpre))) &&
                         (!(flags & E_ROWBIAS) || ((ep.ldrb & 3) == 0 && al16(ep.rb))) &&
                         (!(flags & E_GROUPADD) || eop_kind == 2 || ((ep.ldga & 3) == 0 && al16(ep.ga)));
-    const bool st256 = (N & 7) == 0 && (ep.ldc & 7) == 0 && al32(ep.C);
-    double* myd = dstat + (size_t)q * 2 * npad;
-    const int cmap = colmap16(lane);
+    const bool st256 = (ep.ldc & 7) == 0 && al32(ep.C);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    // Per-thread (= per-row) column statistics accumulate in two spare TMEM regions
+    // [2 npad, 3 npad) and [3 npad, 4 npad): no shuffles in the tile loop, one reduction per kernel.
+    if (STATS) {
+      float z[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) z[i] = 0.f;
+      for (int c0 = half * 16; c0 < npad; c0 += 32) {
+        tmem_st16(tlane + (uint32_t)(2 * npad + c0), z);
+        tmem_st16(tlane + (uint32_t)(3 * npad + c0), z);
+      }
+      tmem_wait_st();
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t pa = (it >> 1) & 1;
       const int m0 = tile * kTileM;
       const int m = m0 + row;
+      const bool partial = m0 + kTileM > M;
       const bool ok = m < M;
       const int mc = ok ? m : M - 1;       // clamped: loads of rows past M stay in bounds, results are discarded
       const float* rbrow = (flags & E_ROWBIAS) ? ep.rb + (size_t)(mc / ep.rbT) * ep.ldrb : nullptr;
@@ -601,68 +680,120 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
       mbar_wait(&tfull[acc], pa);
       tc_fence_after();
       if (eop_kind) mbar_wait(&efull[acc], pa);
-      for (int c0 = half * 16; c0 < npad; c0 += 32) {
-        float v[16], p2[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * npad + c0), v);
-        if (vec_ok) {
+
+      // one 16-column chunk with every operand 16-byte addressable; FULL: the chunk lies inside [0, N)
+      auto chunk_vec = [&](auto full_c, int c0, float* v, float* s1, float* s2) {
+        constexpr bool FULL = decltype(full_c)::value;
+        const int nq = FULL ? 4 : ((N - c0 + 3) >> 2);   // valid column quads
+        float h[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = 0.f;
+        if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (FULL || j < nq) {
+              const float4 t4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+              v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+            }
+        }
+        if (flags & E_ROWBIAS) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (FULL || j < nq) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(rbrow + c0 + 4 * j));
+              v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+            }
+        }
+        if (flags & E_GROUPADD) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (FULL || j < nq) {
+              const float4 t4 = eop_kind == 2 ? *reinterpret_cast<const float4*>(erow + c0 + 4 * j)
+                                              : __ldg(reinterpret_cast<const float4*>(garow + c0 + 4 * j));
+              v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+            }
+        }
+        if (need_h) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (FULL || j < nq) {
+              const float4 t4 = eop_kind == 1 ? *reinterpret_cast<const float4*>(erow + c0 + 4 * j)
+                                              : __ldg(reinterpret_cast<const float4*>(hrow + c0 + 4 * j));
+              h[4 * j] = t4.x; h[4 * j + 1] = t4.y; h[4 * j + 2] = t4.z; h[4 * j + 3] = t4.w;
+            }
+        }
+        if (flags & E_RELUMASK) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int n = c0 + 4 * j;
-            float x[4] = {0.f, 0.f, 0.f, 0.f}, h[4] = {0.f, 0.f, 0.f, 0.f};
-            if (n < N) {
-              const float4 bq = *reinterpret_cast<const float4*>(sbias + n);
-              x[0] = v[4 * j] + bq.x; x[1] = v[4 * j + 1] + bq.y; x[2] = v[4 * j + 2] + bq.z; x[3] = v[4 * j + 3] + bq.w;
-              if (flags & E_ROWBIAS) {
-                const float4 t4 = __ldg(reinterpret_cast<const float4*>(rbrow + n));
-                x[0] += t4.x; x[1] += t4.y; x[2] += t4.z; x[3] += t4.w;
-              }
-              if (flags & E_GROUPADD) {
-                const float4 t4 = eop_kind == 2 ? *reinterpret_cast<const float4*>(erow + n)
-                                                : __ldg(reinterpret_cast<const float4*>(garow + n));
-                x[0] += t4.x; x[1] += t4.y; x[2] += t4.z; x[3] += t4.w;
-              }
-              if (need_h) {
-                const float4 t4 = eop_kind == 1 ? *reinterpret_cast<const float4*>(erow + n)
-                                                : __ldg(reinterpret_cast<const float4*>(hrow + n));
-                h[0] = t4.x; h[1] = t4.y; h[2] = t4.z; h[3] = t4.w;
-              }
-              if (flags & E_RELUMASK) {
-                const float4 sc = *reinterpret_cast<const float4*>(sscale + n), sh = *reinterpret_cast<const float4*>(sshift + n);
-                if (!(fmaf(h[0], sc.x, sh.x) > 0.f)) x[0] = 0.f;
-                if (!(fmaf(h[1], sc.y, sh.y) > 0.f)) x[1] = 0.f;
-                if (!(fmaf(h[2], sc.z, sh.z) > 0.f)) x[2] = 0.f;
-                if (!(fmaf(h[3], sc.w, sh.w) > 0.f)) x[3] = 0.f;
-              }
-              if (flags & E_ACCUM) {
-                const float4 t4 = eop_kind == 3 ? *reinterpret_cast<const float4*>(erow + n)
-                                                : *reinterpret_cast<const float4*>(crow + n);
-                x[0] += t4.x; x[1] += t4.y; x[2] += t4.z; x[3] += t4.w;
-              }
-            }
-            if (!ok) { x[0] = 0.f; x[1] = 0.f; x[2] = 0.f; x[3] = 0.f; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              v[4 * j + i] = x[i];
-              if (STATS) {
-                float t = x[i];
-                if (flags & E_STAT_XHAT) {
-                  t = (h[i] - smean[(n < N ? n : 0) + i]) * srstd[(n < N ? n : 0) + i];
-                }
-                p2[4 * j + i] = (ok && n < N) ? x[i] * t : 0.f;
-              }
-            }
+            const float4 sc = *reinterpret_cast<const float4*>(sscale + c0 + 4 * j);
+            const float4 sh = *reinterpret_cast<const float4*>(sshift + c0 + 4 * j);
+            if (!(fmaf(h[4 * j], sc.x, sh.x) > 0.f)) v[4 * j] = 0.f;
+            if (!(fmaf(h[4 * j + 1], sc.y, sh.y) > 0.f)) v[4 * j + 1] = 0.f;
+            if (!(fmaf(h[4 * j + 2], sc.z, sh.z) > 0.f)) v[4 * j + 2] = 0.f;
+            if (!(fmaf(h[4 * j + 3], sc.w, sh.w) > 0.f)) v[4 * j + 3] = 0.f;
           }
-          if (ok) {
-            if (st256) {
-              if (c0 < N) st8(crow + c0, v, true);
-              if (c0 + 8 < N) st8(crow + c0 + 8, v + 8, true);
-            } else {
+        }
+        if (flags & E_ACCUM) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (c0 + 4 * j < N)
-                  *reinterpret_cast<float4*>(crow + c0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 4; ++j)
+            if (FULL || j < nq) {
+              const float4 t4 = eop_kind == 3 ? *reinterpret_cast<const float4*>(erow + c0 + 4 * j)
+                                              : *reinterpret_cast<const float4*>(crow + c0 + 4 * j);
+              v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
             }
+        }
+        if (!FULL) {
+#pragma unroll
+          for (int j = 1; j < 4; ++j)
+            if (j >= nq) { v[4 * j] = 0.f; v[4 * j + 1] = 0.f; v[4 * j + 2] = 0.f; v[4 * j + 3] = 0.f; }
+        }
+        if (partial && !ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] = 0.f; h[i] = 0.f; }
+        }
+        if (ok) {
+          if (FULL && st256) {
+            st8(crow + c0, v, true);
+            st8(crow + c0 + 8, v + 8, true);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (FULL || j < nq)
+                *reinterpret_cast<float4*>(crow + c0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
+        }
+        if (STATS) {
+          if (flags & E_STAT_XHAT) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 rs = *reinterpret_cast<const float4*>(srstd + c0 + 4 * j);
+              const float4 mr = *reinterpret_cast<const float4*>(smr + c0 + 4 * j);
+              s2[4 * j] = fmaf(v[4 * j], fmaf(h[4 * j], rs.x, mr.x), s2[4 * j]);
+              s2[4 * j + 1] = fmaf(v[4 * j + 1], fmaf(h[4 * j + 1], rs.y, mr.y), s2[4 * j + 1]);
+              s2[4 * j + 2] = fmaf(v[4 * j + 2], fmaf(h[4 * j + 2], rs.z, mr.z), s2[4 * j + 2]);
+              s2[4 * j + 3] = fmaf(v[4 * j + 3], fmaf(h[4 * j + 3], rs.w, mr.w), s2[4 * j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s2[i] = fmaf(v[i], v[i], s2[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s1[i] += v[i];
+        }
+      };
+
+      for (int c0 = half * 16; c0 < npad; c0 += 32) {
+        float v[16], s1[16], s2[16];
+        const uint32_t tcol = tlane + (uint32_t)(acc * npad + c0);
+        if (STATS) {
+          tmem_wait_st();
+          tmem_ld16x3(tcol, tlane + (uint32_t)(2 * npad + c0), tlane + (uint32_t)(3 * npad + c0), v, s1, s2);
+        } else {
+          tmem_ld16(tcol, v);
+        }
+        if (vec_ok) {
+          if (c0 + 16 <= N) chunk_vec(std::true_type{}, c0, v, s1, s2);
+          else chunk_vec(std::false_type{}, c0, v, s1, s2);
         } else {
           // generic element-wise epilogue (odd N / unaligned operands)
 #pragma unroll
@@ -680,18 +811,14 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
               }
               if (flags & E_ACCUM) x += eop_kind == 3 ? erow[n] : crow[n];
               crow[n] = x;
-              t = (flags & E_STAT_XHAT) ? x * ((hp - smean[n]) * srstd[n]) : x * x;
+              t = (flags & E_STAT_XHAT) ? x * fmaf(hp, srstd[n], smr[n]) : x * x;
             }
-            v[i] = x;
-            p2[i] = t;
+            if (STATS) { s1[i] += x; s2[i] += t; }
           }
         }
         if (STATS) {
-          const float s1 = col_reduce16(v, lane), s2 = col_reduce16(p2, lane);
-          if (!(lane & 1) && c0 + cmap < N) {
-            myd[c0 + cmap] += (double)s1;
-            myd[npad + c0 + cmap] += (double)s2;
-          }
+          tmem_st16(tlane + (uint32_t)(2 * npad + c0), s1);
+          tmem_st16(tlane + (uint32_t)(3 * npad + c0), s2);
         }
       }
       tc_fence_before();
@@ -699,6 +826,19 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
     if (STATS) {
+      // fold the per-row accumulators: 16-shuffle transpose reduction per chunk, quadrants summed in double
+      double* myd = dstat + (size_t)q * 2 * npad;
+      const int cmap = colmap16(lane);
+      tmem_wait_st();
+      for (int c0 = half * 16; c0 < npad; c0 += 32) {
+        float v[16], s1[16], s2[16];
+        tmem_ld16x3(tlane + (uint32_t)c0, tlane + (uint32_t)(2 * npad + c0), tlane + (uint32_t)(3 * npad + c0), v, s1, s2);
+        const float r1 = col_reduce16(s1, lane), r2 = col_reduce16(s2, lane);
+        if (!(lane & 1) && c0 + cmap < N) {
+          myd[c0 + cmap] = (double)r1;
+          myd[npad + c0 + cmap] = (double)r2;
+        }
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int n = et; n < N; n += kEpilogue) {
         double a1 = 0.0, a2 = 0.0;
@@ -801,6 +941,11 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, AOp
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it % nstages;
       const uint32_t ph = (it / nstages) & 1;
+      if (CLSR_TC_PREFETCH) {
+        const int mp = (tile + CLSR_TC_PREFETCH * (int)gridDim.x) * kTileM;
+        prefetch_operand(a, mp, M, K, lane);
+        prefetch_operand(b, mp, M, N, lane);
+      }
       mbar_wait(&full[s], ph);
       tc_fence_after();
       if (lane == 0) {
