@@ -1,0 +1,326 @@
+// Row-sharded embedding tables for the configurations whose item table outgrows one GPU's HBM
+// (BASELINE configs 4 and 5).  Global row r lives on rank r % world at local
+// row r / world (round-robin: the frequency-sorted vocabulary, sequential_reviews.py:114-140, would
+// pile every hot id onto rank 0 under a block partition).
+//
+// The reference has no multi-device path (tf.nn.embedding_lookup on one device,
+// sequential_base_model.py:381-437).  Instead of a dedup -> all-to-all(ids) -> gather ->
+// all-to-all(rows) -> scatter pipeline, every rank maps its peers' shards into its own address
+// space (CUDA IPC over NVLink / NVSwitch peer memory) and ONE kernel gathers straight from the
+// owning GPU with 16-byte loads: the transfer is the gather.  The backward pass is the mirror image:
+// red.global.add.v4.f32 straight into the owner's gradient shard.  No staging buffers, no id
+// exchange, no host synchronisation inside the op; ordering against the owners' own reads/writes is
+// the caller's job (one stream-ordered barrier per step, see clsr_b200/sharded.py).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/clsr_b200.h"
+#include "common.cuh"
+
+using namespace clsr;
+
+struct clsr_shard_table {
+  int device = 0, rank = 0, world = 1, dim = 0;
+  long long n_rows = 0, local_rows = 0;
+  float* values = nullptr;
+  float* grad = nullptr;
+  float* peer_values[CLSR_SHARD_MAX_WORLD] = {};
+  float* peer_grad[CLSR_SHARD_MAX_WORLD] = {};
+  bool attached = false;
+  std::string err;
+};
+
+namespace {
+
+thread_local std::string g_shard_error;
+
+int sfail(clsr_shard_table* t, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (t) t->err = buf; else g_shard_error = buf;
+  return code;
+}
+
+#define SCK(t, call)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t _c = (call);                                                                           \
+    if (_c != cudaSuccess) return sfail(t, CLSR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_c)); \
+  } while (0)
+
+struct Peers {
+  float* p[CLSR_SHARD_MAX_WORLD];
+};
+
+// owner / local row of a global id; world is a power of two on every NVSwitch box we target, the
+// general division stays for odd test sizes
+struct Split {
+  int world, shift, mask;
+  __device__ __forceinline__ void operator()(int id, int& owner, long long& local) const {
+    if (shift >= 0) { owner = id & mask; local = id >> shift; }
+    else { owner = id % world; local = id / world; }
+  }
+};
+Split make_split(int world) {
+  Split s; s.world = world; s.shift = -1; s.mask = 0;
+  for (int b = 0; b < 8; ++b)
+    if ((1 << b) == world) { s.shift = b; s.mask = world - 1; }
+  return s;
+}
+
+// hist[p, :] = concat(item[ih[p]], cate[ch[p]]) with both tables row-sharded over peer memory.
+// Same thread mapping as gather_hist_kernel (embed.cuh): one 16-byte vector per thread, the V
+// threads of a position read one contiguous row segment per table and write one contiguous output
+// row; UNROLL independent remote loads are in flight per thread (NVLink latency is ~2x local HBM).
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+shard_gather_hist_kernel(const int32_t* __restrict__ ih, const int32_t* __restrict__ ch, Peers item, Peers cate,
+                         Split sp, int Di, int Dc, float* __restrict__ out, long long npos) {
+  const int VI = Di >> 2, V = (Di + Dc) >> 2;
+  const long long nvec = npos * V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; g0 < nvec; g0 += stride * UNROLL) {
+    const float4* src[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      long long g = g0 + u * stride;
+      g = g < nvec ? g : nvec - 1;   // clamped: the load is always issued, the store is predicated
+      const long long p = g / V;
+      const int q = (int)(g - p * V);
+      int owner;
+      long long local;
+      if (q < VI) {
+        sp(__ldg(ih + p), owner, local);
+        src[u] = reinterpret_cast<const float4*>(item.p[owner] + (size_t)local * Di) + q;
+      } else {
+        sp(__ldg(ch + p), owner, local);
+        src[u] = reinterpret_cast<const float4*>(cate.p[owner] + (size_t)local * Dc) + (q - VI);
+      }
+    }
+    float4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) v[u] = __ldg(src[u]);   // L1-allocating: the hot (low, frequency-sorted) ids and
+                                                            // the padding row are re-read from L1, not over NVLink
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long g = g0 + u * stride;
+      if (g < nvec) stg_stream(reinterpret_cast<float4*>(out) + g, v[u]);
+    }
+  }
+}
+
+// grad_item[owner(ih[p])][local(ih[p]), :] += d_hist[p, 0:Di]; same for the category columns.
+// d_hist is streamed once with 16-byte loads; every vector becomes one 16-byte reduction that the
+// NVSwitch fabric carries to the owning GPU's L2.  Ids are popularity ranks
+// (sequential_reviews.py:114-140) and id 0 pads every window, so the `hot` lowest item ids (and
+// category 0) are first summed per CTA in shared memory and leave the SM once per CTA instead of
+// once per position: without it every rank hammers the same few remote rows.
+__global__ void __launch_bounds__(256)
+shard_scatter_hist_kernel(const float* __restrict__ dX, const int32_t* __restrict__ ih, const int32_t* __restrict__ ch,
+                          Peers gitem, Peers gcate, Split sp, int Di, int Dc, long long npos, int hot) {
+  extern __shared__ float hot_acc[];   // [hot][Di] item rows, then [Dc] category row 0
+  const int VI = Di >> 2, V = (Di + Dc) >> 2;
+  const int nacc = hot * Di + Dc;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) hot_acc[i] = 0.f;
+  __syncthreads();
+  const long long nvec = npos * V;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < nvec;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long p = g / V;
+    const int q = (int)(g - p * V);
+    const float4 v = ldg_stream(reinterpret_cast<const float4*>(dX) + g);
+    int owner;
+    long long local;
+    if (q < VI) {
+      const int id = __ldg(ih + p);
+      if (id < hot) {
+        float* a = hot_acc + id * Di + q * 4;
+        atomicAdd(a + 0, v.x); atomicAdd(a + 1, v.y); atomicAdd(a + 2, v.z); atomicAdd(a + 3, v.w);
+      } else {
+        sp(id, owner, local);
+        red_add_v4(gitem.p[owner] + (size_t)local * Di + q * 4, v);
+      }
+    } else {
+      const int id = __ldg(ch + p);
+      if (id == 0) {
+        float* a = hot_acc + hot * Di + (q - VI) * 4;
+        atomicAdd(a + 0, v.x); atomicAdd(a + 1, v.y); atomicAdd(a + 2, v.z); atomicAdd(a + 3, v.w);
+      } else {
+        sp(id, owner, local);
+        red_add_v4(gcate.p[owner] + (size_t)local * Dc + (q - VI) * 4, v);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x * 4; i < nacc; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(hot_acc + i);
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+    int owner;
+    long long local;
+    if (i < hot * Di) {
+      const int id = i / Di, c = i - id * Di;
+      sp(id, owner, local);
+      red_add_v4(gitem.p[owner] + (size_t)local * Di + c, v);
+    } else {
+      sp(0, owner, local);
+      red_add_v4(gcate.p[owner] + (size_t)local * Dc + (i - hot * Di), v);
+    }
+  }
+}
+
+int check_pair(clsr_shard_table* a, clsr_shard_table* b) {
+  if (!a || !b) return sfail(a, CLSR_ERR_ARG, "null table");
+  if (!a->attached || !b->attached) return sfail(a, CLSR_ERR_STATE, "peer shards not attached (clsr_shard_attach)");
+  if (a->world != b->world || a->rank != b->rank || a->device != b->device)
+    return sfail(a, CLSR_ERR_ARG, "item and category shards belong to different ranks / devices");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int clsr_shard_create(int32_t device, int32_t rank, int32_t world, int64_t n_rows, int32_t dim, int32_t with_grad,
+                      clsr_shard_table** out) {
+  if (!out) return sfail(nullptr, CLSR_ERR_ARG, "null out pointer");
+  *out = nullptr;
+  if (world < 1 || world > CLSR_SHARD_MAX_WORLD || rank < 0 || rank >= world)
+    return sfail(nullptr, CLSR_ERR_ARG, "bad rank %d / world %d (max %d)", rank, world, CLSR_SHARD_MAX_WORLD);
+  if (n_rows <= 0 || n_rows > 0x7fffffffLL || dim <= 0 || (dim & 3))
+    return sfail(nullptr, CLSR_ERR_ARG, "rows must fit int32 ids and dim must be a multiple of 4 (16-byte rows)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return sfail(nullptr, CLSR_ERR_CUDA, "no CUDA device: clsr_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return sfail(nullptr, CLSR_ERR_ARG, "bad device %d", device);
+  clsr_shard_table* t = new clsr_shard_table();
+  t->device = device; t->rank = rank; t->world = world; t->dim = dim; t->n_rows = n_rows;
+  t->local_rows = (n_rows - rank + world - 1) / world;
+  if (t->local_rows < 1) t->local_rows = 1;
+  cudaError_t c = cudaSetDevice(device);
+  const size_t bytes = (size_t)t->local_rows * dim * sizeof(float);
+  if (c == cudaSuccess) c = cudaMalloc(&t->values, bytes);
+  if (c == cudaSuccess) c = cudaMemset(t->values, 0, bytes);
+  if (c == cudaSuccess && with_grad) c = cudaMalloc(&t->grad, bytes);
+  if (c == cudaSuccess && with_grad) c = cudaMemset(t->grad, 0, bytes);
+  if (c != cudaSuccess) {
+    sfail(nullptr, CLSR_ERR_CUDA, "shard allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(c));
+    clsr_shard_destroy(t);
+    return CLSR_ERR_CUDA;
+  }
+  t->peer_values[rank] = t->values;
+  t->peer_grad[rank] = t->grad;
+  t->attached = world == 1;
+  *out = t;
+  return CLSR_OK;
+}
+
+void clsr_shard_destroy(clsr_shard_table* t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  for (int r = 0; r < t->world; ++r) {
+    if (r == t->rank) continue;
+    if (t->peer_values[r]) cudaIpcCloseMemHandle(t->peer_values[r]);
+    if (t->peer_grad[r]) cudaIpcCloseMemHandle(t->peer_grad[r]);
+  }
+  if (t->values) cudaFree(t->values);
+  if (t->grad) cudaFree(t->grad);
+  delete t;
+}
+
+const char* clsr_shard_last_error(const clsr_shard_table* t) { return t ? t->err.c_str() : g_shard_error.c_str(); }
+int64_t clsr_shard_local_rows(const clsr_shard_table* t) { return t ? t->local_rows : 0; }
+float* clsr_shard_local_values(clsr_shard_table* t) { return t ? t->values : nullptr; }
+float* clsr_shard_local_grad(clsr_shard_table* t) { return t ? t->grad : nullptr; }
+
+int clsr_shard_export(clsr_shard_table* t, void* handles_out) {
+  if (!t || !handles_out) return sfail(t, CLSR_ERR_ARG, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  SCK(t, cudaSetDevice(t->device));
+  cudaIpcMemHandle_t h[2];
+  memset(h, 0, sizeof h);
+  SCK(t, cudaIpcGetMemHandle(&h[0], t->values));
+  if (t->grad) SCK(t, cudaIpcGetMemHandle(&h[1], t->grad));
+  memcpy(handles_out, h, sizeof h);
+  return CLSR_OK;
+}
+
+int clsr_shard_attach(clsr_shard_table* t, const void* all_handles) {
+  if (!t || !all_handles) return sfail(t, CLSR_ERR_ARG, "bad argument");
+  if (t->attached) return CLSR_OK;
+  SCK(t, cudaSetDevice(t->device));
+  const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+  for (int r = 0; r < t->world; ++r) {
+    if (r == t->rank) continue;
+    void* p = nullptr;
+    SCK(t, cudaIpcOpenMemHandle(&p, h[2 * r], cudaIpcMemLazyEnablePeerAccess));
+    t->peer_values[r] = static_cast<float*>(p);
+    if (t->grad) {
+      SCK(t, cudaIpcOpenMemHandle(&p, h[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+      t->peer_grad[r] = static_cast<float*>(p);
+    }
+  }
+  t->attached = true;
+  return CLSR_OK;
+}
+
+int clsr_shard_zero_grad(clsr_shard_table* t, void* stream) {
+  if (!t || !t->grad) return sfail(t, CLSR_ERR_ARG, "table has no gradient shard");
+  SCK(t, cudaSetDevice(t->device));
+  SCK(t, cudaMemsetAsync(t->grad, 0, (size_t)t->local_rows * t->dim * sizeof(float), (cudaStream_t)stream));
+  return CLSR_OK;
+}
+
+int clsr_shard_gather_history(clsr_shard_table* item, clsr_shard_table* cate, const int32_t* ih, const int32_t* ch,
+                              int64_t positions, float* out, void* stream) {
+  int rc = check_pair(item, cate);
+  if (rc) return rc;
+  if (!ih || !ch || !out || positions <= 0) return sfail(item, CLSR_ERR_ARG, "bad argument");
+  SCK(item, cudaSetDevice(item->device));
+  Peers pi, pc;
+  for (int r = 0; r < CLSR_SHARD_MAX_WORLD; ++r) { pi.p[r] = item->peer_values[r]; pc.p[r] = cate->peer_values[r]; }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, item->device);
+  const long long nvec = positions * ((item->dim + cate->dim) / 4);
+  long long want = (nvec + 256LL * 4 - 1) / (256LL * 4);
+  const long long cap = (long long)sms * 8;
+  const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  shard_gather_hist_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(ih, ch, pi, pc, make_split(item->world), item->dim,
+                                                                     cate->dim, out, positions);
+  SCK(item, cudaGetLastError());
+  return CLSR_OK;
+}
+
+int clsr_shard_scatter_add_history(clsr_shard_table* item, clsr_shard_table* cate, const int32_t* ih,
+                                   const int32_t* ch, int64_t positions, const float* d_hist, void* stream) {
+  int rc = check_pair(item, cate);
+  if (rc) return rc;
+  if (!item->grad || !cate->grad) return sfail(item, CLSR_ERR_STATE, "tables were created without gradient shards");
+  if (!ih || !ch || !d_hist || positions <= 0) return sfail(item, CLSR_ERR_ARG, "bad argument");
+  SCK(item, cudaSetDevice(item->device));
+  Peers gi, gc;
+  for (int r = 0; r < CLSR_SHARD_MAX_WORLD; ++r) { gi.p[r] = item->peer_grad[r]; gc.p[r] = cate->peer_grad[r]; }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, item->device);
+  const long long nvec = positions * ((item->dim + cate->dim) / 4);
+  long long want = (nvec + 255) / 256;
+  const long long cap = (long long)sms * 4;   // few, long-lived CTAs: each flushes its hot rows once
+  const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  // per-CTA pre-aggregation of the hottest item ids: up to 64 rows / 32 KB of shared memory
+  int hot = (32 * 1024) / (item->dim * 4);
+  if (hot > 64) hot = 64;
+  if ((long long)hot > item->n_rows) hot = (int)item->n_rows;
+  const size_t smem = (size_t)(hot * item->dim + cate->dim) * sizeof(float);
+  shard_scatter_hist_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d_hist, ih, ch, gi, gc, make_split(item->world),
+                                                                      item->dim, cate->dim, positions, hot);
+  SCK(item, cudaGetLastError());
+  return CLSR_OK;
+}
+
+}  // extern "C"

@@ -57,6 +57,9 @@ EXPORTS = [
     "clsr_scatter_history_grad", "clsr_sparse_grad_view", "clsr_nccl_unique_id", "clsr_comm_init",
     "clsr_debug_buffer", "clsr_debug_read", "clsr_set_debug_sync", "clsr_kernel_launches",
     "clsr_set_profiling", "clsr_profile_collect", "clsr_profile_entry", "clsr_debug_gemm", "clsr_debug_dwgemm",
+    "clsr_shard_create", "clsr_shard_destroy", "clsr_shard_last_error", "clsr_shard_local_rows",
+    "clsr_shard_local_values", "clsr_shard_local_grad", "clsr_shard_export", "clsr_shard_attach",
+    "clsr_shard_zero_grad", "clsr_shard_gather_history", "clsr_shard_scatter_add_history",
 ]
 
 _lib = None
@@ -107,6 +110,17 @@ def load_library(path=None):
         "clsr_set_profiling": (C.c_int, [P, I32]),
         "clsr_profile_collect": (C.c_int, [P]),
         "clsr_profile_entry": (C.c_int, [P, I32, C.c_char_p, I32, C.POINTER(C.c_double), C.POINTER(I64)]),
+        "clsr_shard_create": (C.c_int, [I32, I32, I32, I64, I32, I32, C.POINTER(P)]),
+        "clsr_shard_destroy": (None, [P]),
+        "clsr_shard_last_error": (C.c_char_p, [P]),
+        "clsr_shard_local_rows": (I64, [P]),
+        "clsr_shard_local_values": (P, [P]),
+        "clsr_shard_local_grad": (P, [P]),
+        "clsr_shard_export": (C.c_int, [P, P]),
+        "clsr_shard_attach": (C.c_int, [P, P]),
+        "clsr_shard_zero_grad": (C.c_int, [P, P]),
+        "clsr_shard_gather_history": (C.c_int, [P, P, P, P, I64, P, P]),
+        "clsr_shard_scatter_add_history": (C.c_int, [P, P, P, P, I64, P, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -136,6 +136,35 @@ int clsr_sparse_grad_view(clsr_engine* e, int32_t table, const int32_t** unique_
 int clsr_nccl_unique_id(void* out128);                        /* 128 bytes */
 int clsr_comm_init(clsr_engine* e, int32_t rank, int32_t world, const void* id128);
 
+/* ---- row-sharded embedding tables (BASELINE configs 4-5) ------------------
+ * For tables that outgrow one GPU: global row r lives on rank r % world at local row r / world.
+ * The reference has no counterpart (tf.nn.embedding_lookup on one device,
+ * sequential_base_model.py:381-437); these entry points replace that lookup and its
+ * IndexedSlices gradient for a sharded table.  Peers map each other's shards through CUDA IPC
+ * (NVLink / NVSwitch peer memory); gather and scatter-add are single kernels that read /
+ * reduce straight into the owning GPU's memory - there is no id or row exchange step.
+ * The caller orders steps across ranks (one barrier between an owner's update and its peers'
+ * gathers, one between the peers' scatter-adds and the owner's optimizer). */
+#define CLSR_SHARD_MAX_WORLD 16
+typedef struct clsr_shard_table clsr_shard_table;
+int clsr_shard_create(int32_t device, int32_t rank, int32_t world, int64_t n_rows, int32_t dim, int32_t with_grad,
+                      clsr_shard_table** out);
+void clsr_shard_destroy(clsr_shard_table* t);
+const char* clsr_shard_last_error(const clsr_shard_table* t);   /* t may be NULL (creation errors) */
+int64_t clsr_shard_local_rows(const clsr_shard_table* t);
+float* clsr_shard_local_values(clsr_shard_table* t);            /* device pointer [local_rows, dim] */
+float* clsr_shard_local_grad(clsr_shard_table* t);              /* device pointer or NULL */
+int clsr_shard_export(clsr_shard_table* t, void* handles_out);  /* 2 x 64 bytes: values, gradient */
+int clsr_shard_attach(clsr_shard_table* t, const void* all_handles); /* world x 128 bytes, rank-major */
+int clsr_shard_zero_grad(clsr_shard_table* t, void* cuda_stream);
+/* K1+K3 on sharded tables: out[p,:] = concat(item[ih[p]], cate[ch[p]]); device pointers. */
+int clsr_shard_gather_history(clsr_shard_table* item, clsr_shard_table* cate, const int32_t* item_hist,
+                              const int32_t* cate_hist, int64_t positions, float* out, void* cuda_stream);
+/* K13 on sharded tables: owner's gradient shard row += d_hist[p, item | cate columns]. */
+int clsr_shard_scatter_add_history(clsr_shard_table* item, clsr_shard_table* cate, const int32_t* item_hist,
+                                   const int32_t* cate_hist, int64_t positions, const float* d_hist,
+                                   void* cuda_stream);
+
 /* ---- introspection for parity tests ------------------------------------------------ */
 /* Named intermediate buffers of the last step (device pointers, fp32). */
 int clsr_debug_buffer(clsr_engine* e, const char* name, const float** dev_ptr, int64_t* numel);
