@@ -22,6 +22,7 @@
 #include "gemm.cuh"
 #include "head.cuh"
 #include "rnn.cuh"
+#include "rnn_tc.cuh"
 #include "tc_gemm.cuh"
 
 using namespace clsr;
@@ -546,6 +547,12 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   return 0;
 }
 
+// tensor-core recurrences: instantiated for the model's 40-wide states (H == U == item_dim + cate_dim)
+bool rnn_tc_ok(const clsr_engine* e) {
+  if (getenv("CLSR_RNN_SIMT")) return false;
+  return e->cfg.math_mode == 1 && e->U == 40 && e->H == 40;
+}
+
 bool tc_eligible(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, bool stats) {
   if (e->cfg.math_mode != 1 || M < 1024) return false;
   if (const char* only = getenv("CLSR_TC_ONLY")) {  // developer bisection aid: comma-separated GEMM names
@@ -877,6 +884,18 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
   const int nblk = cdiv(S, RNN_NSEQ);
   {
     if ((rc = fork_aux(e))) return rc;
+    if (rnn_tc_ok(e)) {
+      // mma.sync kernels: weights in registers, states thread-local (rnn_tc.cuh)
+      rtc::gru_fwd_tc_kernel<40><<<nblk, 160, 0, e->aux[0]>>>(PX, NX, e->oG1, e->oC1, us, W("Wgh1"), W("Wch1"), e->d_len, S, T,
+                                                            e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"));
+      e->launches++;
+      rtc::gru_fwd_tc_kernel<40><<<nblk, 160, 0, e->aux[1]>>>(PX, NX, e->oG2, e->oC2, nullptr, W("Wgh2"), W("Wch2"), e->d_len, S,
+                                                            T, e->B("g2"), e->B("c2"), e->B("hp2"), e->B("rh2"), e->B("fs"));
+      e->launches++;
+      rtc::lstm_fwd_tc_kernel<40><<<nblk, 160, 0, st>>>(PX, NX, e->oL, e->oTN, e->oTL, W("Km"), e->d_len, S, T, e->B("G4"),
+                                                      e->B("cp"), e->B("mp"), e->B("R"));
+      e->launches++;
+    } else {
     size_t smg = (size_t)(U * 2 * U + U * U + 3 * U * RNN_LD) * 4;
     gru_fwd_kernel<<<nblk, RNN_THREADS, smg, e->aux[0]>>>(PX, NX, e->oG1, e->oC1, us, W("Wgh1"), W("Wch1"), e->d_len, S, T, U,
                                                        e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"));
@@ -889,6 +908,7 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
     lstm_fwd_kernel<<<nblk, RNN_THREADS, sml, st>>>(PX, NX, e->oL, e->oTN, e->oTL, W("Km"), e->d_len, S, T, H,
                                                     e->B("G4"), e->B("cp"), e->B("mp"), e->B("R"));
     e->launches++;
+    }
     if ((rc = join_aux(e, "rnn_fwd(gru_sti|gru_causal2|time4lstm)"))) return rc;
   }
 
@@ -1069,6 +1089,17 @@ int backward(clsr_engine* e, const StepCtx& c) {
   {
     // the three BPTT kernels write disjoint column ranges of dPX: run them side by side
     if ((rc = fork_aux(e))) return rc;
+    if (rnn_tc_ok(e)) {
+      rtc::lstm_bwd_tc_kernel<40><<<nblk, 160, 0, st>>>(PX, NX, e->oL, e->oTN, e->oTL, e->B("G4"), e->B("cp"), W("KmT"), dR,
+                                                      e->d_len, S, T, dPX);
+      e->launches++;
+      rtc::gru_bwd_tc_kernel<40><<<nblk, 160, 0, e->aux[0]>>>(e->B("g1"), e->B("c1"), e->B("hp1"), W("Wgh1T"), W("Wch1T"),
+                                                            e->B("dsti"), e->d_len, S, T, dPX, NX, e->oG1, e->oC1, e->B("dus"));
+      e->launches++;
+      rtc::gru_bwd_tc_kernel<40><<<nblk, 160, 0, e->aux[1]>>>(e->B("g2"), e->B("c2"), e->B("hp2"), W("Wgh2T"), W("Wch2T"),
+                                                            e->B("dfs"), e->d_len, S, T, dPX, NX, e->oG2, e->oC2, nullptr);
+      e->launches++;
+    } else {
     size_t sml = (size_t)(H * 4 * H + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
     lstm_bwd_kernel<<<nblk, RNN_THREADS, sml, st>>>(PX, NX, e->oL, e->oTN, e->oTL, e->B("G4"), e->B("cp"), W("KmT"), dR,
                                                     e->d_len, S, T, H, dPX);
@@ -1081,6 +1112,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
     gru_bwd_kernel<<<nblk, RNN_THREADS, smg2, e->aux[1]>>>(e->B("g2"), e->B("c2"), e->B("hp2"), W("Wgh2T"), W("Wch2T"), e->B("dfs"),
                                                         e->d_len, S, T, H, dPX, NX, e->oG2, e->oC2, nullptr);
     e->launches++;
+    }
     if ((rc = join_aux(e, "rnn_bwd(time4lstm|gru_sti|gru_causal2)"))) return rc;
   }
   float *dX = e->B("dX"), *TNL = e->B("TNL"), *dTNL = e->B("dTNL");
