@@ -14,7 +14,7 @@ pool_fwd_kernel(const float* __restrict__ h1, int A1, const float* __restrict__ 
                 const float* __restrict__ bout, const float* __restrict__ V, int Dv,
                 const int* __restrict__ len, int rows, int T, int G, float* __restrict__ w_out,
                 float* __restrict__ att, float* __restrict__ hm, float* __restrict__ hr, int recent_k) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* s_scale = sm;
   float* s_shift = s_scale + A1;
   float* s_w = s_shift + A1;
@@ -26,6 +26,7 @@ pool_fwd_kernel(const float* __restrict__ h1, int A1, const float* __restrict__ 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* sc = s_sc + wid * T;
   const float b0 = bout[0];
+  const bool vec4 = (A1 & 3) == 0 && (reinterpret_cast<uintptr_t>(h1) & 15) == 0;
   for (int row = blockIdx.x * wpb + wid; row < rows; row += gridDim.x * wpb) {
     const int s = row / G;
     const int L = len[s];
@@ -33,7 +34,20 @@ pool_fwd_kernel(const float* __restrict__ h1, int A1, const float* __restrict__ 
     for (int t = lane; t < L; t += 32) {
       const float* hp = h1 + ((size_t)row * T + t) * A1;
       float dot = b0;
-      for (int n = 0; n < A1; ++n) dot = fmaf(fmaxf(0.f, fmaf(hp[n], s_scale[n], s_shift[n])), s_w[n], dot);
+      if (vec4) {
+        // one 16-byte load per four channels (the lane's 4*A1-byte row is contiguous)
+        for (int n = 0; n < A1; n += 4) {
+          const float4 h = __ldg(reinterpret_cast<const float4*>(hp + n));
+          const float4 sc4 = *reinterpret_cast<const float4*>(s_scale + n), sh4 = *reinterpret_cast<const float4*>(s_shift + n);
+          const float4 w4 = *reinterpret_cast<const float4*>(s_w + n);
+          dot = fmaf(fmaxf(0.f, fmaf(h.x, sc4.x, sh4.x)), w4.x, dot);
+          dot = fmaf(fmaxf(0.f, fmaf(h.y, sc4.y, sh4.y)), w4.y, dot);
+          dot = fmaf(fmaxf(0.f, fmaf(h.z, sc4.z, sh4.z)), w4.z, dot);
+          dot = fmaf(fmaxf(0.f, fmaf(h.w, sc4.w, sh4.w)), w4.w, dot);
+        }
+      } else {
+        for (int n = 0; n < A1; ++n) dot = fmaf(fmaxf(0.f, fmaf(hp[n], s_scale[n], s_shift[n])), s_w[n], dot);
+      }
       sc[t] = dot;
       mx = fmaxf(mx, dot);
     }
@@ -109,6 +123,17 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
   float st1[MAXSLOT], st2[MAXSLOT], dwo[MAXSLOT], dbo = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXSLOT; ++i) { st1[i] = 0.f; st2[i] = 0.f; dwo[i] = 0.f; }
+  // quad mapping of the dy1 pass (A1 multiple of 4, at most 32 quads)
+  const int nq = A1 >> 2;
+  const bool quad = (A1 & 3) == 0 && nq <= 32 && ((reinterpret_cast<uintptr_t>(h1) | reinterpret_cast<uintptr_t>(dy1)) & 15) == 0;
+  const int ntl = quad ? 32 / nq : 1;
+  const int n4 = quad ? lane % nq : 0, tl = quad ? lane / nq : 0;
+  float q_sc[4], q_sh[4], q_mn[4], q_rs[4], q_wo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = quad ? n4 * 4 + i : 0;
+    q_sc[i] = s_scale[n]; q_sh[i] = s_shift[n]; q_mn[i] = s_mean[n]; q_rs[i] = s_rstd[n]; q_wo[i] = s_w[n];
+  }
 
   for (int s = blockIdx.x * wpb + wid; s < nseq; s += gridDim.x * wpb) {
     const int sv = s / vdiv;
@@ -137,6 +162,31 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
         dbo += v;
       }
       __syncwarp();
+      if (quad) {
+        // lane = (position lane tl, channel quad n4): 16-byte loads / stores, nq * ntl lanes cover ntl
+        // consecutive positions (contiguous 4*A1*ntl bytes) per iteration; statistics stay per lane
+        if (lane < nq * ntl) {
+          const float4* hp4 = reinterpret_cast<const float4*>(h1 + row * T * A1) + n4;
+          float4* dp4 = reinterpret_cast<float4*>(dy1 + row * T * A1) + n4;
+#pragma unroll 4
+          for (int t = tl; t < T; t += ntl) {
+            const float4 h = __ldg(hp4 + (size_t)t * nq);
+            const float d = dsc[t];
+            const float hh[4] = {h.x, h.y, h.z, h.w};
+            float vv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float y = fmaf(hh[i], q_sc[i], q_sh[i]);
+              const float v = (y > 0.f) ? d * q_wo[i] : 0.f;
+              vv[i] = v;
+              st1[i] += v;
+              st2[i] = fmaf(v, (hh[i] - q_mn[i]) * q_rs[i], st2[i]);
+              dwo[i] = fmaf(fmaxf(y, 0.f), d, dwo[i]);
+            }
+            dp4[(size_t)t * nq] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+          }
+        }
+      } else {
 #pragma unroll
       for (int sl = 0; sl < MAXSLOT; ++sl) {
         const int n = lane + 32 * sl;
@@ -155,6 +205,7 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
             dwo[sl] = fmaf(fmaxf(y, 0.f), d, dwo[sl]);
           }
         }
+      }
       }
       for (int d = lane; dV && d < Dv; d += 32) {
         const float da = dat[d];
@@ -176,8 +227,8 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
   }
 #pragma unroll
   for (int sl = 0; sl < MAXSLOT; ++sl) {
-    const int n = lane + 32 * sl;
-    if (n < A1) {
+    const int n = quad ? n4 * 4 + sl : lane + 32 * sl;
+    if (n < A1 && (!quad || lane < nq * ntl)) {
       atomicAdd(&s_acc[n], st1[sl]); atomicAdd(&s_acc[A1 + n], st2[sl]); atomicAdd(&s_acc[2 * A1 + n], dwo[sl]);
     }
   }
@@ -282,6 +333,115 @@ __global__ void mulrow_bwd_kernel(const float* __restrict__ dP, int D, const flo
       dtgt[row * lddt + k] += tot;
     }
     __syncthreads();
+  }
+}
+
+// 16-byte vectorised forms of h0_reduce_kernel / mulrow_bwd_kernel (A0, D multiples of 4, aligned
+// rows).  blockDim = (width / 4, NY); a thread owns one column quad and the positions ty, ty + NY, ...
+// (at most TP of them), keeps the group sums of its positions in registers and writes them once, so
+// the kernel is a pure stream: every input is read once with independent 16-byte loads and nothing is
+// read-modified-written.  Dynamic shared memory: G * NY * (width / 4) float4.
+template <int TP>
+__global__ void __launch_bounds__(1024)
+h0_reduce_v4_kernel(const float* __restrict__ dy0, const float* __restrict__ h0, int A0, const float* __restrict__ al,
+                    const float* __restrict__ be, const float* __restrict__ ga, int T, int G,
+                    float* __restrict__ dinv, float* __restrict__ dqb) {
+  extern __shared__ float4 sq4[];  // [G][NY][NX]
+  const int s = blockIdx.x;
+  const int n4 = threadIdx.x, ty = threadIdx.y, nx = blockDim.x, ny = blockDim.y;
+  const float4 a = reinterpret_cast<const float4*>(al)[n4], b = reinterpret_cast<const float4*>(be)[n4];
+  const float4 c = reinterpret_cast<const float4*>(ga)[n4];
+  const float4* d4 = reinterpret_cast<const float4*>(dy0);
+  const float4* h4 = reinterpret_cast<const float4*>(h0);
+  float4 inv[TP];
+#pragma unroll
+  for (int i = 0; i < TP; ++i) inv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int g = 0; g < G; ++g) {
+    const size_t row = (size_t)s * G + g;
+    float4 accq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < TP; ++i) {
+      const int t = ty + i * ny;
+      if (t < T) {
+        const size_t o = (row * T + t) * nx + n4;
+        const float4 d = ldg_stream(d4 + o), h = ldg_stream(h4 + o);
+        float4 v;
+        v.x = fmaf(a.x, d.x, fmaf(b.x, h.x, c.x)); v.y = fmaf(a.y, d.y, fmaf(b.y, h.y, c.y));
+        v.z = fmaf(a.z, d.z, fmaf(b.z, h.z, c.z)); v.w = fmaf(a.w, d.w, fmaf(b.w, h.w, c.w));
+        accq.x += v.x; accq.y += v.y; accq.z += v.z; accq.w += v.w;
+        inv[i].x += v.x; inv[i].y += v.y; inv[i].z += v.z; inv[i].w += v.w;
+      }
+    }
+    sq4[((size_t)g * ny + ty) * nx + n4] = accq;
+  }
+  if (dinv) {
+#pragma unroll
+    for (int i = 0; i < TP; ++i) {
+      const int t = ty + i * ny;
+      if (t < T) reinterpret_cast<float4*>(dinv)[((size_t)s * T + t) * nx + n4] = inv[i];
+    }
+  }
+  __syncthreads();
+  for (int g = ty; g < G; g += ny) {
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = 0; y < ny; ++y) {
+      const float4 v = sq4[((size_t)g * ny + y) * nx + n4];
+      tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+    }
+    reinterpret_cast<float4*>(dqb)[((size_t)s * G + g) * nx + n4] = tot;
+  }
+}
+
+template <int TP>
+__global__ void __launch_bounds__(1024)
+mulrow_bwd_v4_kernel(const float* __restrict__ dP, int D, const float* __restrict__ as, int lda, int off,
+                     const float* __restrict__ tgt, int ldt, int T, int G, float* __restrict__ da2,
+                     float* __restrict__ dtgt, int lddt) {
+  extern __shared__ float4 sq4[];  // [G][NY][NX]
+  const int s = blockIdx.x;
+  const int n4 = threadIdx.x, ty = threadIdx.y, nx = blockDim.x, ny = blockDim.y;
+  const float4* p4 = reinterpret_cast<const float4*>(dP);
+  float4 a2v[TP], da[TP];
+#pragma unroll
+  for (int i = 0; i < TP; ++i) {
+    const int t = ty + i * ny;
+    da[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    a2v[i] = da[i];
+    if (t < T) a2v[i] = __ldg(reinterpret_cast<const float4*>(as + ((size_t)s * T + t) * lda + off) + n4);
+  }
+  for (int g = 0; g < G; ++g) {
+    const size_t row = (size_t)s * G + g;
+    const float4 tg = __ldg(reinterpret_cast<const float4*>(tgt + row * ldt) + n4);
+    float4 acct = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < TP; ++i) {
+      const int t = ty + i * ny;
+      if (t < T) {
+        const float4 d = ldg_stream(p4 + (row * T + t) * nx + n4);
+        acct.x = fmaf(d.x, a2v[i].x, acct.x); acct.y = fmaf(d.y, a2v[i].y, acct.y);
+        acct.z = fmaf(d.z, a2v[i].z, acct.z); acct.w = fmaf(d.w, a2v[i].w, acct.w);
+        da[i].x = fmaf(d.x, tg.x, da[i].x); da[i].y = fmaf(d.y, tg.y, da[i].y);
+        da[i].z = fmaf(d.z, tg.z, da[i].z); da[i].w = fmaf(d.w, tg.w, da[i].w);
+      }
+    }
+    sq4[((size_t)g * ny + ty) * nx + n4] = acct;
+  }
+#pragma unroll
+  for (int i = 0; i < TP; ++i) {
+    const int t = ty + i * ny;
+    if (t < T) reinterpret_cast<float4*>(da2)[((size_t)s * T + t) * nx + n4] = da[i];
+  }
+  __syncthreads();
+  for (int g = ty; g < G; g += ny) {
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = 0; y < ny; ++y) {
+      const float4 v = sq4[((size_t)g * ny + y) * nx + n4];
+      tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(dtgt + ((size_t)s * G + g) * lddt) + n4;
+    float4 o = *dst;
+    o.x += tot.x; o.y += tot.y; o.z += tot.z; o.w += tot.w;
+    *dst = o;
   }
 }
 

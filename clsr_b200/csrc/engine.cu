@@ -977,6 +977,33 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
   return 0;
 }
 
+// dinv / dqb reductions of the BatchNorm-backward input gradient (attn.cuh): vectorised stream when the
+// layer width allows it.
+int h0_reduce(clsr_engine* e, const char* name, const float* dy0, const float* h0, const BnLayer& bn, int S, int T,
+              int G, float* dinv, float* dqb) {
+  const int A0 = bn.N, nx4 = A0 / 4;
+  int ny = cdiv(T, 4);
+  if (nx4 > 0 && ny * nx4 > 1024) ny = 1024 / nx4;
+  if (ny > 32) ny = 32;
+  if (ny < 1) ny = 1;
+  const int tp = cdiv(T, ny);
+  const size_t smv = (size_t)G * ny * nx4 * 16;
+  const bool vec = (A0 & 3) == 0 && tp <= 8 && smv <= 96 * 1024 &&
+                   !(((uintptr_t)dy0 | (uintptr_t)h0 | (uintptr_t)dinv | (uintptr_t)dqb | (uintptr_t)bn.al |
+                      (uintptr_t)bn.be | (uintptr_t)bn.ga) & 15);
+  if (vec && tp <= 4)
+    h0_reduce_v4_kernel<4><<<S, dim3(nx4, ny), smv, e->stream>>>(dy0, h0, A0, bn.al, bn.be, bn.ga, T, G, dinv, dqb);
+  else if (vec)
+    h0_reduce_v4_kernel<8><<<S, dim3(nx4, ny), smv, e->stream>>>(dy0, h0, A0, bn.al, bn.be, bn.ga, T, G, dinv, dqb);
+  else {
+    int nx = ((A0 + 31) / 32) * 32;
+    dim3 blk(nx, 4);
+    h0_reduce_kernel<<<S, blk, (size_t)4 * A0 * 4, e->stream>>>(dy0, h0, A0, bn.al, bn.be, bn.ga, T, G, dinv, dqb);
+  }
+  POST(name);
+  return 0;
+}
+
 int backward(clsr_engine* e, const StepCtx& c) {
   const int B = c.B, G = c.G, S = c.S, T = c.T;
   const int D = e->D, U = e->U, H = e->H, Q = e->Q, A0 = e->A0, A1 = e->A1, NX = e->NX, Di = e->Di, Dc = e->Dc;
@@ -1043,20 +1070,27 @@ int backward(clsr_engine* e, const StepCtx& c) {
                    e->Pg + ms.w1, A1, nullptr)))
     return rc;
   if ((rc = bn_bwd(e, ms.bn0, (double)MB))) return rc;
-  {
-    int nx = ((A0 + 31) / 32) * 32;
-    dim3 blk(nx, 4);
-    h0_reduce_kernel<<<S, blk, (size_t)4 * A0 * 4, st>>>(dy0s, h0s, A0, ms.bn0.al, ms.bn0.be, ms.bn0.ga, T, G,
-                                                        e->B("dinvs"), e->B("dqbs"));
-    POST("h0_reduce_short");
-  }
+  if ((rc = h0_reduce(e, "h0_reduce_short", dy0s, h0s, ms.bn0, S, T, G, e->B("dinvs"), e->B("dqbs")))) return rc;
   AOp dh0s = a_affine2(dy0s, h0s, A0, ms.bn0);
   if ((rc = gemm(e, "dP", (int)MB, D, A0, dh0s, W("Ws0tT"), D, e_store(e->B("dP"), D), false))) return rc;
   if ((rc = dwgemm(e, "dWs0t", (int)MB, D, A0, a_mulrow(as, Q, U, tgt, D, T, G), dh0s, dW("Ws0t"), A0, nullptr))) return rc;
   {
-    int nx = ((D + 31) / 32) * 32;
-    dim3 blk(nx, 4);
-    mulrow_bwd_kernel<<<S, blk, (size_t)4 * D * 4, st>>>(e->B("dP"), D, as, Q, U, tgt, D, T, G, e->B("da2"), e->B("dtgt"), D);
+    const int nx4 = D / 4;
+    int ny = cdiv(T, 4);
+    if (ny * nx4 > 1024) ny = 1024 / nx4;
+    if (ny > 32) ny = 32;
+    const int tp = cdiv(T, ny);
+    const size_t smv = (size_t)G * ny * nx4 * 16;
+    float *dPb = e->B("dP"), *da2 = e->B("da2"), *dtg = e->B("dtgt");
+    const bool vec = (D & 3) == 0 && (Q & 3) == 0 && (U & 3) == 0 && tp <= 8 && smv <= 96 * 1024 &&
+                     !(((uintptr_t)dPb | (uintptr_t)as | (uintptr_t)tgt | (uintptr_t)da2 | (uintptr_t)dtg) & 15);
+    if (vec && tp <= 4) mulrow_bwd_v4_kernel<4><<<S, dim3(nx4, ny), smv, st>>>(dPb, D, as, Q, U, tgt, D, T, G, da2, dtg, D);
+    else if (vec) mulrow_bwd_v4_kernel<8><<<S, dim3(nx4, ny), smv, st>>>(dPb, D, as, Q, U, tgt, D, T, G, da2, dtg, D);
+    else {
+      int nx = ((D + 31) / 32) * 32;
+      dim3 blk(nx, 4);
+      mulrow_bwd_kernel<<<S, blk, (size_t)4 * D * 4, st>>>(dPb, D, as, Q, U, tgt, D, T, G, da2, dtg, D);
+    }
     POST("mulrow_bwd");
   }
   if ((rc = gemm(e, "dFs", (int)M, Q + U, A0, a_plain(e->B("dinvs"), A0), W("Ws0iT"), Q + U, e_store(e->B("dFs"), Q + U), false)))
@@ -1160,13 +1194,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
                    e->Pg + ml.w1, A1, nullptr)))
     return rc;
   if ((rc = bn_bwd(e, ml.bn0, (double)M))) return rc;
-  {
-    int nx = ((A0 + 31) / 32) * 32;
-    dim3 blk(nx, 4);
-    h0_reduce_kernel<<<S, blk, (size_t)4 * A0 * 4, st>>>(dy0l, h0l, A0, ml.bn0.al, ml.bn0.be, ml.bn0.ga, T, 1, nullptr,
-                                                        e->B("dqbl"));
-    POST("h0_reduce_long");
-  }
+  if ((rc = h0_reduce(e, "h0_reduce_long", dy0l, h0l, ml.bn0, S, T, 1, nullptr, e->B("dqbl")))) return rc;
   AOp dh0l = a_affine2(dy0l, h0l, A0, ml.bn0);
   if ((rc = gemm(e, "dFl", (int)M, 2 * U, A0, dh0l, W("Wl0T"), 2 * U, e_store(e->B("dFl"), 2 * U), false))) return rc;
   if ((rc = dwgemm(e, "dWl0", (int)M, 2 * U, A0, a_catmul(al, U, U, 0, ul, U, T), dh0l, dW("Wl0"), A0, nullptr))) return rc;
@@ -1403,6 +1431,10 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
     CKCU(cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smf > 49152 ? smf : 49152)));
   }
 
+  CKCU(cudaFuncSetAttribute(h0_reduce_v4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CKCU(cudaFuncSetAttribute(h0_reduce_v4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CKCU(cudaFuncSetAttribute(mulrow_bwd_v4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CKCU(cudaFuncSetAttribute(mulrow_bwd_v4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   {
     cudaFuncAttributes fa;
     CKCU(cudaFuncGetAttributes(&fa, tc::tc_gemm_kernel<true>));
