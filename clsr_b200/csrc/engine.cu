@@ -1315,8 +1315,17 @@ int optimizer_step(clsr_engine* e) {
                                                        e->counts + cnt_ix[tb], e->cg[tb], e->tab_dim[tb], hp, e->sumsq + tb);
       POST("adam_lazy");
     } else {
-      adam_sweep_kernel<<<e->num_sms * 8, 256, 0, st>>>(e->tab[tb], e->tab_m[tb], e->tab_v[tb], e->slot[slot_ix[tb]],
-                                                        e->cg[tb], e->tab_dim[tb], e->tab_rows[tb], hp, e->sumsq + tb);
+      static const int un = getenv("CLSR_ADAM_UN") ? atoi(getenv("CLSR_ADAM_UN")) : 2;
+      static const int gm = getenv("CLSR_ADAM_GRID") ? atoi(getenv("CLSR_ADAM_GRID")) : 16;
+      if (un == 8)
+        adam_sweep_kernel<8><<<e->num_sms * gm, 256, 0, st>>>(e->tab[tb], e->tab_m[tb], e->tab_v[tb], e->slot[slot_ix[tb]],
+                                                             e->cg[tb], e->tab_dim[tb], e->tab_rows[tb], hp, e->sumsq + tb);
+      else if (un == 2)
+        adam_sweep_kernel<2><<<e->num_sms * gm, 256, 0, st>>>(e->tab[tb], e->tab_m[tb], e->tab_v[tb], e->slot[slot_ix[tb]],
+                                                             e->cg[tb], e->tab_dim[tb], e->tab_rows[tb], hp, e->sumsq + tb);
+      else
+        adam_sweep_kernel<4><<<e->num_sms * gm, 256, 0, st>>>(e->tab[tb], e->tab_m[tb], e->tab_v[tb], e->slot[slot_ix[tb]],
+                                                             e->cg[tb], e->tab_dim[tb], e->tab_rows[tb], hp, e->sumsq + tb);
       POST("adam_sweep");
     }
   }

@@ -918,6 +918,10 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, AOp
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 12) {
+    const int pa = ((colsum ? K + 1 : K) + 7) >> 3, pb = (N + 7) >> 3;   // planes per operand
+    int octa = (kDwProducers / 8 * pa + (pa + pb) / 2) / (pa + pb);
+    if (octa < pa) octa = pa;
+    if (kDwProducers / 8 - octa < pb) octa = kDwProducers / 8 - pb;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it % nstages;
@@ -928,8 +932,10 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, AOp
       const uint32_t b_hi = a_hi + L.a_bytes;
       const uint32_t b_lo = b_hi + L.b_bytes / 2;
       const int m0 = tile * kTileM;
-      produce_tile(a, fa, sva, 128, m0, M, K, colsum ? K : -1, tid, kDwProducers, a_hi, a_lo);
-      produce_tile(b, fb, svb, 256, m0, M, N, -1, tid, kDwProducers, b_hi, b_lo);
+      // the producer octets are split between the two operands in proportion to their plane counts, so
+      // the loads of A and B are in flight together (one exposed load latency per slab, not two)
+      if (tid < octa * 8) produce_tile(a, fa, sva, 128, m0, M, K, colsum ? K : -1, tid, octa * 8, a_hi, a_lo);
+      else produce_tile(b, fb, svb, 256, m0, M, N, -1, tid - octa * 8, kDwProducers - octa * 8, b_hi, b_lo);
       fence_proxy_async();
       mbar_arrive(&full[s]);
     }
