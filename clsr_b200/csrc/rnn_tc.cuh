@@ -95,6 +95,12 @@ CLSR_DEVINL void matmul(float (&c)[4], const ATile<K>& a, const BFrag<ATile<K>::
   }
 }
 
+// Gate non-linearities of the tensor-core path: ex2.approx-based exp and a correctly rounded
+// reciprocal (absolute error ~1e-7, an order of magnitude below the 2^-16 operand error of the split
+// products feeding them).  The fp32 SIMT kernels keep expf / tanhf.
+CLSR_DEVINL float sigm(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+CLSR_DEVINL float tanh_(float x) { return 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * x)); }
+
 CLSR_DEVINL float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 CLSR_DEVINL void st2(float* p, float x, float y) { *reinterpret_cast<float2*>(p) = make_float2(x, y); }
 
@@ -166,8 +172,8 @@ gru_fwd_tc_kernel(const float* __restrict__ PX, int ldpx, int colg, int colc, co
     float u[4], rhv[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float r = sigmoid_acc(ar[e]);
-      u[e] = sigmoid_acc(au[e]);
+      const float r = sigm(ar[e]);
+      u[e] = sigm(au[e]);
       ar[e] = r;
       rhv[e] = r * h[e];
     }
@@ -188,7 +194,7 @@ gru_fwd_tc_kernel(const float* __restrict__ PX, int ldpx, int colg, int colc, co
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       if (t < G.len[r]) {
-        const float c0 = tanhf(ac[2 * r]), c1 = tanhf(ac[2 * r + 1]);
+        const float c0 = tanh_(ac[2 * r]), c1 = tanh_(ac[2 * r + 1]);
         st2(cand + (G.rowbase[r] + t) * U + G.col, c0, c1);
         h[2 * r] = u[2 * r] * h[2 * r] + (1.f - u[2 * r]) * c0;
         h[2 * r + 1] = u[2 * r + 1] * h[2 * r + 1] + (1.f - u[2 * r + 1]) * c1;
@@ -341,13 +347,13 @@ lstm_fwd_tc_kernel(const float* __restrict__ PX, int ldpx, int colL, int colTN, 
     float gi[4], gj[4], gf[4], go[4], cn[4], mn[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      gi[e] = sigmoid_acc(acc[0][e]);
-      gj[e] = tanhf(acc[1][e]);
-      gf[e] = sigmoid_acc(acc[2][e] + 1.0f);
-      go[e] = sigmoid_acc(acc[3][e]);
-      const float sn = sigmoid_acc(tn[e]), sl = sigmoid_acc(tl[e]);
+      gi[e] = sigm(acc[0][e]);
+      gj[e] = tanh_(acc[1][e]);
+      gf[e] = sigm(acc[2][e] + 1.0f);
+      go[e] = sigm(acc[3][e]);
+      const float sn = sigm(tn[e]), sl = sigm(tl[e]);
       cn[e] = gf[e] * sl * c[e] + gi[e] * sn * gj[e];
-      mn[e] = go[e] * tanhf(cn[e]);
+      mn[e] = go[e] * tanh_(cn[e]);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -427,9 +433,9 @@ lstm_bwd_tc_kernel(const float* __restrict__ PX, int ldpx, int colL, int colTN, 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const bool live = t < G.len[e >> 1];
-      const float sn = sigmoid_acc(tn[e]), sl = sigmoid_acc(tl[e]);
+      const float sn = sigm(tn[e]), sl = sigm(tl[e]);
       const float cn = gf[e] * sl * cp[e] + gi[e] * sn * gj[e];
-      const float tc = tanhf(cn);
+      const float tc = tanh_(cn);
       const float dmt = dm[e] + dr[e];
       const float dcn = dc[e] + dmt * go[e] * (1.f - tc * tc);
       dpo[e] = live ? dmt * tc * go[e] * (1.f - go[e]) : 0.f;
