@@ -4,6 +4,7 @@
 //
 // The step is a fixed sequence of kernel launches on one stream over a workspace allocated at
 // creation; no allocation, no host synchronisation until the scalar losses are read back.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -508,6 +509,46 @@ int alloc_bn(clsr_engine* e, BnLayer* b) {
 // ---- launch helpers --------------------------------------------------------------------------------
 inline int round16(int x) { return (x + 15) & ~15; }
 
+// ---- TMA tensor maps for the operand loads of the tcgen05 kernels -----------------------------------
+// cuTensorMapEncodeTiled is fetched through the runtime (no link against libcuda).  One map describes an
+// fp32 matrix [rows, cols] with row pitch ld; the kernels load boxes of {8 columns, 128 rows} = one plane.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+bool make_tmap(CUtensorMap* m, const float* base, int cols, long long rows, int ld) {
+  memset(m, 0, sizeof *m);
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc || !base) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {8, (cuuint32_t)tc::kTileM};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// Number of operand streams the TMA can load for this prologue (0: register loads): the rows must be plain
+// matrix rows, 16-byte aligned, and K a whole number of planes.
+int tma_streams(const AOp& a, int K) {
+  static const bool off = getenv("CLSR_NO_TMA") != nullptr;
+  if (off || !encode_tiled() || (K & 7) || K <= 0) return 0;
+  auto ok = [](const float* p, int ld) { return p && !((uintptr_t)p & 15) && !(ld & 3); };
+  if (a.mode == A_PLAIN || a.mode == A_BNRELU) return ok(a.A, a.lda) ? 1 : 0;
+  if (a.mode == A_AFFINE2) return (ok(a.A, a.lda) && ok(a.A2, a.lda2)) ? 2 : 0;
+  return 0;
+}
+
 // One tcgen05 launch: K <= 160 (W resident in shared memory), N <= 256 (one UMMA, one TMEM accumulator).
 int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, const float* W, int ldw,
                 const EpiOp& ep, bool stats) {
@@ -522,17 +563,25 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
     else if ((ep.flags & E_ACCUM) && ep.ldc == N && al16p(ep.C)) eop = 3;
   }
   const int st = stats ? 1 : 0;
-  tc::Smem L = tc::smem_layout(kpad, npad, N, nstages, eop, st);
-  if (L.total > e->tc_smem_max) {
-    nstages = 1;
-    L = tc::smem_layout(kpad, npad, N, nstages, eop, st);
+  int tma = tma_streams(a, K);
+  // first configuration that fits shared memory: prefer two stages + operand prefetch + TMA
+  const int cand[][3] = {{2, eop, tma}, {2, eop, tma == 2 ? 0 : tma}, {1, eop, tma}, {2, 0, tma},
+                         {1, eop, 0},   {2, 0, 0},                   {1, 0, 0}};
+  tc::Smem L;
+  bool fits = false;
+  for (const auto& c : cand) {
+    L = tc::smem_layout(kpad, npad, N, c[0], c[1], st, c[2]);
+    if (L.total <= e->tc_smem_max) { nstages = c[0]; eop = c[1]; tma = c[2]; fits = true; break; }
   }
-  if (L.total > e->tc_smem_max && eop) {
-    eop = 0; nstages = 2;
-    L = tc::smem_layout(kpad, npad, N, nstages, eop, st);
-    if (L.total > e->tc_smem_max) { nstages = 1; L = tc::smem_layout(kpad, npad, N, nstages, eop, st); }
+  if (!fits) return fail(e, CLSR_ERR_ARG, "tc_gemm %s: K=%d N=%d does not fit shared memory", name, K, N);
+  CUtensorMap tmA, tmA2;
+  memset(&tmA2, 0, sizeof tmA2);
+  if (tma >= 1 && !make_tmap(&tmA, a.A, K, M, a.lda)) tma = 0;
+  if (tma == 2 && !make_tmap(&tmA2, a.A2, K, M, a.lda2)) tma = 0;
+  if (!tma) {
+    memset(&tmA, 0, sizeof tmA);
+    L = tc::smem_layout(kpad, npad, N, nstages, eop, st, 0);
   }
-  if (L.total > e->tc_smem_max) return fail(e, CLSR_ERR_ARG, "tc_gemm %s: K=%d N=%d does not fit shared memory", name, K, N);
   uint32_t cols = 32;
   while ((int)cols < (stats ? 4 : 2) * npad) cols <<= 1;   // two accumulators (+ two statistic regions)
   int per_sm = e->smem_optin / (L.total + 6 * 1024);
@@ -541,8 +590,8 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   if (per_sm < 1) per_sm = 1;
   int tiles = cdiv(M, tc::kTileM);
   int grid = tiles < e->num_sms * per_sm ? tiles : e->num_sms * per_sm;
-  if (stats) tc::tc_gemm_kernel<true><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, a, W, ldw, ep);
-  else tc::tc_gemm_kernel<false><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, a, W, ldw, ep);
+  if (stats) tc::tc_gemm_kernel<true><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, tma, a, W, ldw, ep, tmA, tmA2);
+  else tc::tc_gemm_kernel<false><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, tma, a, W, ldw, ep, tmA, tmA2);
   POST(name);
   return 0;
 }
@@ -615,21 +664,41 @@ int tc_dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& 
   for (int n0 = 0; n0 < N; n0 += per) {
     int nn = N - n0 < per ? N - n0 : per;
     int npad = round16(nn);
-    int nstages = 2;
-    tc::DwSmem L = tc::dw_smem_layout(npad, nstages);
-    if (L.total > e->tc_dw_smem_max) { nstages = 1; L = tc::dw_smem_layout(npad, nstages); }
-    if (L.total > e->tc_dw_smem_max) return fail(e, CLSR_ERR_ARG, "tc_dwgemm %s: N slab %d does not fit", name, nn);
-    uint32_t cols = 32;
-    while ((int)cols < npad) cols <<= 1;
     AOp b2 = b;
     if (n0) {
       if (b.mode != A_PLAIN) return fail(e, CLSR_ERR_ARG, "tc_dwgemm %s: column slabs need a plain B operand", name);
       b2.A = b.A + n0;
     }
+    int nstages = 2;
+    int ta = tma_streams(a, K), tb = tma_streams(b2, nn);
+    static const bool prefer_tma = getenv("CLSR_DW_PREFER_TMA") != nullptr;
+    const int cand_a[][3] = {{2, ta, tb}, {2, ta == 2 ? 0 : ta, tb}, {2, ta == 2 ? 0 : ta, tb == 2 ? 0 : tb}, {1, ta, tb}, {2, 0, 0}, {1, 0, 0}};
+    const int cand_b[][3] = {{2, ta, tb}, {1, ta, tb}, {2, ta == 2 ? 0 : ta, tb}, {2, ta == 2 ? 0 : ta, tb == 2 ? 0 : tb}, {2, 0, 0}, {1, 0, 0}};
+    const int (*cand)[3] = prefer_tma ? cand_b : cand_a;
+    tc::DwSmem L;
+    bool fits = false;
+    for (int ci = 0; ci < 6; ++ci) {
+      const int* c = cand[ci];
+      L = tc::dw_smem_layout(K, nn, npad, c[0], c[1], c[2]);
+      if (L.total <= e->tc_dw_smem_max) { nstages = c[0]; ta = c[1]; tb = c[2]; fits = true; break; }
+    }
+    if (!fits) return fail(e, CLSR_ERR_ARG, "tc_dwgemm %s: N slab %d does not fit", name, nn);
+    CUtensorMap tmA, tmA2, tmB, tmB2;
+    memset(&tmA, 0, sizeof tmA); memset(&tmA2, 0, sizeof tmA2); memset(&tmB, 0, sizeof tmB); memset(&tmB2, 0, sizeof tmB2);
+    bool okm = true;
+    if (ta >= 1) okm = okm && make_tmap(&tmA, a.A, K, M, a.lda);
+    if (ta == 2) okm = okm && make_tmap(&tmA2, a.A2, K, M, a.lda2);
+    if (tb >= 1) okm = okm && make_tmap(&tmB, b2.A, nn, M, b2.lda);
+    if (tb == 2) okm = okm && make_tmap(&tmB2, b2.A2, nn, M, b2.lda2);
+    if (!okm) { ta = tb = 0; L = tc::dw_smem_layout(K, nn, npad, nstages, 0, 0); }
+    uint32_t cols = 32;
+    while ((int)cols < npad) cols <<= 1;
     int tiles = cdiv(M, tc::kTileM);
     int grid = tiles < e->num_sms ? tiles : e->num_sms;
-    tc::tc_dw_kernel<<<grid, tc::kDwThreads, L.total, e->stream>>>(M, K, nn, npad, nstages, cols, a, b2, dW + n0, lddw,
-                                                                 colsum ? colsum + n0 : nullptr);
+    const int octa = tc::dw_split(tc::kDwProducers / 8, ((colsum ? K + 1 : K) + 7) / 8, (nn + 7) / 8, tc::piece_cost(a.mode),
+                                  tc::piece_cost(b2.mode));
+    tc::tc_dw_kernel<<<grid, tc::kDwThreads, L.total, e->stream>>>(M, K, nn, npad, nstages, cols, ta, tb, octa, a, b2, dW + n0, lddw,
+                                                                 colsum ? colsum + n0 : nullptr, tmA, tmA2, tmB, tmB2);
     POST(name);
   }
   return 0;

@@ -28,6 +28,7 @@
 // of tile i+1, the MMA of tile i and the epilogue of tile i-1 overlap.  W (K x N, small) is split
 // once per CTA and stays resident in shared memory.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include <type_traits>
@@ -48,8 +49,10 @@ namespace tc {
 #endif
 
 constexpr int kTileM = 128;
-constexpr int kProducers = 224;                         // warps 0-6
-constexpr int kMmaWarp = 7;                             // MMA / bulk-copy warp
+constexpr int kProducers = 192;                         // warps 0-5
+constexpr int kLoadWarp = 6;                            // TMA operand loads / L2 prefetch
+constexpr int kMmaWarp = 7;                             // MMA issue + epilogue-operand bulk copies
+constexpr int kPlaneBytes = 4096;                       // one operand plane: 128 rows x (16 B hi + 16 B lo)
 constexpr int kEpilogue = 256;                          // warps 8-15
 constexpr int kThreads = 512;                           // 16 warps x 128 registers fill the register file
 
@@ -83,6 +86,13 @@ CLSR_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// 2-D tiled TMA load: box {8 columns, 128 rows} of an fp32 matrix = one operand plane's raw 4 KB
+CLSR_DEVINL void tma_load_plane(uint32_t smem_dst, const CUtensorMap* tm, int col, int row, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(tm), "r"(smem_u32(bar)), "r"(col), "r"(row)
+      : "memory");
 }
 // L2 prefetch of a contiguous byte range (no shared-memory destination, no completion tracking)
 CLSR_DEVINL void l2_prefetch(const void* gsrc, uint32_t bytes) {
@@ -173,9 +183,30 @@ CLSR_DEVINL uint32_t make_idesc(int npad) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
-// x[0..7] -> 8 bf16 "hi" + 8 bf16 "lo" (both round-to-nearest), one 16-byte shared-memory store each
+// Operand stage layout: plane p (8 K-elements) = 16 row-octet blocks of 256 bytes; a block holds the UMMA
+// core matrix of the bf16 hi parts (8 rows x 16 B) followed by the core matrix of the lo parts.  The raw
+// fp32 data of the same 8 rows x 8 elements is also exactly 256 bytes (8 x 32 B), which is what lets a TMA
+// box {8 columns, 128 rows} land in the plane and be converted in place.
+CLSR_DEVINL uint32_t piece_off(int plane, int r) { return (uint32_t)(plane * kPlaneBytes + (r >> 3) * 256 + (r & 7) * 16); }
+
+// x[0..7] -> 8 bf16 "hi" at dst, 8 bf16 "lo" at dst + 128 (both round-to-nearest), 16-byte shared stores
 // (32-bit shared-window addresses: no generic-pointer arithmetic in the producer loops).
-CLSR_DEVINL void split_store8(const float* x, uint32_t hi_dst, uint32_t lo_dst) {
+CLSR_DEVINL void split_store8(const float* x, uint32_t dst) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    const uint32_t hu = *reinterpret_cast<uint32_t*>(&hb);
+    const float h0 = __uint_as_float(hu << 16), h1 = __uint_as_float(hu & 0xffff0000u);
+    __nv_bfloat162 lb = __floats2bfloat162_rn(x[2 * i] - h0, x[2 * i + 1] - h1);
+    h[i] = hu;
+    l[i] = *reinterpret_cast<uint32_t*>(&lb);
+  }
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0+128], {%1,%2,%3,%4};" ::"r"(dst), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+}
+// W (the small resident operand) keeps separate hi / lo arrays
+CLSR_DEVINL void split_store8_w(const float* x, uint32_t hi_dst, uint32_t lo_dst) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -188,6 +219,11 @@ CLSR_DEVINL void split_store8(const float* x, uint32_t hi_dst, uint32_t lo_dst) 
   }
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hi_dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(lo_dst), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+}
+CLSR_DEVINL float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
 CLSR_DEVINL bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -288,7 +324,7 @@ CLSR_DEVINL void load_piece(const AOp& a, int m, int k0, bool second, F8& ra, F8
 // would keep its destination registers live across the whole kernel).
 template <int MODE, bool V256>
 CLSR_DEVINL void produce_fast(const AOp& a, const float* sv, int svld, int m0, int M, int nfull, int ptid, int nprod,
-                              uint32_t hi, uint32_t lo) {
+                              uint32_t base) {
   const int noct = nprod >> 3;
   const int per = noct / nfull;
   const int o = ptid >> 3, rl = ptid & 7;
@@ -309,8 +345,8 @@ CLSR_DEVINL void produce_fast(const AOp& a, const float* sv, int svld, int m0, i
     c2[0] = u0.x; c2[1] = u0.y; c2[2] = u0.z; c2[3] = u0.w; c2[4] = u1.x; c2[5] = u1.y; c2[6] = u1.z; c2[7] = u1.w;
   }
   const int rstep = per * 8;
-  const uint32_t sstep = (uint32_t)rstep * 16;
-  uint32_t soff = (uint32_t)(cc * (kTileM * 16) + (ro0 * 8 + rl) * 16);
+  const uint32_t sstep = (uint32_t)per * 256;
+  uint32_t soff = base + (uint32_t)(cc * kPlaneBytes + ro0 * 256 + rl * 16);
   // pieces in flight per thread: UN1 x 32 bytes (one stream) or UN2 x 64 bytes (two streams)
   constexpr int UN = (MODE == A_AFFINE2 || MODE == A_CATMUL || MODE == A_MULROW) ? CLSR_TC_UN2 : CLSR_TC_UN1;
 #pragma unroll 1
@@ -351,14 +387,79 @@ CLSR_DEVINL void produce_fast(const AOp& a, const float* sv, int svld, int m0, i
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = 0.f;
       }
-      split_store8(x, hi + soff + u * sstep, lo + soff + u * sstep);
+      split_store8(x, soff + u * sstep);
+    }
+  }
+}
+
+// In-place conversion of planes that the TMA delivered as raw fp32 (modes whose rows are plain matrix
+// rows: A_PLAIN, A_BNRELU, A_AFFINE2 with the second stream in raw2).  Same plane ownership as
+// produce_fast.  The eight threads of an octet read their block's 256 raw bytes, synchronise among
+// themselves, then overwrite the block with its hi / lo core matrices.
+template <int MODE>
+CLSR_DEVINL void convert_tile(const float* sv, int svld, int m0, int M, int nfull, int ptid, int nprod, uint32_t base,
+                              uint32_t raw2) {
+  const int noct = nprod >> 3;
+  const int per = noct / nfull;
+  const int o = ptid >> 3, rl = ptid & 7;
+  const int cc = o % nfull, ro0 = o / nfull;
+  if (ro0 >= per) return;
+  const int k0 = cc * 8;
+  const bool full = m0 + kTileM <= M;
+  const unsigned omask = 0xFFu << (8 * ((threadIdx.x & 31) >> 3));
+  float c0[8], c1[8], c2[8];
+  if (MODE == A_BNRELU || MODE == A_AFFINE2) {
+    const float4 p0 = *reinterpret_cast<const float4*>(sv + k0), p1 = *reinterpret_cast<const float4*>(sv + k0 + 4);
+    const float4 q0 = *reinterpret_cast<const float4*>(sv + svld + k0), q1 = *reinterpret_cast<const float4*>(sv + svld + k0 + 4);
+    c0[0] = p0.x; c0[1] = p0.y; c0[2] = p0.z; c0[3] = p0.w; c0[4] = p1.x; c0[5] = p1.y; c0[6] = p1.z; c0[7] = p1.w;
+    c1[0] = q0.x; c1[1] = q0.y; c1[2] = q0.z; c1[3] = q0.w; c1[4] = q1.x; c1[5] = q1.y; c1[6] = q1.z; c1[7] = q1.w;
+  }
+  if (MODE == A_AFFINE2) {
+    const float4 u0 = *reinterpret_cast<const float4*>(sv + 2 * svld + k0), u1 = *reinterpret_cast<const float4*>(sv + 2 * svld + k0 + 4);
+    c2[0] = u0.x; c2[1] = u0.y; c2[2] = u0.z; c2[3] = u0.w; c2[4] = u1.x; c2[5] = u1.y; c2[6] = u1.z; c2[7] = u1.w;
+  }
+  const uint32_t step = (uint32_t)per * 256;
+  uint32_t off = (uint32_t)(cc * kPlaneBytes + ro0 * 256);
+  constexpr int UN = 2;
+#pragma unroll 1
+  for (int ro = ro0; ro < 16; ro += per * UN, off += step * UN) {
+    float4 a0[UN], a1[UN], b0[UN], b1[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      // the second block of the last iteration may lie past the plane: read block `ro` again instead
+      const uint32_t o2 = off + (ro + u * per < 16 ? u * step : 0) + rl * 32;
+      a0[u] = lds4(base + o2); a1[u] = lds4(base + o2 + 16);
+      if (MODE == A_AFFINE2) { b0[u] = lds4(raw2 + o2); b1[u] = lds4(raw2 + o2 + 16); }
+    }
+    __syncwarp(omask);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (ro + u * per >= 16) continue;
+      const float v[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
+      float x[8];
+      if (MODE == A_PLAIN) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = v[i];
+      } else if (MODE == A_BNRELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaxf(0.f, fmaf(v[i], c0[i], c1[i]));
+      } else {
+        const float h[8] = {b0[u].x, b0[u].y, b0[u].z, b0[u].w, b1[u].x, b1[u].y, b1[u].z, b1[u].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaf(c0[i], v[i], fmaf(c1[i], h[i], c2[i]));
+      }
+      if (!full && m0 + (ro + u * per) * 8 + rl >= M) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = 0.f;
+      }
+      split_store8(x, base + off + u * step + rl * 16);
     }
   }
 }
 
 // Element-wise pieces: planes [c_lo, c_hi) (K edge, unaligned operands, the constant-one column).
 CLSR_DEVINL void produce_slow(const AOp& a, int m0, int M, int K, int c_lo, int c_hi, int one_col, int ptid,
-                                          int nprod, uint32_t hi, uint32_t lo) {
+                                          int nprod, uint32_t base) {
   const int ntask = kTileM * (c_hi - c_lo);
 #pragma unroll 1
   for (int task = ptid; task < ntask; task += nprod) {
@@ -371,33 +472,47 @@ CLSR_DEVINL void produce_slow(const AOp& a, int m0, int M, int K, int c_lo, int 
       x[i] = (m < M && k < K) ? a.load(m, k) : 0.f;
       if (k == one_col && m < M) x[i] = 1.0f;
     }
-    const uint32_t off = (uint32_t)(cc * kTileM * 16 + r * 16);
-    split_store8(x, hi + off, lo + off);
+    split_store8(x, base + piece_off(cc, r));
   }
 }
 
 // One operand tile (rows m0..m0+127, columns [0,K) and optionally a constant-one column at one_col).
 template <int MODE>
 CLSR_DEVINL void produce_fast_v(const AOp& a, bool v256, const float* sv, int svld, int m0, int M, int nfull, int ptid,
-                                int nprod, uint32_t hi, uint32_t lo) {
-  if (v256) produce_fast<MODE, true>(a, sv, svld, m0, M, nfull, ptid, nprod, hi, lo);
-  else produce_fast<MODE, false>(a, sv, svld, m0, M, nfull, ptid, nprod, hi, lo);
+                                int nprod, uint32_t base) {
+  if (v256) produce_fast<MODE, true>(a, sv, svld, m0, M, nfull, ptid, nprod, base);
+  else produce_fast<MODE, false>(a, sv, svld, m0, M, nfull, ptid, nprod, base);
 }
-CLSR_DEVINL void produce_tile(const AOp& a, Fast f, const float* sv, int svld, int m0, int M, int K, int one_col,
-                              int ptid, int nprod, uint32_t hi, uint32_t lo) {
-  int nfull = f.ok ? (K >> 3) : 0;
+// tma: 0 = the producers load the operand themselves; 1 / 2 = the loader warp's TMA has put the raw rows of
+// one / two streams into the stage (and raw2) and the producers only convert them.
+CLSR_DEVINL void produce_tile(const AOp& a, Fast f, int tma, const float* sv, int svld, int m0, int M, int K, int one_col,
+                              int ptid, int nprod, uint32_t base, uint32_t raw2) {
+  int nfull = (f.ok || tma) ? (K >> 3) : 0;
   if (nfull > (nprod >> 3)) nfull = 0;   // more planes than thread octets: element-wise path
   const int kall = one_col >= K ? one_col + 1 : K;
   const int nall = (kall + 7) >> 3;
-  if (nfull > 0) switch (a.mode) {
-    case A_PLAIN: produce_fast_v<A_PLAIN>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, hi, lo); break;
-    case A_BNRELU: produce_fast_v<A_BNRELU>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, hi, lo); break;
-    case A_AFFINE2: produce_fast_v<A_AFFINE2>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, hi, lo); break;
-    case A_CATMUL: produce_fast_v<A_CATMUL>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, hi, lo); break;
-    case A_MULROW: produce_fast_v<A_MULROW>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, hi, lo); break;
-    default: produce_fast_v<A_CAT2ROW>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, hi, lo); break;
+  if (nfull > 0 && tma) {
+    if (a.mode == A_PLAIN) convert_tile<A_PLAIN>(sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
+    else if (a.mode == A_BNRELU) convert_tile<A_BNRELU>(sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
+    else convert_tile<A_AFFINE2>(sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
+  } else if (nfull > 0) switch (a.mode) {
+    case A_PLAIN: produce_fast_v<A_PLAIN>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, base); break;
+    case A_BNRELU: produce_fast_v<A_BNRELU>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, base); break;
+    case A_AFFINE2: produce_fast_v<A_AFFINE2>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, base); break;
+    case A_CATMUL: produce_fast_v<A_CATMUL>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, base); break;
+    case A_MULROW: produce_fast_v<A_MULROW>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, base); break;
+    default: produce_fast_v<A_CAT2ROW>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, base); break;
   }
-  if (nall > nfull) produce_slow(a, m0, M, K, nfull, nall, one_col, ptid, nprod, hi, lo);
+  if (nall > nfull) produce_slow(a, m0, M, K, nfull, nall, one_col, ptid, nprod, base);
+}
+
+// Loader warp: TMA loads of the raw planes of one tile (tma = number of streams), all arriving on `bar`.
+CLSR_DEVINL void tma_issue_tile(int tma, const CUtensorMap* t1, const CUtensorMap* t2, int nplanes, int m0, uint32_t base,
+                                uint32_t raw2, uint64_t* bar, int lane) {
+  for (int p = lane; p < nplanes; p += 32) {
+    tma_load_plane(base + p * kPlaneBytes, t1, p * 8, m0, bar);
+    if (tma == 2) tma_load_plane(raw2 + p * kPlaneBytes, t2, p * 8, m0, bar);
+  }
 }
 
 // L2 prefetch of the HBM-streamed rows of one operand tile, issued by one warp a few tiles ahead of the
@@ -468,17 +583,20 @@ CLSR_DEVINL int colmap16(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3)
 
 struct Smem {
   // byte offsets into dynamic shared memory
-  int w_hi, w_lo, a_stage0, a_stage_bytes, eop, eop_bytes, vec, dstat, bars, total;
+  int w_hi, w_lo, a_stage0, a_stage_bytes, raw2, raw2_bytes, eop, eop_bytes, vec, dstat, bars, total;
 };
-// eop != 0 reserves two [128 x N] fp32 tiles for the prefetched epilogue operand.
-__host__ __device__ inline Smem smem_layout(int kpad, int npad, int N, int nstages, int eop, int stats) {
+// eop != 0 reserves two [128 x N] fp32 tiles for the prefetched epilogue operand; tma == 2 reserves one raw
+// buffer per stage for the second operand stream.
+__host__ __device__ inline Smem smem_layout(int kpad, int npad, int N, int nstages, int eop, int stats, int tma) {
   Smem s;
   const int wbytes = kpad * npad * 2;
   s.w_hi = 0;
   s.w_lo = wbytes;
   s.a_stage0 = 2 * wbytes;
-  s.a_stage_bytes = 2 * kTileM * kpad * 2;  // hi + lo
-  s.eop = s.a_stage0 + nstages * s.a_stage_bytes;
+  s.a_stage_bytes = (kpad / 8) * kPlaneBytes;
+  s.raw2 = s.a_stage0 + nstages * s.a_stage_bytes;
+  s.raw2_bytes = tma == 2 ? s.a_stage_bytes : 0;
+  s.eop = s.raw2 + nstages * s.raw2_bytes;
   s.eop_bytes = eop ? ((kTileM * N * 4 + 127) & ~127) : 0;
   s.vec = s.eop + 2 * s.eop_bytes;
   s.dstat = s.vec + (3 * kpad + 5 * npad) * 4;   // prologue vectors + bias / scale / shift / mean / rstd
@@ -491,13 +609,16 @@ __host__ __device__ inline Smem smem_layout(int kpad, int npad, int N, int nstag
 // STATS: accumulate per-column statistics into ep.stat (see gemm.cuh).
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tmem_cols, int eop_kind, AOp a,
-               const float* __restrict__ W, int ldw, EpiOp ep) {
+tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tmem_cols, int eop_kind, int tma, AOp a,
+               const float* __restrict__ W, int ldw, EpiOp ep, const __grid_constant__ CUtensorMap tmA,
+               const __grid_constant__ CUtensorMap tmA2) {
+  // tma: 0 = producers read the operand with register loads; 1 / 2 = the loader warp brings the raw rows of
+  // one / two operand streams in with 2-D TMA (one box per plane) and the producers convert in place.
   // eop_kind: which per-element epilogue operand is prefetched into shared memory by bulk copy
   // (0 none, 1 hpre, 2 group-add rows, 3 old C for accumulation); the host only selects one when the
   // operand rows are contiguous (leading dimension == N).
   extern __shared__ __align__(128) uint8_t smem[];
-  const Smem L = smem_layout(kpad, npad, N, nstages, eop_kind, STATS ? 1 : 0);
+  const Smem L = smem_layout(kpad, npad, N, nstages, eop_kind, STATS ? 1 : 0, tma);
   uint8_t* w_hi = smem + L.w_hi;
   uint8_t* w_lo = smem + L.w_lo;
   float* sv = reinterpret_cast<float*>(smem + L.vec);     // [3][kpad]
@@ -513,7 +634,8 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
   uint64_t* tfull = bars + 4;     // [2]
   uint64_t* tempty = bars + 6;    // [2]
   uint64_t* efull = bars + 8;     // [2] epilogue-operand tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* rawfull = bars + 10;  // [2] raw operand planes landed (TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (M + kTileM - 1) / kTileM;
@@ -530,7 +652,7 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
       x[i] = (k < K && n < N) ? W[(size_t)k * ldw + n] : 0.f;
     }
     const uint32_t off = (uint32_t)(c * npad * 16 + n * 16);
-    split_store8(x, smem_u32(w_hi) + off, smem_u32(w_lo) + off);
+    split_store8_w(x, smem_u32(w_hi) + off, smem_u32(w_lo) + off);
   }
   // operand stages start as zeros: planes past ceil(K/8) are never written again
   for (int i = tid; i < (nstages * L.a_stage_bytes) / 16; i += kThreads)
@@ -555,6 +677,7 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpilogue / 32);
       mbar_init(&efull[i], 1);
+      mbar_init(&rawfull[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -565,32 +688,53 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kMmaWarp) {
-    // =============================== producers ===============================
+  if (warp < kLoadWarp) {
+    // =============================== producers / converters ===============================
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it % nstages;
       const uint32_t ph = (it / nstages) & 1;
-      mbar_wait(&empty[s], ph ^ 1);
-      const uint32_t a_hi = smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes);
-      const uint32_t a_lo = a_hi + kTileM * kpad * 2;
-      produce_tile(a, fa, sv, kpad, tile * kTileM, M, K, -1, tid, kProducers, a_hi, a_lo);
+      if (tma) mbar_wait(&rawfull[s], ph);      // implies empty[s]: the loader waited for it
+      else {
+        mbar_wait(&empty[s], ph ^ 1);
+        // register-load path: warp 0 prefetches the rows of a later tile into L2 (paced by the pipeline)
+        if (CLSR_TC_PREFETCH && warp == 0)
+          prefetch_operand(a, (tile + CLSR_TC_PREFETCH * (int)gridDim.x) * kTileM, M, K, lane);
+      }
+      const uint32_t a_base = smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes);
+      const uint32_t a_raw2 = smem_u32(smem + L.raw2 + s * L.raw2_bytes);
+      produce_tile(a, fa, tma, sv, kpad, tile * kTileM, M, K, -1, tid, kProducers, a_base, a_raw2);
       fence_proxy_async();
       mbar_arrive(&full[s]);
+    }
+  } else if (warp == kLoadWarp) {
+    // =============================== operand loader ===============================
+    // (idle on the register-load path: a role that nothing waits for must not wait on the ring barriers,
+    //  it could fall two phases behind and alias the parity)
+    int it = 0;
+    for (int tile = blockIdx.x; tma && tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it % nstages;
+      const uint32_t ph = (it / nstages) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      const int nplanes = K >> 3;
+      if (lane == 0) mbar_expect_tx(&rawfull[s], (uint32_t)(nplanes * kPlaneBytes * tma));
+      __syncwarp();
+      tma_issue_tile(tma, &tmA, &tmA2, nplanes, tile * kTileM, smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes),
+                     smem_u32(smem + L.raw2 + s * L.raw2_bytes), &rawfull[s], lane);
     }
   } else if (warp == kMmaWarp) {
     // ====================== MMA issue + epilogue-operand prefetch ======================
     const uint32_t idesc = make_idesc(npad);
-    const uint32_t lbo_a = kTileM * 16, lbo_b = (uint32_t)npad * 16, sbo = 128;
-    const uint64_t bdesc_hi = make_desc(smem_u32(w_hi), lbo_b, sbo);
-    const uint64_t bdesc_lo = make_desc(smem_u32(w_lo), lbo_b, sbo);
+    // A: planes 4 KB apart, 8-row groups 256 B apart, lo core matrices 128 B behind the hi ones; W: plain planes
+    const uint32_t lbo_a = kPlaneBytes, sbo_a = 256, lbo_b = (uint32_t)npad * 16, sbo_b = 128;
+    const uint64_t bdesc_hi = make_desc(smem_u32(w_hi), lbo_b, sbo_b);
+    const uint64_t bdesc_lo = make_desc(smem_u32(w_lo), lbo_b, sbo_b);
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it % nstages;
       const uint32_t ph = (it / nstages) & 1;
       const int acc = it & 1;
       const uint32_t pa = (it >> 1) & 1;
-      if (CLSR_TC_PREFETCH) prefetch_operand(a, (tile + CLSR_TC_PREFETCH * (int)gridDim.x) * kTileM, M, K, lane);
       mbar_wait(&tempty[acc], pa ^ 1);   // the epilogue of tile it-2 has released accumulator and operand tile
       if (eop_kind && lane == 0) {
         const int m0 = tile * kTileM;
@@ -616,8 +760,8 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_base = smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes);
-        const uint64_t adesc_hi = make_desc(a_base, lbo_a, sbo);
-        const uint64_t adesc_lo = make_desc(a_base + kTileM * kpad * 2, lbo_a, sbo);
+        const uint64_t adesc_hi = make_desc(a_base, lbo_a, sbo_a);
+        const uint64_t adesc_lo = make_desc(a_base + 128, lbo_a, sbo_a);
         const uint32_t d = tmem_base + (uint32_t)(acc * npad);
         for (int kb = 0; kb < nkb; ++kb) {
           // advance both operands by one 16-wide K block = two planes
@@ -869,36 +1013,69 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
 // TMEM read + fp32 atomicAdd per CTA at the end.  A constant-one column appended to A at index K
 // yields the column sums of op_b(B) (bias gradients) in accumulator row K for free.
 struct DwSmem {
-  int a_bytes, b_bytes, stage_bytes, bars, total;
+  int a_bytes, b_bytes, a2_bytes, b2_bytes, stage_bytes, bars, total;
 };
-__host__ __device__ inline DwSmem dw_smem_layout(int npad, int nstages) {
+// Stage = [A planes (16) | B planes (npad / 8) | raw second stream of A | raw second stream of B].
+__host__ __device__ inline DwSmem dw_smem_layout(int K, int N, int npad, int nstages, int tma_a, int tma_b) {
   DwSmem s;
-  s.a_bytes = 2 * 16 * kTileM * 16;           // hi + lo, 16 planes (128 MMA lanes) x 128 rows x 16 B
-  s.b_bytes = 2 * (npad / 8) * kTileM * 16;   // hi + lo
-  s.stage_bytes = s.a_bytes + s.b_bytes;
+  s.a_bytes = 16 * kPlaneBytes;            // 16 planes = the 128 MMA lanes
+  s.b_bytes = (npad / 8) * kPlaneBytes;
+  s.a2_bytes = tma_a == 2 ? (K >> 3) * kPlaneBytes : 0;
+  s.b2_bytes = tma_b == 2 ? (N >> 3) * kPlaneBytes : 0;
+  s.stage_bytes = s.a_bytes + s.b_bytes + s.a2_bytes + s.b2_bytes;
   s.bars = nstages * s.stage_bytes;
   s.total = s.bars + 128;
   return s;
 }
 
-constexpr int kDwProducers = 384;
-constexpr int kDwThreads = kDwProducers + 32;  // 12 producer warps (warps 0-3 also run the final epilogue) + MMA warp
+// Split of the producer octets between the two operands: every octet owns one plane and every
+// floor(octets / planes)-th row octet of it, so the slab time of a group is ceil(16 / floor(octets / planes))
+// pieces per thread times the cost of a piece; pick the split with the smallest maximum.
+inline int dw_split(int noct, int planes_a, int planes_b, int cost_a, int cost_b) {
+  int best = planes_a, best_cost = 1 << 30;
+  for (int oa = planes_a; oa <= noct - planes_b; ++oa) {
+    const int pa = oa / planes_a, pb = (noct - oa) / planes_b;
+    const int ca = ((16 + pa - 1) / pa) * cost_a, cb = ((16 + pb - 1) / pb) * cost_b;
+    const int c = ca > cb ? ca : cb;
+    if (c < best_cost) { best_cost = c; best = oa; }
+  }
+  return best;
+}
+inline int piece_cost(int mode) {   // relative instruction cost of producing one piece
+  switch (mode) {
+    case A_PLAIN: return 10;
+    case A_BNRELU: return 12;
+    case A_AFFINE2: return 18;
+    case A_CATMUL: return 18;
+    case A_MULROW: return 24;
+    default: return 13;
+  }
+}
+
+constexpr int kDwProducers = 384;              // warps 0-11 (warps 0-3 also run the final epilogue)
+constexpr int kDwLoadWarp = 12;                // TMA operand loads / L2 prefetch
+constexpr int kDwMmaWarp = 13;
+constexpr int kDwThreads = 448;
 
 __global__ void __launch_bounds__(kDwThreads, 1)
-tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, AOp a, AOp b,
-             float* __restrict__ dW, int lddw, float* __restrict__ colsum) {
+tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, int tma_a, int tma_b, int octa, AOp a, AOp b,
+             float* __restrict__ dW, int lddw, float* __restrict__ colsum, const __grid_constant__ CUtensorMap tmA,
+             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmB2) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(16) float sva[3 * 128];
   __shared__ __align__(16) float svb[3 * 256];
-  const DwSmem L = dw_smem_layout(npad, nstages);
+  const DwSmem L = dw_smem_layout(K, N, npad, nstages, tma_a, tma_b);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint64_t* full = bars;       // [2]
-  uint64_t* empty = bars + 2;  // [2]
-  uint64_t* done = bars + 4;   // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* full = bars;         // [2]
+  uint64_t* empty = bars + 2;    // [2]
+  uint64_t* done = bars + 4;     // [1]
+  uint64_t* rawfull = bars + 5;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (M + kTileM - 1) / kTileM;
   const Fast fa = fast_eligible(a), fb = fast_eligible(b);
+  const bool any_tma = tma_a || tma_b;
 
   // zero the operand stages once: lanes / columns past the operand widths stay zero for the whole kernel
   for (int i = tid; i < (nstages * L.stage_bytes) / 16; i += kDwThreads)
@@ -906,61 +1083,81 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, AOp
   stage_vectors(a, sva, 128, K, tid, kDwThreads);
   stage_vectors(b, svb, 256, N, tid, kDwThreads);
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], kDwProducers); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], kDwProducers); mbar_init(&empty[i], 1); mbar_init(&rawfull[i], 1); }
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == kDwMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 12) {
-    const int pa = ((colsum ? K + 1 : K) + 7) >> 3, pb = (N + 7) >> 3;   // planes per operand
-    int octa = (kDwProducers / 8 * pa + (pa + pb) / 2) / (pa + pb);
-    if (octa < pa) octa = pa;
-    if (kDwProducers / 8 - octa < pb) octa = kDwProducers / 8 - pb;
+  if (warp < kDwLoadWarp) {
+    // octa (chosen on the host, dw_split): producer octets that work on A; the rest work on B
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it % nstages;
       const uint32_t ph = (it / nstages) & 1;
-      mbar_wait(&empty[s], ph ^ 1);
-      const uint32_t a_hi = smem_u32(smem + s * L.stage_bytes);
-      const uint32_t a_lo = a_hi + L.a_bytes / 2;
-      const uint32_t b_hi = a_hi + L.a_bytes;
-      const uint32_t b_lo = b_hi + L.b_bytes / 2;
+      // a group whose operand comes by TMA waits for the raw planes (which implies empty[s]: the loader
+      // waited for it); a group that loads its operand itself only needs the stage to be free
+      if (tid < octa * 8 ? tma_a != 0 : tma_b != 0) mbar_wait(&rawfull[s], ph);
+      else {
+        mbar_wait(&empty[s], ph ^ 1);
+        // register-load path: the first warp of the group prefetches the rows of a later slab into L2
+        if (CLSR_TC_PREFETCH) {
+          const int mp = (tile + CLSR_TC_PREFETCH * (int)gridDim.x) * kTileM;
+          if (warp == 0 && !tma_a) prefetch_operand(a, mp, M, K, lane);
+          if (warp == (octa * 8 + 31) / 32 && tid >= octa * 8 && !tma_b) prefetch_operand(b, mp, M, N, lane);
+        }
+      }
+      const uint32_t a_base = smem_u32(smem + s * L.stage_bytes);
+      const uint32_t b_base = a_base + L.a_bytes;
+      const uint32_t a_raw2 = b_base + L.b_bytes;
+      const uint32_t b_raw2 = a_raw2 + L.a2_bytes;
       const int m0 = tile * kTileM;
       // the producer octets are split between the two operands in proportion to their plane counts, so
       // the loads of A and B are in flight together (one exposed load latency per slab, not two)
-      if (tid < octa * 8) produce_tile(a, fa, sva, 128, m0, M, K, colsum ? K : -1, tid, octa * 8, a_hi, a_lo);
-      else produce_tile(b, fb, svb, 256, m0, M, N, -1, tid - octa * 8, kDwProducers - octa * 8, b_hi, b_lo);
+      if (tid < octa * 8) produce_tile(a, fa, tma_a, sva, 128, m0, M, K, colsum ? K : -1, tid, octa * 8, a_base, a_raw2);
+      else produce_tile(b, fb, tma_b, svb, 256, m0, M, N, -1, tid - octa * 8, kDwProducers - octa * 8, b_base, b_raw2);
       fence_proxy_async();
       mbar_arrive(&full[s]);
+    }
+  } else if (warp == kDwLoadWarp) {
+    // idle unless an operand comes by TMA (see the loader role of tc_gemm_kernel)
+    int it = 0;
+    for (int tile = blockIdx.x; any_tma && tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it % nstages;
+      const uint32_t ph = (it / nstages) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      const uint32_t a_base = smem_u32(smem + s * L.stage_bytes);
+      const uint32_t b_base = a_base + L.a_bytes;
+      const uint32_t a_raw2 = b_base + L.b_bytes;
+      const uint32_t b_raw2 = a_raw2 + L.a2_bytes;
+      if (lane == 0)
+        mbar_expect_tx(&rawfull[s], (uint32_t)(((K >> 3) * tma_a + (N >> 3) * tma_b) * kPlaneBytes));
+      __syncwarp();
+      if (tma_a) tma_issue_tile(tma_a, &tmA, &tmA2, K >> 3, tile * kTileM, a_base, a_raw2, &rawfull[s], lane);
+      if (tma_b) tma_issue_tile(tma_b, &tmB, &tmB2, N >> 3, tile * kTileM, b_base, b_raw2, &rawfull[s], lane);
     }
   } else {
     // MMA issue: D[128 x npad] += A^T-slab . B-slab, both operands MN-major
     const uint32_t idesc = make_idesc(npad) | (1u << 15) | (1u << 16);
-    const uint32_t lbo = 128, sbo = kTileM * 16;  // MN-major: LBO = 8-row group along the reduction, SBO = plane
+    const uint32_t lbo = 256, sbo = kPlaneBytes;  // MN-major: LBO = 8-row group along the reduction, SBO = plane
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it % nstages;
       const uint32_t ph = (it / nstages) & 1;
-      if (CLSR_TC_PREFETCH) {
-        const int mp = (tile + CLSR_TC_PREFETCH * (int)gridDim.x) * kTileM;
-        prefetch_operand(a, mp, M, K, lane);
-        prefetch_operand(b, mp, M, N, lane);
-      }
       mbar_wait(&full[s], ph);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_base = smem_u32(smem + s * L.stage_bytes);
         const uint32_t b_base = a_base + L.a_bytes;
-        const uint64_t a_hi = make_desc(a_base, lbo, sbo), a_lo = make_desc(a_base + L.a_bytes / 2, lbo, sbo);
-        const uint64_t b_hi = make_desc(b_base, lbo, sbo), b_lo = make_desc(b_base + L.b_bytes / 2, lbo, sbo);
+        const uint64_t a_hi = make_desc(a_base, lbo, sbo), a_lo = make_desc(a_base + 128, lbo, sbo);
+        const uint64_t b_hi = make_desc(b_base, lbo, sbo), b_lo = make_desc(b_base + 128, lbo, sbo);
         for (int rb = 0; rb < kTileM / 16; ++rb) {
-          const uint64_t adv = (uint64_t)((rb * 16 * 16) >> 4);  // 16 rows x 16 bytes
+          const uint64_t adv = (uint64_t)((rb * 2 * 256) >> 4);  // 16 rows = two 256-byte row-octet blocks
           umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (it > 0 || rb > 0) ? 1u : 0u);
           umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
           umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
@@ -993,7 +1190,7 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, AOp
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kDwMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
