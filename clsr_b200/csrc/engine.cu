@@ -671,10 +671,8 @@ int tc_dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& 
     }
     int nstages = 2;
     int ta = tma_streams(a, K), tb = tma_streams(b2, nn);
-    static const bool prefer_tma = getenv("CLSR_DW_PREFER_TMA") != nullptr;
-    const int cand_a[][3] = {{2, ta, tb}, {2, ta == 2 ? 0 : ta, tb}, {2, ta == 2 ? 0 : ta, tb == 2 ? 0 : tb}, {1, ta, tb}, {2, 0, 0}, {1, 0, 0}};
-    const int cand_b[][3] = {{2, ta, tb}, {1, ta, tb}, {2, ta == 2 ? 0 : ta, tb}, {2, ta == 2 ? 0 : ta, tb == 2 ? 0 : tb}, {2, 0, 0}, {1, 0, 0}};
-    const int (*cand)[3] = prefer_tma ? cand_b : cand_a;
+    // first configuration that fits: two stages beat TMA with one stage (measured on dWs0t: 0.25 vs 0.28 ms)
+    const int cand[][3] = {{2, ta, tb}, {2, ta == 2 ? 0 : ta, tb}, {2, ta == 2 ? 0 : ta, tb == 2 ? 0 : tb}, {1, ta, tb}, {2, 0, 0}, {1, 0, 0}};
     tc::DwSmem L;
     bool fits = false;
     for (int ci = 0; ci < 6; ++ci) {

@@ -1032,13 +1032,15 @@ __host__ __device__ inline DwSmem dw_smem_layout(int K, int N, int npad, int nst
 // floor(octets / planes)-th row octet of it, so the slab time of a group is ceil(16 / floor(octets / planes))
 // pieces per thread times the cost of a piece; pick the split with the smallest maximum.
 inline int dw_split(int noct, int planes_a, int planes_b, int cost_a, int cost_b) {
-  int best = planes_a, best_cost = 1 << 30;
-  for (int oa = planes_a; oa <= noct - planes_b; ++oa) {
+  // whole warps only (4 octets): a warp that straddles the two groups would run both kinds of work serially
+  int best = -1, best_cost = 1 << 30;
+  for (int oa = (planes_a + 3) / 4 * 4; oa <= noct - planes_b; oa += 4) {
     const int pa = oa / planes_a, pb = (noct - oa) / planes_b;
     const int ca = ((16 + pa - 1) / pa) * cost_a, cb = ((16 + pb - 1) / pb) * cost_b;
     const int c = ca > cb ? ca : cb;
     if (c < best_cost) { best_cost = c; best = oa; }
   }
+  if (best < 0) best = planes_a;   // no warp-aligned split leaves room for B: fall back to the tightest one
   return best;
 }
 inline int piece_cost(int mode) {   // relative instruction cost of producing one piece
