@@ -184,6 +184,9 @@ shard_scatter_hist_kernel(const float* __restrict__ dX, const int32_t* __restric
 // owners with ONE cp.reduce.async.bulk.add.f32 each - the fabric carries a 448-byte reduction instead of
 // 28 sixteen-byte ones.  NSLOT positions per warp are in flight.  Hot ids (popularity ranks < hot, category
 // 0) are still summed per CTA in shared memory first, cooperatively by the 32 lanes.
+// Measured (config-4 rows, 2 GPUs): same 0.53 ms as the element-wise kernel with 28x fewer reduction
+// instructions; without the padding-row cache either form takes 1.4 ms.  The remaining cost scales with the
+// remote share, not with packet count or hot-row count (A/B in DESIGN.md section 7).
 constexpr int SB_WARPS = 8, SB_NSLOT = 4;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -449,6 +452,7 @@ int clsr_shard_scatter_add_history(clsr_shard_table* item, clsr_shard_table* cat
   if (hot > 64) hot = 64;
   if ((long long)hot > item->n_rows) hot = (int)item->n_rows;
   static const bool use_red = getenv("CLSR_SHARD_SCATTER_RED") != nullptr;   // element-wise reductions (A/B, fallback)
+
   if (!use_red) {
     const int D = item->dim + cate->dim;
     const int nacc = hot * item->dim + cate->dim;
