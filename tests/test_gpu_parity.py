@@ -91,12 +91,24 @@ def test_ragged_batch_and_long_window(cuda_lib):
     _check(res)
 
 
-def _train_both(optimizer, group, steps, clip, G=5, S=20, seed=5):
+def test_ragged_long_window_tensor_core_path(cuda_lib):
+    """T = 250, 13 sequences: 3250 / 16250 operand rows = partial last tiles for the TMA loads, the
+    in-place conversion and the row-per-thread epilogue."""
+    G, S, T = 5, 13, 250
+    feed, prm = PU.small_problem(S=S, G=G, T=T, seed=11)
+    eng = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, T=T, G=G, math_mode=1)
+    res, _ = PU.compare_step(eng, feed, prm, G, G, metric=PU.relerr_l2)
+    bad = {k: v for k, v in res.items() if not k.endswith("b_nn_output") and
+           not v < (FWD_TOL if k.startswith(("fwd/", "loss/")) else 0.5 if k.startswith("uniq/") else 2e-2)}
+    assert not bad, bad
+
+
+def _train_both(optimizer, group, steps, clip, G=5, S=20, seed=5, **kw):
     import torch
     from oracle import clsr_oracle as O
     feed, prm = PU.small_problem(S=S, G=G, seed=seed)
     feeds = [feed] + [PU.small_problem(S=S, G=G, seed=seed + 10 + i)[0] for i in range(steps - 1)]
-    eng = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, G=G, optimizer=optimizer, max_grad_norm=clip)
+    eng = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, G=G, optimizer=optimizer, max_grad_norm=clip, **kw)
     cfg = PU.oracle_config(G, optimizer=optimizer, max_grad_norm=clip)
     ref = {k: v.copy() for k, v in prm.items()}
     slots = {}
@@ -126,6 +138,14 @@ def test_training_steps_match_oracle(cuda_lib, optimizer):
     assert not bad, bad
 
 
+def test_training_steps_tensor_core_path(cuda_lib):
+    """Three optimizer steps with math_mode=1 (tcgen05 GEMMs, mma.sync recurrences): losses within 2e-4,
+    every variable within 5 % of the distance the oracle moved it (Adam normalises gradient noise)."""
+    worst, _ = _train_both("adam", group=5, steps=3, clip=2.0, S=32, math_mode=1)
+    bad = {k: v for k, v in worst.items() if v[0] > 0.05 * v[1] + 1e-7}
+    assert not bad, bad
+
+
 def test_clip_by_norm_on_slices(cuda_lib):
     """max_grad_norm small enough that every variable is clipped; ungrouped run = TF semantics
     (norm over the concatenated, not yet de-duplicated IndexedSlices)."""
@@ -151,6 +171,20 @@ def test_predict_matches_oracle(cuda_lib):
     # logits within 1e-3 relative (north star)
     logit = eng.debug("logit", (S,))
     assert PU.relerr(logit, ref["logit"].numpy().reshape(-1)) < 1e-3
+
+
+def test_predict_tensor_core_path(cuda_lib):
+    """Inference on the tensor-core path: logits within 1e-3 relative (north star)."""
+    import torch
+    from oracle import clsr_oracle as O
+    S = 61
+    feed, prm = PU.small_problem(S=S, G=1, seed=19)
+    eng = PU.make_engine(prm, NI, NC, NU, max_rows=64, G=5, training=False, math_mode=1)
+    pred, alpha = eng.predict(feed, group=1)
+    ref = O.predict(prm, feed, PU.oracle_config(5), torch.float64)
+    assert PU.relerr(pred, ref["pred"].numpy().reshape(-1)) < FWD_TOL
+    assert PU.relerr(alpha, ref["alpha"].numpy().reshape(-1)) < FWD_TOL
+    assert PU.relerr(eng.debug("logit", (S,)), ref["logit"].numpy().reshape(-1)) < 1e-3
 
 
 def test_gather_bit_exact_and_scatter_add(cuda_lib):
