@@ -939,8 +939,12 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
 
   // ---- hoisted input projections of the three recurrences ----
   float *TNL = e->B("TNL"), *PX = e->B("PX");
-  time_feat_kernel<<<grid1d(e, M * 2 * H, 256), 256, 0, st>>>(c.ttn, c.tfa, c.seq_stride, T, e->P + e->p_tw1, e->P + e->p_tb1,
-                                                             e->P + e->p_tw2, e->P + e->p_tb2, H, TNL, M);
+  if ((H & 3) == 0)
+    time_feat_v4_kernel<<<grid1d(e, M * 2 * H / 4, 256, 16), 256, 0, st>>>(c.ttn, c.tfa, c.seq_stride, T, e->P + e->p_tw1,
+                                                                          e->P + e->p_tb1, e->P + e->p_tw2, e->P + e->p_tb2, H, TNL, M);
+  else
+    time_feat_kernel<<<grid1d(e, M * 2 * H, 256), 256, 0, st>>>(c.ttn, c.tfa, c.seq_stride, T, e->P + e->p_tw1, e->P + e->p_tb1,
+                                                               e->P + e->p_tw2, e->P + e->p_tb2, H, TNL, M);
   POST("time_feat");
   if ((rc = gemm(e, "px", (int)M, NX, D, a_plain(X, D), W("Wx_all"), NX, e_store(PX, NX, W("bx_all")), false))) return rc;
   if ((rc = gemm(e, "px_time", (int)M, 3 * H, 2 * H, a_plain(TNL, 2 * H), W("Wt"), 3 * H,
@@ -1225,10 +1229,17 @@ int backward(clsr_engine* e, const StepCtx& c) {
     return rc;
   {
     int ppc = cdiv(M, (long long)e->num_sms * 4);
-    int nx = ((2 * H + 31) / 32) * 32, ny = 1024 / nx > 8 ? 8 : (1024 / nx > 0 ? 1024 / nx : 1);
-    time_feat_bwd_kernel<<<cdiv(M, ppc), dim3(nx, ny), (size_t)2 * ny * 2 * H * 4, st>>>(
-        dTNL, TNL, c.ttn, c.tfa, c.seq_stride, T, H, M, ppc, e->Pg + e->p_tw1, e->Pg + e->p_tb1, e->Pg + e->p_tw2,
-        e->Pg + e->p_tb2);
+    if ((H & 3) == 0 && 2 * H / 4 <= 32) {
+      const int q4 = 2 * H / 4, ny = 1024 / q4 > 32 ? 32 : 1024 / q4;
+      time_feat_bwd_v4_kernel<<<cdiv(M, ppc), dim3(q4, ny), (size_t)2 * ny * 2 * H * 4, st>>>(
+          dTNL, TNL, c.ttn, c.tfa, c.seq_stride, T, H, M, ppc, e->Pg + e->p_tw1, e->Pg + e->p_tb1, e->Pg + e->p_tw2,
+          e->Pg + e->p_tb2);
+    } else {
+      int nx = ((2 * H + 31) / 32) * 32, ny = 1024 / nx > 8 ? 8 : (1024 / nx > 0 ? 1024 / nx : 1);
+      time_feat_bwd_kernel<<<cdiv(M, ppc), dim3(nx, ny), (size_t)2 * ny * 2 * H * 4, st>>>(
+          dTNL, TNL, c.ttn, c.tfa, c.seq_stride, T, H, M, ppc, e->Pg + e->p_tw1, e->Pg + e->p_tb1, e->Pg + e->p_tw2,
+          e->Pg + e->p_tb2);
+    }
     POST("time_feat_bwd");
   }
   if ((rc = dwgemm(e, "dWgh1", (int)M, U, 2 * U, a_plain(e->B("hp1"), U), a_plain(dPX + e->oG1, NX), dW("Wgh1"), 2 * U, nullptr))) return rc;
@@ -1371,7 +1382,7 @@ int optimizer_step(clsr_engine* e) {
   double t = (double)e->adam_step;
   float lr_t = (float)(cf.learning_rate * sqrt(1.0 - pow((double)cf.beta2, t)) / (1.0 - pow((double)cf.beta1, t)));
   AdamDense hd = {lr_t, cf.beta1, cf.beta2, cf.adam_eps, cf.clip_norm ? cf.max_grad_norm : 0.f};
-  dense_adam_kernel<<<(int)e->dense.size(), 256, 0, st>>>(e->d_vars, e->P, e->Pm, e->Pv, e->Pg, e->d_norms, hd);
+  dense_adam_kernel<<<(int)e->dense.size(), 1024, 0, st>>>(e->d_vars, e->P, e->Pm, e->Pv, e->Pg, e->d_norms, hd);
   POST("dense_adam");
   AdamHyper hp = {lr_t, cf.beta1, cf.beta2, cf.adam_eps, cf.clip_norm ? cf.max_grad_norm : 0.f};
   const int slot_ix[4] = {0, 1, 2, 2}, cnt_ix[4] = {1, 2, 3, 3};
@@ -1701,7 +1712,7 @@ int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, cls
   if ((rc = sparse_grads(e, c))) return rc;
   blockop_kernel<<<e->n_unprep, 256, 0, e->stream>>>(e->ops_unprep, e->Pg, e->dWd);
   POST("unprep_grads");
-  dense_l2_norm_kernel<<<(int)e->dense.size(), 256, 0, e->stream>>>(e->d_vars, e->P, e->Pg, e->cfg.layer_l2, e->d_norms, e->acc);
+  dense_l2_norm_kernel<<<(int)e->dense.size(), 1024, 0, e->stream>>>(e->d_vars, e->P, e->Pg, e->cfg.layer_l2, e->d_norms, e->acc);
   POST("dense_l2_norm");
   loss_finalize_kernel<<<1, 32, 0, e->stream>>>(e->acc, e->counts, e->counts + 3, c.G, e->U, e->cfg.embed_l2,
                                                 e->cfg.contrastive_weight, e->cfg.discrepancy_weight, e->d_losses);

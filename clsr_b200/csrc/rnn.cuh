@@ -461,4 +461,68 @@ __global__ void time_feat_bwd_kernel(const float* __restrict__ dTNL, const float
   }
 }
 
+// 16-byte vectorised forms of the two time-feature kernels (H multiple of 4): one thread = one column quad of
+// one position, a quarter of the index arithmetic and of the memory instructions.
+__global__ void time_feat_v4_kernel(const float* __restrict__ ttn, const float* __restrict__ tfa, int seq_stride,
+                                    int T, const float* __restrict__ w1, const float* __restrict__ b1,
+                                    const float* __restrict__ w2, const float* __restrict__ b2, int H,
+                                    float* __restrict__ TNL, long long npos) {
+  const int Q4 = (2 * H) >> 2;
+  const long long n = npos * Q4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / Q4;
+    const int j = (int)(i - p * Q4) * 4;
+    const long long s = p / T;
+    const long long io = s * seq_stride + (p - s * T);
+    const bool first = j < H;
+    const float tm = first ? ttn[io] : tfa[io];
+    const float* w = first ? w1 + j : w2 + (j - H);   // scalar loads: the vectors sit at arbitrary offsets of the
+    const float* b = first ? b1 + j : b2 + (j - H);   // dense-variable buffer
+    float4 v;
+    v.x = tanhf(fmaf(tm, __ldg(w), __ldg(b))); v.y = tanhf(fmaf(tm, __ldg(w + 1), __ldg(b + 1)));
+    v.z = tanhf(fmaf(tm, __ldg(w + 2), __ldg(b + 2))); v.w = tanhf(fmaf(tm, __ldg(w + 3), __ldg(b + 3)));
+    reinterpret_cast<float4*>(TNL)[i] = v;
+  }
+}
+
+// blockDim = (2H / 4 column quads, NY row lanes); dynamic shared memory 2 * NY * 2H floats.
+__global__ void time_feat_bwd_v4_kernel(const float* __restrict__ dTNL, const float* __restrict__ TNL,
+                                        const float* __restrict__ ttn, const float* __restrict__ tfa,
+                                        int seq_stride, int T, int H, long long npos, int pos_per_cta,
+                                        float* __restrict__ dw1, float* __restrict__ db1,
+                                        float* __restrict__ dw2, float* __restrict__ db2) {
+  extern __shared__ float red[];  // [2][NY][2H]
+  const int H2 = 2 * H, Q4 = H2 >> 2;
+  const int q = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
+  const int j = q * 4;
+  const long long p0 = (long long)blockIdx.x * pos_per_cta;
+  const long long p1 = min(npos, p0 + pos_per_cta);
+  float aw[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* tsrc = j < H ? ttn : tfa;
+#pragma unroll 4
+  for (long long p = p0 + ty; p < p1; p += ny) {
+    const long long s = p / T;
+    const float tm = tsrc[s * seq_stride + (p - s * T)];
+    const float4 y = ldg_stream(reinterpret_cast<const float4*>(TNL) + p * Q4 + q);
+    const float4 g = ldg_stream(reinterpret_cast<const float4*>(dTNL) + p * Q4 + q);
+    const float d0 = g.x * (1.f - y.x * y.x), d1 = g.y * (1.f - y.y * y.y);
+    const float d2 = g.z * (1.f - y.z * y.z), d3 = g.w * (1.f - y.w * y.w);
+    aw[0] = fmaf(d0, tm, aw[0]); aw[1] = fmaf(d1, tm, aw[1]); aw[2] = fmaf(d2, tm, aw[2]); aw[3] = fmaf(d3, tm, aw[3]);
+    ab[0] += d0; ab[1] += d1; ab[2] += d2; ab[3] += d3;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[(0 * ny + ty) * H2 + j + i] = aw[i];
+    red[(1 * ny + ty) * H2 + j + i] = ab[i];
+  }
+  __syncthreads();
+  for (int c = ty * Q4 + q; c < H2; c += ny * Q4) {
+    float sw = 0.f, sb = 0.f;
+    for (int y = 0; y < ny; ++y) { sw += red[(0 * ny + y) * H2 + c]; sb += red[(1 * ny + y) * H2 + c]; }
+    if (c < H) { atomicAdd(dw1 + c, sw); atomicAdd(db1 + c, sb); }
+    else { atomicAdd(dw2 + c - H, sw); atomicAdd(db2 + c - H, sb); }
+  }
+}
+
 }  // namespace clsr
