@@ -264,6 +264,29 @@ __global__ void pool_dv_kernel(const float* __restrict__ w, const float* __restr
   }
 }
 
+// 16-byte form (Dv multiple of 4): one thread per (s, t, column quad).
+__global__ void pool_dv_v4_kernel(const float* __restrict__ w, const float* __restrict__ datt,
+                                  const int* __restrict__ len, int S, int T, int G, int Dv, float* __restrict__ dV) {
+  const int Q4 = Dv >> 2;
+  const long long n = (long long)S * T * Q4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Q4);
+    const long long st = i / Q4;
+    const int t = (int)(st % T), s = (int)(st / T);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < len[s]) {
+      for (int g = 0; g < G; ++g) {
+        const size_t b = (size_t)s * G + g;
+        const float wt = __ldg(w + b * T + t);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(datt + b * Dv) + q);
+        acc.x = fmaf(wt, d.x, acc.x); acc.y = fmaf(wt, d.y, acc.y); acc.z = fmaf(wt, d.z, acc.z); acc.w = fmaf(wt, d.w, acc.w);
+      }
+    }
+    reinterpret_cast<float4*>(dV)[i] = acc;
+  }
+}
+
 // dh0 = al*dy0 + be*h0 + ga (BatchNorm backward of the first attention layer), reduced two ways:
 //   dinv[s,t,n] = sum_g dh0[(s*G+g), t, n]      (skipped when dinv == nullptr)
 //   dqb[b,n]    = sum_t dh0[b, t, n]

@@ -85,13 +85,27 @@ __global__ void compact_ids_kernel(const int32_t* __restrict__ src, int T, int s
 __global__ void mark_unique_kernel(const int32_t* __restrict__ ids, long long n, int T, int seq_stride,
                                    int32_t* __restrict__ slot, int32_t* __restrict__ uniq,
                                    int32_t* __restrict__ counter) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long s = i / T;
-    int id = __ldg(ids + s * seq_stride + (i - s * T));
-    if (slot[id] == -1) {
-      if (atomicCAS(&slot[id], -1, -2) == -1) {
-        int c = atomicAdd(counter, 1);
+  // uniform trip count so the warp stays converged for the ballot; the append counter is bumped once per
+  // warp (a per-id atomicAdd on one address serialises ~10^5 atomics per step)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nround = (n + stride - 1) / stride * stride;
+  const int lane = threadIdx.x & 31;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    bool claim = false;
+    int id = 0;
+    if (i < n) {
+      const long long s = i / T;
+      id = __ldg(ids + s * seq_stride + (i - s * T));
+      if (slot[id] == -1) claim = atomicCAS(&slot[id], -1, -2) == -1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, claim);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(counter, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (claim) {
+        const int c = base + __popc(m & ((1u << lane) - 1u));
         uniq[c] = id;
         slot[id] = c;
       }

@@ -1127,7 +1127,10 @@ int backward(clsr_engine* e, const StepCtx& c) {
         e->d_len, B, T, 1, G, dy1s, ms.bn1.stat_b, e->Pg + ms.wo, e->Pg + ms.bo, nullptr, 0, nullptr, nullptr,
         e->cfg.contrastive_recent_k);
     POST("pool_bwd_short");
-    pool_dv_kernel<<<grid1d(e, M * H, 256), 256, 0, st>>>(e->B("ws"), e->B("dafs"), e->d_len, S, T, G, H, dR);
+    if ((H & 3) == 0 && !(((uintptr_t)e->B("dafs") | (uintptr_t)dR) & 15))
+      pool_dv_v4_kernel<<<grid1d(e, M * H / 4, 256, 16), 256, 0, st>>>(e->B("ws"), e->B("dafs"), e->d_len, S, T, G, H, dR);
+    else
+      pool_dv_kernel<<<grid1d(e, M * H, 256), 256, 0, st>>>(e->B("ws"), e->B("dafs"), e->d_len, S, T, G, H, dR);
     POST("pool_dv_short");
   }
   if ((rc = bn_bwd(e, ms.bn1, (double)MB))) return rc;
