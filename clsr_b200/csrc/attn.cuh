@@ -101,7 +101,7 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
                 const float* __restrict__ dhr, int recent_k) {
   // vdiv > 1: every "sequence" index here is a single row (G == 1) whose values / length belong to
   // sequence s / vdiv; dV is then produced by pool_dv_kernel (dV == nullptr here).
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int wpb = blockDim.x >> 5;
   float* s_scale = sm;
   float* s_shift = s_scale + A1;
@@ -109,7 +109,7 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
   float* s_rstd = s_mean + A1;
   float* s_w = s_rstd + A1;
   float* s_acc = s_w + A1;            // [3][A1] + 1 : stat1, stat2, dwout, dbout
-  float* s_warp = s_acc + 3 * A1 + 1;  // per warp: dsc[T], wrow[T], dat[Dv]
+  float* s_warp = s_acc + ((3 * A1 + 1 + 3) & ~3);  // per warp: dsc[T], wrow[T], dat[Dv] (16-byte aligned when T is even)
   for (int i = threadIdx.x; i < A1; i += blockDim.x) {
     s_scale[i] = scale[i]; s_shift[i] = shift[i]; s_mean[i] = mean[i]; s_rstd[i] = rstd[i]; s_w[i] = wout[i];
   }
@@ -128,6 +128,9 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
   const bool quad = (A1 & 3) == 0 && nq <= 32 && ((reinterpret_cast<uintptr_t>(h1) | reinterpret_cast<uintptr_t>(dy1)) & 15) == 0;
   const int ntl = quad ? 32 / nq : 1;
   const int n4 = quad ? lane % nq : 0, tl = quad ? lane / nq : 0;
+  // values V / datt rows addressable with 16-byte vectors (dat sits at a 16-byte aligned shared offset)
+  const bool vvec = (Dv & 3) == 0 && (Dv >> 2) <= 32 && (T & 1) == 0 && (A1 & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(V) & 15) == 0;
   float q_sc[4], q_sh[4], q_mn[4], q_rs[4], q_wo[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -148,7 +151,15 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
         float dwt = 0.f, wt = 0.f;
         if (t < L) {
           const float* vp = V + ((size_t)sv * T + t) * Dv;
-          for (int d = 0; d < Dv; ++d) dwt = fmaf(dat[d], vp[d], dwt);
+          if (vvec) {
+            for (int d = 0; d < Dv; d += 4) {
+              const float4 x = __ldg(reinterpret_cast<const float4*>(vp + d));
+              const float4 a = *reinterpret_cast<const float4*>(dat + d);
+              dwt = fmaf(a.x, x.x, fmaf(a.y, x.y, fmaf(a.z, x.z, fmaf(a.w, x.w, dwt))));
+            }
+          } else {
+            for (int d = 0; d < Dv; ++d) dwt = fmaf(dat[d], vp[d], dwt);
+          }
           wt = w[row * T + t];
           dot = fmaf(wt, dwt, dot);
         }
@@ -207,6 +218,44 @@ pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, con
         }
       }
       }
+      if (dV && vvec && ((reinterpret_cast<uintptr_t>(dV) & 15) == 0)) {
+        // lane = (position lane, column quad): 16-byte read-modify-writes of dV, nqv * ntlv lanes active
+        const int nqv = Dv >> 2, ntlv = 32 / nqv;
+        if (lane < nqv * ntlv) {
+          const int d4 = (lane % nqv) * 4, tl2 = lane / nqv;
+          const float4 da = *reinterpret_cast<const float4*>(dat + d4);
+          float4 pm = make_float4(0.f, 0.f, 0.f, 0.f), pr = pm;
+          if (dhm) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(dhm + (size_t)s * Dv + d4));
+            const float inv = 1.f / (float)L;
+            pm = make_float4(t4.x * inv, t4.y * inv, t4.z * inv, t4.w * inv);
+          }
+          if (dhr) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(dhr + (size_t)s * Dv + d4));
+            const float inv = 1.f / (float)kk;
+            pr = make_float4(t4.x * inv, t4.y * inv, t4.z * inv, t4.w * inv);
+          }
+          float* op = dV + (size_t)s * T * Dv + d4;
+          for (int t = tl2; t < T; t += ntlv) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < L) {
+              const float wt = wrow[t];
+              v = make_float4(wt * da.x, wt * da.y, wt * da.z, wt * da.w);
+              if (g == 0) {
+                v.x += pm.x; v.y += pm.y; v.z += pm.z; v.w += pm.w;
+                if (t >= L - kk) { v.x += pr.x; v.y += pr.y; v.z += pr.z; v.w += pr.w; }
+              }
+            }
+            float4* o4 = reinterpret_cast<float4*>(op + (size_t)t * Dv);
+            if (g == 0 && !dV_accum) *o4 = v;
+            else if (t < L) {
+              float4 o = *o4;
+              o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+              *o4 = o;
+            }
+          }
+        }
+      } else
       for (int d = lane; dV && d < Dv; d += 32) {
         const float da = dat[d];
         const float pm = dhm ? dhm[(size_t)s * Dv + d] / (float)L : 0.f;

@@ -565,8 +565,9 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   const int st = stats ? 1 : 0;
   int tma = tma_streams(a, K);
   // first configuration that fits shared memory: prefer two stages + operand prefetch + TMA
-  const int cand[][3] = {{2, eop, tma}, {2, eop, tma == 2 ? 0 : tma}, {1, eop, tma}, {2, 0, tma},
-                         {1, eop, 0},   {2, 0, 0},                   {1, 0, 0}};
+  // (two operand stages matter more than the prefetched epilogue operand)
+  const int cand[][3] = {{2, eop, tma}, {2, eop, tma == 2 ? 0 : tma}, {2, 0, tma}, {1, eop, tma},
+                         {2, 0, 0},     {1, eop, 0},                  {1, 0, 0}};
   tc::Smem L;
   bool fits = false;
   for (const auto& c : cand) {
@@ -1119,7 +1120,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
   float *dy1s = e->B("dy1s"), *dy0s = e->B("dy0s"), *dR = e->B("dR");
   {
     int wpb = 4;
-    size_t sm = (size_t)(5 * A1 + 3 * A1 + 1 + wpb * (2 * T + H)) * 4;
+    size_t sm = (size_t)(5 * A1 + 3 * A1 + 4 + wpb * (2 * T + H)) * 4;
     // one warp per ROW (5x the parallelism of one warp per group); the group sum of the values
     // gradient is a separate small kernel
     pool_bwd_kernel<<<grid1d(e, cdiv(B, wpb), 1, 16), 128, sm, st>>>(
@@ -1257,7 +1258,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
   float *dy1l = e->B("dy1l"), *dy0l = e->B("dy0l");
   {
     int wpb = 4;
-    size_t sm = (size_t)(5 * A1 + 3 * A1 + 1 + wpb * (2 * T + D)) * 4;
+    size_t sm = (size_t)(5 * A1 + 3 * A1 + 4 + wpb * (2 * T + D)) * 4;
     pool_bwd_kernel<<<grid1d(e, cdiv(S, wpb), 1, 8), 128, sm, st>>>(
         e->B("dafl"), e->B("wl"), X, D, h1l, A1, ml.bn1.scale, ml.bn1.shift, ml.bn1.mean, ml.bn1.rstd, e->P + ml.wo,
         e->d_len, S, T, 1, 1, dy1l, ml.bn1.stat_b, e->Pg + ml.wo, e->Pg + ml.bo, dX, 1, e->B("dhm"), e->B("dhr"),
@@ -1515,7 +1516,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
     CKCU(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml));
     CKCU(cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
     CKCU(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
-    size_t smp = (size_t)(8 * e->A1 + 1 + 4 * (2 * T + D)) * 4;
+    size_t smp = (size_t)(8 * e->A1 + 4 + 4 * (2 * T + D)) * 4;
     CKCU(cudaFuncSetAttribute(pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smp > 49152 ? smp : 49152)));
     size_t smf = (size_t)(3 * e->A1 + 4 * T) * 4;
     CKCU(cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smf > 49152 ? smf : 49152)));
