@@ -75,6 +75,12 @@ struct clsr_engine {
   int smem_optin = 49152;
   int tc_smem_max = 49152;
   int tc_dw_smem_max = 49152;
+  // pending problems of a grouped weight-gradient launch (tc_dw_group_kernel)
+  bool dw_grouping = false;
+  tc::DwGroup dwg;
+  long long dwg_weight[tc::kDwGroupMax];
+  int dwg_tiles[tc::kDwGroupMax];
+  int dwg_smem = 0;
 
   int T, Di, Dc, D, U, H, Q, A0, A1, L0, L1, CA, NX;
   int oG1, oC1, oG2, oC2, oL, oO, oTN, oTL;
@@ -694,6 +700,20 @@ int tc_dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& 
     while ((int)cols < npad) cols <<= 1;
     int tiles = cdiv(M, tc::kTileM);
     int grid = tiles < e->num_sms ? tiles : e->num_sms;
+    if (e->dw_grouping && e->dwg.n < tc::kDwGroupMax) {
+      // deferred: becomes one problem of the next grouped launch (dw_group_flush)
+      tc::DwProblem& P = e->dwg.p[e->dwg.n];
+      P.M = M; P.K = K; P.N = nn; P.npad = npad; P.nstages = nstages; P.tma_a = ta; P.tma_b = tb; P.lddw = lddw;
+      P.octa = tc::dw_split(tc::kDwProducers / 8, ((colsum ? K + 1 : K) + 7) / 8, (nn + 7) / 8, tc::piece_cost(a.mode),
+                            tc::piece_cost(b2.mode));
+      P.tmem_cols = cols; P.a = a; P.b = b2; P.dW = dW + n0; P.colsum = colsum ? colsum + n0 : nullptr;
+      P.tmA = tmA; P.tmA2 = tmA2; P.tmB = tmB; P.tmB2 = tmB2;
+      e->dwg_weight[e->dwg.n] = (long long)tiles * (((colsum ? K + 1 : K) + 7) / 8 + (nn + 7) / 8);
+      e->dwg_tiles[e->dwg.n] = tiles;
+      if (L.total > e->dwg_smem) e->dwg_smem = L.total;
+      e->dwg.n++;
+      continue;
+    }
     const int octa = tc::dw_split(tc::kDwProducers / 8, ((colsum ? K + 1 : K) + 7) / 8, (nn + 7) / 8, tc::piece_cost(a.mode),
                                   tc::piece_cost(b2.mode));
     tc::tc_dw_kernel<<<grid, tc::kDwThreads, L.total, e->stream>>>(M, K, nn, npad, nstages, cols, ta, tb, octa, a, b2, dW + n0, lddw,
@@ -718,6 +738,47 @@ int dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& a, 
   else dw_kernel<false><<<grid, 256, 0, e->stream>>>(M, K, N, a, b, dW, lddw, nullptr, rows_per);
   POST(name);
   return 0;
+}
+
+// Launch the deferred weight-gradient problems as one grid partitioned in proportion to their work.
+int dw_group_flush(clsr_engine* e, const char* name) {
+  e->dw_grouping = false;
+  tc::DwGroup& g = e->dwg;
+  if (g.n == 0) return 0;
+  long long wsum = 0;
+  for (int i = 0; i < g.n; ++i) wsum += e->dwg_weight[i];
+  int left = e->num_sms;
+  for (int i = 0; i < g.n; ++i) {
+    int c = (int)((long long)e->num_sms * e->dwg_weight[i] / wsum);
+    if (c < 1) c = 1;
+    if (c > e->dwg_tiles[i]) c = e->dwg_tiles[i];
+    g.p[i].ncta = c;
+    left -= c;
+  }
+  for (int guard = 0; left != 0 && guard < 4 * e->num_sms; ++guard) {   // hand the rounding remainder to the busiest problems
+    int best = -1;
+    double bl = -1.0;
+    for (int i = 0; i < g.n; ++i) {
+      const double load = (double)e->dwg_weight[i] / g.p[i].ncta;
+      if (left > 0 ? (g.p[i].ncta < e->dwg_tiles[i] && load > bl) : (g.p[i].ncta > 1 && (bl < 0 || load < bl))) { bl = load; best = i; }
+    }
+    if (best < 0) break;
+    g.p[best].ncta += left > 0 ? 1 : -1;
+    left += left > 0 ? -1 : 1;
+  }
+  int c0 = 0;
+  for (int i = 0; i < g.n; ++i) { g.p[i].cta0 = c0; c0 += g.p[i].ncta; }
+  tc::tc_dw_group_kernel<<<c0, tc::kDwThreads, e->dwg_smem, e->stream>>>(g);
+  POST(name);
+  g.n = 0;
+  e->dwg_smem = 0;
+  return 0;
+}
+void dw_group_begin(clsr_engine* e) {
+  static const bool off = getenv("CLSR_DW_NO_GROUP") != nullptr;   // developer switch: one launch per weight gradient
+  e->dw_grouping = !off && e->cfg.math_mode == 1;
+  e->dwg.n = 0;
+  e->dwg_smem = 0;
 }
 
 AOp a_plain(const float* A, int lda) {
@@ -1170,6 +1231,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
   }
   if ((rc = gemm(e, "dFs", (int)M, Q + U, A0, a_plain(e->B("dinvs"), A0), W("Ws0iT"), Q + U, e_store(e->B("dFs"), Q + U), false)))
     return rc;
+  dw_group_begin(e);   // dWs0i, dWs0q, dWatts: launched together once the last one's operands exist
   if ((rc = dwgemm(e, "dWs0i", (int)M, Q + U, A0, a_catmul(as, Q, Q, 0, sti, U, T), a_plain(e->B("dinvs"), A0), dW("Ws0i"),
                    A0, nullptr)))
     return rc;
@@ -1189,6 +1251,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
     return rc;
   if ((rc = dwgemm(e, "dWatts", (int)M, H, Q, a_plain(R, H), a_plain(e->B("das"), Q), e->Pg + e->p_watts, Q, nullptr)))
     return rc;
+  if ((rc = dw_group_flush(e, "dW_short_group"))) return rc;
 
   // ---- BPTT through the three recurrences ----
   float *PX = e->B("PX"), *dPX = e->B("dPX");
@@ -1226,6 +1289,8 @@ int backward(clsr_engine* e, const StepCtx& c) {
   }
   float *dX = e->B("dX"), *TNL = e->B("TNL"), *dTNL = e->B("dTNL");
   if ((rc = gemm(e, "dX", (int)M, D, NX, a_plain(dPX, NX), W("Wx_allT"), D, e_store(dX, D), false))) return rc;
+  // the seven weight gradients fed by dPX are independent of everything up to the optimizer: one grouped launch
+  dw_group_begin(e);
   if ((rc = dwgemm(e, "dWx", (int)M, D, NX, a_plain(X, D), a_plain(dPX, NX), dW("Wx_all"), NX, dW("bx_all")))) return rc;
   if ((rc = gemm(e, "dTNL", (int)M, 2 * H, 3 * H, a_plain(dPX + e->oO, NX), W("WtT"), 2 * H, e_store(dTNL, 2 * H), false)))
     return rc;
@@ -1251,6 +1316,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
   if ((rc = dwgemm(e, "dWgh2", (int)M, H, 2 * H, a_plain(e->B("hp2"), H), a_plain(dPX + e->oG2, NX), dW("Wgh2"), 2 * H, nullptr))) return rc;
   if ((rc = dwgemm(e, "dWch2", (int)M, H, H, a_plain(e->B("rh2"), H), a_plain(dPX + e->oC2, NX), dW("Wch2"), H, nullptr))) return rc;
   if ((rc = dwgemm(e, "dKm", (int)M, H, 4 * H, a_plain(e->B("mp"), H), a_plain(dPX + e->oL, NX), dW("Km"), 4 * H, nullptr))) return rc;
+  if ((rc = dw_group_flush(e, "dW_bptt_group"))) return rc;
 
   // ---- long-term attention ----
   Mlp& ml = e->mlp_long;
@@ -1272,6 +1338,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
     ep.rstd = ml.bn0.rstd; ep.stat = ml.bn0.stat_b;
     if ((rc = gemm(e, "dy0l", (int)M, A0, A1, a_affine2(dy1l, h1l, A1, ml.bn1), W("W1lT"), A0, ep, true))) return rc;
   }
+  dw_group_begin(e);   // dW1l, dWl0, dWl0q, dWattl
   if ((rc = dwgemm(e, "dW1l", (int)M, A0, A1, a_bnrelu(h0l, A0, ml.bn0), a_affine2(dy1l, h1l, A1, ml.bn1),
                    e->Pg + ml.w1, A1, nullptr)))
     return rc;
@@ -1294,6 +1361,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
     return rc;
   if ((rc = dwgemm(e, "dWattl", (int)M, D, U, a_plain(X, D), a_plain(e->B("dal"), U), e->Pg + e->p_wattl, U, nullptr)))
     return rc;
+  if ((rc = dw_group_flush(e, "dW_long_group"))) return rc;
   (void)Di; (void)Dc; (void)CA;
   return 0;
 }
@@ -1527,6 +1595,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
     CKCU(cudaFuncGetAttributes(&fa, tc::tc_dw_kernel));
     e->tc_dw_smem_max = e->smem_optin - (int)fa.sharedSizeBytes - 256;
     CKCU(cudaFuncSetAttribute(tc::tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tc_dw_smem_max));
+    CKCU(cudaFuncSetAttribute(tc::tc_dw_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tc_dw_smem_max));
   }
   build_inventory(e);
   CKC(dalloc(e, &e->P, e->Ptot));

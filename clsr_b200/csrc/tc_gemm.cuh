@@ -1059,14 +1059,12 @@ constexpr int kDwLoadWarp = 12;                // TMA operand loads / L2 prefetc
 constexpr int kDwMmaWarp = 13;
 constexpr int kDwThreads = 448;
 
-__global__ void __launch_bounds__(kDwThreads, 1)
-tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, int tma_a, int tma_b, int octa, AOp a, AOp b,
-             float* __restrict__ dW, int lddw, float* __restrict__ colsum, const __grid_constant__ CUtensorMap tmA,
-             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmB2) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(16) float sva[3 * 128];
-  __shared__ __align__(16) float svb[3 * 256];
+// Body of the weight-gradient kernel for one problem; `cta` of `nctas` CTAs share the problem's row slabs.
+// (The tensor maps are passed by address: they must stay in the kernel's parameter space.)
+CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, int N, int npad, int nstages,
+                         uint32_t tmem_cols, int tma_a, int tma_b, int octa, const AOp& a, const AOp& b,
+                         float* __restrict__ dW, int lddw, float* __restrict__ colsum, const CUtensorMap* tmA,
+                         const CUtensorMap* tmA2, const CUtensorMap* tmB, const CUtensorMap* tmB2, int cta, int nctas) {
   const DwSmem L = dw_smem_layout(K, N, npad, nstages, tma_a, tma_b);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full = bars;         // [2]
@@ -1099,7 +1097,7 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, int
   if (warp < kDwLoadWarp) {
     // octa (chosen on the host, dw_split): producer octets that work on A; the rest work on B
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < ntiles; tile += nctas, ++it) {
       const int s = it % nstages;
       const uint32_t ph = (it / nstages) & 1;
       // a group whose operand comes by TMA waits for the raw planes (which implies empty[s]: the loader
@@ -1109,7 +1107,7 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, int
         mbar_wait(&empty[s], ph ^ 1);
         // register-load path: the first warp of the group prefetches the rows of a later slab into L2
         if (CLSR_TC_PREFETCH) {
-          const int mp = (tile + CLSR_TC_PREFETCH * (int)gridDim.x) * kTileM;
+          const int mp = (tile + CLSR_TC_PREFETCH * nctas) * kTileM;
           if (warp == 0 && !tma_a) prefetch_operand(a, mp, M, K, lane);
           if (warp == (octa * 8 + 31) / 32 && tid >= octa * 8 && !tma_b) prefetch_operand(b, mp, M, N, lane);
         }
@@ -1129,7 +1127,7 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, int
   } else if (warp == kDwLoadWarp) {
     // idle unless an operand comes by TMA (see the loader role of tc_gemm_kernel)
     int it = 0;
-    for (int tile = blockIdx.x; any_tma && tile < ntiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; any_tma && tile < ntiles; tile += nctas, ++it) {
       const int s = it % nstages;
       const uint32_t ph = (it / nstages) & 1;
       mbar_wait(&empty[s], ph ^ 1);
@@ -1140,15 +1138,15 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, int
       if (lane == 0)
         mbar_expect_tx(&rawfull[s], (uint32_t)(((K >> 3) * tma_a + (N >> 3) * tma_b) * kPlaneBytes));
       __syncwarp();
-      if (tma_a) tma_issue_tile(tma_a, &tmA, &tmA2, K >> 3, tile * kTileM, a_base, a_raw2, &rawfull[s], lane);
-      if (tma_b) tma_issue_tile(tma_b, &tmB, &tmB2, N >> 3, tile * kTileM, b_base, b_raw2, &rawfull[s], lane);
+      if (tma_a) tma_issue_tile(tma_a, tmA, tmA2, K >> 3, tile * kTileM, a_base, a_raw2, &rawfull[s], lane);
+      if (tma_b) tma_issue_tile(tma_b, tmB, tmB2, N >> 3, tile * kTileM, b_base, b_raw2, &rawfull[s], lane);
     }
   } else {
     // MMA issue: D[128 x npad] += A^T-slab . B-slab, both operands MN-major
     const uint32_t idesc = make_idesc(npad) | (1u << 15) | (1u << 16);
     const uint32_t lbo = 256, sbo = kPlaneBytes;  // MN-major: LBO = 8-row group along the reduction, SBO = plane
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < ntiles; tile += nctas, ++it) {
       const int s = it % nstages;
       const uint32_t ph = (it / nstages) & 1;
       mbar_wait(&full[s], ph);
@@ -1171,7 +1169,7 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, int
     if (lane == 0) umma_commit(done);
     __syncwarp();
   }
-  if (warp < 4 && ntiles > (int)blockIdx.x) {
+  if (warp < 4 && ntiles > (int)cta) {
     // final epilogue: accumulator lane = dW row
     mbar_wait(done, 0);
     tc_fence_after();
@@ -1196,6 +1194,47 @@ tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, int
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+}
+
+__global__ void __launch_bounds__(kDwThreads, 1)
+tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, int tma_a, int tma_b, int octa, AOp a, AOp b,
+             float* __restrict__ dW, int lddw, float* __restrict__ colsum, const __grid_constant__ CUtensorMap tmA,
+             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmB2) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(16) float sva[3 * 128];
+  __shared__ __align__(16) float svb[3 * 256];
+  dw_body(smem, sva, svb, M, K, N, npad, nstages, tmem_cols, tma_a, tma_b, octa, a, b, dW, lddw, colsum, &tmA, &tmA2, &tmB,
+          &tmB2, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Several independent weight-gradient problems in ONE launch: the launches over M = S*T rows process only ~11
+// slabs per CTA each, so pipeline fill, TMEM allocation and the final atomics dominate them; here the grid is
+// partitioned between the problems in proportion to their work and every CTA runs dw_body on its share.
+constexpr int kDwGroupMax = 8;
+struct DwProblem {
+  int M, K, N, npad, nstages, tma_a, tma_b, octa, lddw, cta0, ncta;
+  uint32_t tmem_cols;
+  AOp a, b;
+  float* dW;
+  float* colsum;
+  CUtensorMap tmA, tmA2, tmB, tmB2;
+};
+struct DwGroup {
+  int n;
+  DwProblem p[kDwGroupMax];
+};
+
+__global__ void __launch_bounds__(kDwThreads, 1)
+tc_dw_group_kernel(const __grid_constant__ DwGroup g) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(16) float sva[3 * 128];
+  __shared__ __align__(16) float svb[3 * 256];
+  int i = 0;
+  while (i + 1 < g.n && (int)blockIdx.x >= g.p[i].cta0 + g.p[i].ncta) ++i;
+  const DwProblem& P = g.p[i];
+  dw_body(smem, sva, svb, P.M, P.K, P.N, P.npad, P.nstages, P.tmem_cols, P.tma_a, P.tma_b, P.octa, P.a, P.b, P.dW, P.lddw,
+          P.colsum, &P.tmA, &P.tmA2, &P.tmB, &P.tmB2, (int)blockIdx.x - P.cta0, P.ncta);
 }
 
 }  // namespace tc
