@@ -13,7 +13,7 @@ timeout 900 ncu --set full --clock-control none --import-source on \
   --launch-skip 19 --launch-count 19 -o $O/${R}_full_misc -f $B > $O/ncu2.log 2>&1
 # (3) the tcgen05 kernels of one step: speed-of-light, memory, occupancy, warp states
 timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy \
-  --section WarpStateStats --section SchedulerStats --clock-control none -k regex:"tc_gemm_kernel|tc_dw_kernel" \
-  --launch-skip 54 --launch-count 54 -o $O/${R}_tc -f $B > $O/ncu3.log 2>&1
-tail -2 $O/ncu1.log $O/ncu2.log $O/ncu3.log | cut -c1-200
+  --section WarpStateStats --section SchedulerStats --clock-control none -k regex:"tc_gemm_kernel|tc_dw_kernel|tc_dw_group_kernel" \
+  --launch-skip 42 --launch-count 42 -o $O/${R}_tc -f $B > $O/ncu3.log 2>&1   # 34 GEMM + 5 single + 3 grouped weight-gradient launches per step
+for f in $O/ncu1.log $O/ncu2.log $O/ncu3.log; do tail -n 2 $f | cut -c1-200; done
 ls -la $O/*.ncu-rep
