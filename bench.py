@@ -151,6 +151,29 @@ def algorithmic_bytes(name, S, B, T, w):
     return tab.get(name)
 
 
+def step_roofline(T, seq_per_s_per_gpu, hbm_gbs, tensor_tflops=1388.2):
+    """Whole-step bounds of SURVEY.md 8d / BASELINE.md section 3 for the D=40 model: minimum HBM bytes and
+    (group-deduplicated) FLOPs per user-sequence, and the fraction of each bound the measured rate reaches."""
+    D = U = H = 40
+    A0, A1, L0, L1, Gr = 80, 40, 100, 64, G
+    Q = U + D
+    g_min = T * 8 + T * D * 4 + Gr * (8 + D * 4) + (4 + 2 * U * 4) + 3 * T * 4 + 2 * T * D * 4
+    long_ = 2 * T * (D * U + 4 * U * A0 + A0 * A1 + A1)
+    lstm = 2 * T * (2 * D * H + 4 * H * H + 4 * H * (D + H))
+    gru = 2 * T * 3 * H * (D + H)
+    short = 2 * T * (H * Q + 4 * Q * A0 + A0 * A1 + A1)
+    alpha = 2 * ((2 * H + 2 * D + 1) * A0 + A0 * A1 + A1)
+    logit = 2 * ((H + D) * L0 + L0 * L1 + L1)
+    flops = 3 * (long_ + lstm + 2 * gru + Gr * (short + alpha + logit))
+    hbm_bound = hbm_gbs * 1e9 / g_min
+    cmp_bound = tensor_tflops * 1e12 / flops
+    return {"hbm_min_bytes_per_seq": g_min, "hbm_bound_seq_per_s_per_gpu": hbm_bound,
+            "frac_of_hbm_bound": seq_per_s_per_gpu / hbm_bound, "flops_per_seq": flops,
+            "tensor_peak_tflops": tensor_tflops, "compute_bound_seq_per_s_per_gpu": cmp_bound,
+            "frac_of_compute_bound": seq_per_s_per_gpu / cmp_bound,
+            "note": "the step is latency / instruction bound at D=40 (SURVEY 8d); per-kernel rooflines are in `roofline` and `kernels`"}
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -318,6 +341,10 @@ def run_b200(a):
                               key=lambda x: -x[1])[:12],
         "last_losses": last,
     }
+    try:
+        out["step_roofline"] = step_roofline(T, S * a.steps / (ms / 1e3), hbm_peak)
+    except Exception as ex:  # informational only
+        out["step_roofline"] = {"error": str(ex)}
     if a.profile_out:
         with open(a.profile_out, "w") as f:
             json.dump({"per_kernel": per_kernel, "ms_per_step": ms / a.steps}, f, indent=1)
