@@ -70,6 +70,50 @@ __global__ void gather_rows_kernel(const int32_t* __restrict__ idx, int idx_stri
   }
 }
 
+// Device-resident feeds: copy what the step reads (one row per sequence, every row's target ids and
+// labels) into the engine's compact staging block, validating every id against its table size.  An id
+// outside [0, n) is replaced by 0 (the padding row) and reported through err[0] (bit 0 users, 1 items,
+// 2 cates, 3 item_history, 4 cate_history) -- a foreign feed must not turn into out-of-bounds reads in the
+// gathers or out-of-bounds writes through the slot tables.
+struct StageFeed {
+  const int32_t *users, *items, *cates, *ih, *ch, *mask;
+  const float *tfa, *ttn, *labels;
+  int32_t *o_ih, *o_ch, *o_mask, *o_users, *o_items, *o_cates;
+  float *o_tfa, *o_ttn, *o_labels;
+  int S, G, T, B;
+  long long n_items, n_cates, n_users;
+  int32_t* err;
+};
+__global__ void stage_device_feed_kernel(StageFeed a) {
+  const long long M = (long long)a.S * a.T;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
+    const long long s = i / a.T;
+    const long long src = s * a.G * a.T + (i - s * a.T);
+    int it = __ldg(a.ih + src), ct = __ldg(a.ch + src);
+    if ((unsigned long long)(long long)it >= (unsigned long long)a.n_items) { bad |= 8; it = 0; }
+    if ((unsigned long long)(long long)ct >= (unsigned long long)a.n_cates) { bad |= 16; ct = 0; }
+    a.o_ih[i] = it; a.o_ch[i] = ct;
+    a.o_mask[i] = __ldg(a.mask + src);
+    a.o_tfa[i] = __ldg(a.tfa + src);
+    a.o_ttn[i] = __ldg(a.ttn + src);
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.B; i += stride) {
+    int it = __ldg(a.items + i), ct = __ldg(a.cates + i);
+    if ((unsigned long long)(long long)it >= (unsigned long long)a.n_items) { bad |= 2; it = 0; }
+    if ((unsigned long long)(long long)ct >= (unsigned long long)a.n_cates) { bad |= 4; ct = 0; }
+    a.o_items[i] = it; a.o_cates[i] = ct;
+    a.o_labels[i] = a.labels ? __ldg(a.labels + i) : 0.f;
+    if (i < a.S) {
+      int u = __ldg(a.users + i * a.G);
+      if ((unsigned long long)(long long)u >= (unsigned long long)a.n_users) { bad |= 1; u = 0; }
+      a.o_users[i] = u;
+    }
+  }
+  if (bad) atomicOr(a.err, bad);
+}
+
 // dst[i] = src[(i / T) * seq_stride + i % T]: contiguous copy of a strided id array (all-gather staging)
 __global__ void compact_ids_kernel(const int32_t* __restrict__ src, int T, int seq_stride, long long n,
                                    int32_t* __restrict__ dst) {

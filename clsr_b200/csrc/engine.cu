@@ -117,8 +117,9 @@ struct clsr_engine {
   int32_t* counts = nullptr;  // [0] contrastive rows, [1] uniq items, [2] uniq cates, [3] uniq users
   double* sumsq = nullptr;    // [4]
   double* acc = nullptr;      // [16]
-  float* d_losses = nullptr;  // [5]
+  float* d_losses = nullptr;  // [16]: 5 losses, 4 table-gradient norms
   float* h_losses = nullptr;  // pinned
+  unsigned long long* d_clip_steps = nullptr;  // [1] shared-history steps with an active table clip
 
   // staged inputs
   int32_t *in_users, *in_items, *in_cates, *in_ih, *in_ch, *in_mask, *d_len;
@@ -127,6 +128,8 @@ struct clsr_engine {
   size_t h_stage_bytes = 0;
   cudaEvent_t h2d_done = nullptr;  // the staging buffer may be rewritten once this has fired
   float* h_out = nullptr;  // pinned [2*Bmax]
+  int32_t* d_err = nullptr;   // [1] id-range flags of the last device-resident feed (stage_device_feed_kernel)
+  int32_t* h_err = nullptr;   // pinned mirror, copied after every step
 
   // data-parallel state (NCCL is dlopen'ed by clsr_comm_init)
   int world = 1, rank = 0;
@@ -894,58 +897,98 @@ struct StepCtx {
 int stage_inputs(clsr_engine* e, const clsr_batch* b, StepCtx* c, bool need_labels) {
   const int T = e->T;
   c->B = b->rows; c->G = b->group; c->S = b->rows / b->group; c->T = T;
+  // device layout of the staged block: [ih | ch | mask | tfa | ttn | users | items | cates | labels]
+  const int S = c->S, B = c->B, G = c->G;
+  const size_t seq_i = (size_t)S * T * 4;
+  {
+    char* d = (char*)e->in_ih;
+    c->ih = (const int32_t*)d; d += seq_i;
+    c->ch = (const int32_t*)d; d += seq_i;
+    c->mask = (const int32_t*)d; d += seq_i;
+    c->tfa = (const float*)d; d += seq_i;
+    c->ttn = (const float*)d; d += seq_i;
+    c->users = (const int32_t*)d; d += (size_t)S * 4;
+    c->items = (const int32_t*)d; d += (size_t)B * 4;
+    c->cates = (const int32_t*)d; d += (size_t)B * 4;
+    c->labels = (const float*)d;
+    c->seq_stride = T;
+    c->user_stride = 1;
+  }
   if (b->on_device) {
-    c->users = b->users; c->items = b->items; c->cates = b->cates; c->ih = b->item_history;
-    c->ch = b->cate_history; c->mask = b->mask; c->tfa = b->time_from_first_action; c->ttn = b->time_to_now;
-    c->labels = b->labels;
-    c->seq_stride = c->G * T;
-    c->user_stride = c->G;
+    // Device-resident feed: one kernel compacts it into the same staging block (one row per sequence) and
+    // validates every id against its table; the step itself only ever reads engine-owned, validated arrays.
+    StageFeed a;
+    a.users = b->users; a.items = b->items; a.cates = b->cates; a.ih = b->item_history; a.ch = b->cate_history;
+    a.mask = b->mask; a.tfa = b->time_from_first_action; a.ttn = b->time_to_now; a.labels = need_labels ? b->labels : nullptr;
+    a.o_ih = const_cast<int32_t*>(c->ih); a.o_ch = const_cast<int32_t*>(c->ch); a.o_mask = const_cast<int32_t*>(c->mask);
+    a.o_tfa = const_cast<float*>(c->tfa); a.o_ttn = const_cast<float*>(c->ttn); a.o_users = const_cast<int32_t*>(c->users);
+    a.o_items = const_cast<int32_t*>(c->items); a.o_cates = const_cast<int32_t*>(c->cates);
+    a.o_labels = const_cast<float*>(c->labels);
+    a.S = S; a.G = G; a.T = T; a.B = B;
+    a.n_items = e->cfg.n_items; a.n_cates = e->cfg.n_cates; a.n_users = e->cfg.n_users;
+    a.err = e->d_err;
+    CK(cudaMemsetAsync(e->d_err, 0, sizeof(int32_t), e->stream));
+    stage_device_feed_kernel<<<grid1d(e, (long long)S * T, 256, 4), 256, 0, e->stream>>>(a);
+    POST("stage_device_feed");
+    CK(cudaMemcpyAsync(e->h_err, e->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     return 0;
   }
-  // Host feed: pack only what the step reads (one row per sequence) into pinned staging, then a
-  // single async H2D copy.
-  const int S = c->S, B = c->B, G = c->G;
-  size_t seq_i = (size_t)S * T * 4;
+  // Host feed: pack only what the step reads (one row per sequence) into pinned staging, validate the ids
+  // against the table sizes, then a single async H2D copy.
   size_t need = 5 * seq_i + (size_t)S * 4 + (size_t)B * 4 * 3;
   if (need > e->h_stage_bytes) return fail(e, CLSR_ERR_ARG, "batch exceeds staging capacity");
   CK(cudaEventSynchronize(e->h2d_done));
   char* hp = e->h_stage;
   auto pack_rows = [&](const void* src, size_t row_bytes) {
-    const char* s = (const char*)src;
-    if (G == 1) memcpy(hp, s, row_bytes * S);
-    else for (int i = 0; i < S; ++i) memcpy(hp + row_bytes * i, s + row_bytes * (size_t)i * G, row_bytes);
+    const char* sp = (const char*)src;
+    if (G == 1) memcpy(hp, sp, row_bytes * S);
+    else for (int i = 0; i < S; ++i) memcpy(hp + row_bytes * i, sp + row_bytes * (size_t)i * G, row_bytes);
     char* r = hp;
     hp += row_bytes * S;
     return r;
   };
+  // any id outside [0, limit)?  (branch-free min/max scan: vectorises)
+  auto out_of_range = [](const int32_t* p, size_t n, long long limit) {
+    uint32_t mx = 0;
+    for (size_t i = 0; i < n; ++i) { const uint32_t v = (uint32_t)p[i]; mx = v > mx ? v : mx; }
+    return n > 0 && (long long)mx >= limit;   // negative ids wrap to >= 2^31
+  };
   size_t rowb = (size_t)T * 4;
   char* base = hp;
-  pack_rows(b->item_history, rowb);
-  pack_rows(b->cate_history, rowb);
+  const int32_t* p_ih = (const int32_t*)pack_rows(b->item_history, rowb);
+  const int32_t* p_ch = (const int32_t*)pack_rows(b->cate_history, rowb);
   pack_rows(b->mask, rowb);
   pack_rows(b->time_from_first_action, rowb);
   pack_rows(b->time_to_now, rowb);
-  pack_rows(b->users, 4);
+  const int32_t* p_us = (const int32_t*)pack_rows(b->users, 4);
+  const int32_t* p_it = (const int32_t*)hp;
   memcpy(hp, b->items, (size_t)B * 4); hp += (size_t)B * 4;
+  const int32_t* p_ct = (const int32_t*)hp;
   memcpy(hp, b->cates, (size_t)B * 4); hp += (size_t)B * 4;
   if (need_labels && b->labels) memcpy(hp, b->labels, (size_t)B * 4);
   hp += (size_t)B * 4;
-  // device layout mirrors the staging layout inside one contiguous block starting at in_ih
+  if (out_of_range(p_ih, (size_t)S * T, e->cfg.n_items)) return fail(e, CLSR_ERR_ARG, "item_history holds an id outside [0, %lld)", (long long)e->cfg.n_items);
+  if (out_of_range(p_ch, (size_t)S * T, e->cfg.n_cates)) return fail(e, CLSR_ERR_ARG, "item_cate_history holds an id outside [0, %lld)", (long long)e->cfg.n_cates);
+  if (out_of_range(p_us, (size_t)S, e->cfg.n_users)) return fail(e, CLSR_ERR_ARG, "users holds an id outside [0, %lld)", (long long)e->cfg.n_users);
+  if (out_of_range(p_it, (size_t)B, e->cfg.n_items)) return fail(e, CLSR_ERR_ARG, "items holds an id outside [0, %lld)", (long long)e->cfg.n_items);
+  if (out_of_range(p_ct, (size_t)B, e->cfg.n_cates)) return fail(e, CLSR_ERR_ARG, "cates holds an id outside [0, %lld)", (long long)e->cfg.n_cates);
   CK(cudaMemcpyAsync(e->in_ih, base, (size_t)(hp - base), cudaMemcpyHostToDevice, e->stream));
   CK(cudaEventRecord(e->h2d_done, e->stream));
-  char* d = (char*)e->in_ih;
-  c->ih = (const int32_t*)d; d += seq_i;
-  c->ch = (const int32_t*)d; d += seq_i;
-  c->mask = (const int32_t*)d; d += seq_i;
-  c->tfa = (const float*)d; d += seq_i;
-  c->ttn = (const float*)d; d += seq_i;
-  c->users = (const int32_t*)d; d += (size_t)S * 4;
-  c->items = (const int32_t*)d; d += (size_t)B * 4;
-  c->cates = (const int32_t*)d; d += (size_t)B * 4;
-  c->labels = (const float*)d;
-  c->seq_stride = T;
-  c->user_stride = 1;
   return 0;
+}
+
+// Raise the id-range error of a device-resident feed (flags written by stage_device_feed_kernel) once the
+// stream has been synchronised.
+int check_feed_flags(clsr_engine* e) {
+  const int f = e->h_err ? *e->h_err : 0;
+  if (!f) return 0;
+  *e->h_err = 0;
+  static const char* names[5] = {"users", "items", "cates", "item_history", "item_cate_history"};
+  std::string which;
+  for (int i = 0; i < 5; ++i)
+    if (f & (1 << i)) which += std::string(which.empty() ? "" : ", ") + names[i];
+  return fail(e, CLSR_ERR_ARG, "device-resident feed holds ids outside their tables (%s); they were read as id 0",
+              which.c_str());
 }
 
 int check_batch(clsr_engine* e, const clsr_batch* b, bool train) {
@@ -1630,9 +1673,13 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
   CKC(dalloc(e, &e->counts, 8));
   CKC(dalloc(e, &e->sumsq, 4));
   CKC(dalloc(e, &e->acc, 16));
-  CKC(dalloc(e, &e->d_losses, 8));
-  CKCU(cudaMallocHost((void**)&e->h_losses, 8 * sizeof(float)));
+  CKC(dalloc(e, &e->d_losses, 16));
+  CKC(dalloc(e, &e->d_clip_steps, 1));
+  CKCU(cudaMallocHost((void**)&e->h_losses, 16 * sizeof(float)));
   CKCU(cudaMallocHost((void**)&e->h_out, (size_t)2 * Bm * sizeof(float)));
+  CKC(dalloc(e, &e->d_err, 1));
+  CKCU(cudaMallocHost((void**)&e->h_err, sizeof(int32_t)));
+  *e->h_err = 0;
 
   // staged inputs: one contiguous block [ih | ch | mask | tfa | ttn | users | items | cates | labels]
   {
@@ -1682,6 +1729,7 @@ void clsr_destroy(clsr_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_losses) cudaFreeHost(e->h_losses);
   if (e->h_out) cudaFreeHost(e->h_out);
+  if (e->h_err) cudaFreeHost(e->h_err);
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->h2d_done) cudaEventDestroy(e->h2d_done);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -1750,10 +1798,24 @@ int64_t clsr_get_adam_step(const clsr_engine* e) { return e ? e->adam_step : -1;
 int clsr_set_debug_sync(clsr_engine* e, int32_t on) { if (!e) return CLSR_ERR_ARG; e->debug_sync = on != 0; return CLSR_OK; }
 int64_t clsr_kernel_launches(const clsr_engine* e) { return e ? e->launches : 0; }
 
+// Clip diagnostics of the last synchronised training step: the four table-gradient norms the clip used, and
+// the number of shared-history (group > 1) steps so far in which one of them exceeded max_grad_norm.
+int clsr_clip_report(clsr_engine* e, float* norms4, int64_t* grouped_active_steps) {
+  if (!e) return CLSR_ERR_ARG;
+  CK(cudaStreamSynchronize(e->stream));
+  if (norms4) for (int t = 0; t < 4; ++t) norms4[t] = e->h_losses[5 + t];
+  if (grouped_active_steps) {
+    unsigned long long n = 0;
+    CK(cudaMemcpy(&n, e->d_clip_steps, sizeof n, cudaMemcpyDeviceToHost));
+    *grouped_active_steps = (int64_t)n;
+  }
+  return CLSR_OK;
+}
+
 int clsr_synchronize(clsr_engine* e) {
   if (!e) return CLSR_ERR_ARG;
   CK(cudaStreamSynchronize(e->stream));
-  return CLSR_OK;
+  return check_feed_flags(e);
 }
 
 int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, clsr_losses* out) {
@@ -1780,17 +1842,21 @@ int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, cls
   dense_l2_norm_kernel<<<(int)e->dense.size(), 1024, 0, e->stream>>>(e->d_vars, e->P, e->Pg, e->cfg.layer_l2, e->d_norms, e->acc);
   POST("dense_l2_norm");
   loss_finalize_kernel<<<1, 32, 0, e->stream>>>(e->acc, e->counts, e->counts + 3, c.G, e->U, e->cfg.embed_l2,
-                                                e->cfg.contrastive_weight, e->cfg.discrepancy_weight, e->d_losses);
+                                                e->cfg.contrastive_weight, e->cfg.discrepancy_weight, e->sumsq,
+                                                e->cfg.clip_norm ? e->cfg.max_grad_norm : 0.f, c.G, e->d_clip_steps,
+                                                e->d_losses);
   POST("loss_finalize");
   if (!(flags & CLSR_STEP_NO_OPTIMIZER)) {
     if ((rc = optimizer_step(e))) return rc;
   }
   if ((rc = reset_slots(e))) return rc;
-  CK(cudaMemcpyAsync(e->h_losses, e->d_losses, 5 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->h_losses, e->d_losses, 9 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   if (out) {
     CK(cudaStreamSynchronize(e->stream));
+    if ((rc = check_feed_flags(e))) return rc;
     out->loss = e->h_losses[0]; out->data_loss = e->h_losses[1]; out->regular_loss = e->h_losses[2];
     out->contrastive_loss = e->h_losses[3]; out->discrepancy_loss = e->h_losses[4];
+    for (int t = 0; t < 4; ++t) out->table_grad_norm[t] = e->h_losses[5 + t];
   }
   return CLSR_OK;
 }
@@ -1812,6 +1878,7 @@ int clsr_predict(clsr_engine* e, const clsr_batch* batch, float* pred, float* al
   CK(cudaMemcpyAsync(e->h_out, e->B("pred"), (size_t)B * 4, cudaMemcpyDeviceToHost, e->stream));
   if (alpha) CK(cudaMemcpyAsync(e->h_out + e->Bmax, e->B("alpha"), (size_t)B * 4, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  if ((rc = check_feed_flags(e))) return rc;
   memcpy(pred, e->h_out, (size_t)B * 4);
   if (alpha) memcpy(alpha, e->h_out + e->Bmax, (size_t)B * 4);
   return CLSR_OK;

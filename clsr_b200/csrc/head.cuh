@@ -394,9 +394,13 @@ __global__ void dense_adam_kernel(const DenseVar* __restrict__ vars, float* __re
 // Scalar outputs of the step (clsr.py:22-34): [loss, data, regular, contrastive, discrepancy].
 // acc: [0] data, [1..4] contrastive sums, [5] item rows^2, [6] cate rows^2, [7] user_long rows^2,
 //      [8] user_short rows^2, [9] sum (long-short)^2, [10] dense regular term.
+// out[5..8] = L2 norms of the four table gradients as the clip sees them (tf.clip_by_norm on the
+// IndexedSlices values, base_model.py:289-297); clip_steps[0] += 1 when a shared-history step (G > 1) has one
+// of them above max_grad_norm -- the case in which the group-summed slice norm differs from TF's.
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, const int32_t* __restrict__ counts,
                                      const int32_t* __restrict__ n_users, int G, int U, float embed_l2,
-                                     float cw, float dw, float* __restrict__ out) {
+                                     float cw, float dw, const double* __restrict__ sumsq, float clip, int group,
+                                     unsigned long long* __restrict__ clip_steps, float* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double den = (double)G * (double)counts[0];
   double con = (double)cw * (acc[1] + acc[2] + acc[3] + acc[4]) / den;
@@ -405,6 +409,13 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, const int32
   double data = acc[0];
   out[0] = (float)(data + reg + con + disc);
   out[1] = (float)data; out[2] = (float)reg; out[3] = (float)con; out[4] = (float)disc;
+  bool active = false;
+  for (int t = 0; t < 4; ++t) {
+    const float nrm = (float)sqrt(sumsq[t]);
+    out[5 + t] = nrm;
+    active = active || (clip > 0.f && nrm > clip);
+  }
+  if (active && group > 1) clip_steps[0] += 1ull;
 }
 
 }  // namespace clsr

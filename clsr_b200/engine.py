@@ -46,7 +46,8 @@ class Batch(C.Structure):
 
 class Losses(C.Structure):
     _fields_ = [("loss", C.c_float), ("data_loss", C.c_float), ("regular_loss", C.c_float),
-                ("contrastive_loss", C.c_float), ("discrepancy_loss", C.c_float)]
+                ("contrastive_loss", C.c_float), ("discrepancy_loss", C.c_float),
+                ("table_grad_norm", C.c_float * 4)]
 
 
 EXPORTS = [
@@ -60,6 +61,7 @@ EXPORTS = [
     "clsr_shard_create", "clsr_shard_destroy", "clsr_shard_last_error", "clsr_shard_local_rows",
     "clsr_shard_local_values", "clsr_shard_local_grad", "clsr_shard_export", "clsr_shard_attach",
     "clsr_shard_zero_grad", "clsr_shard_gather_history", "clsr_shard_scatter_add_history",
+    "clsr_crc32c", "clsr_clip_report",
 ]
 
 _lib = None
@@ -121,6 +123,8 @@ def load_library(path=None):
         "clsr_shard_zero_grad": (C.c_int, [P, P]),
         "clsr_shard_gather_history": (C.c_int, [P, P, P, P, I64, P, P]),
         "clsr_shard_scatter_add_history": (C.c_int, [P, P, P, P, I64, P, P]),
+        "clsr_crc32c": (U32, [P, C.c_uint64, U32]),
+        "clsr_clip_report": (C.c_int, [P, P, C.POINTER(I64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -216,6 +220,7 @@ class Engine:
                 self.table_m[t] = torch.zeros(shp, dtype=torch.float32, device=self.device)
                 self.table_v[t] = torch.zeros(shp, dtype=torch.float32, device=self.device)
             self._bind(t)
+        self.last_table_grad_norms = (0.0, 0.0, 0.0, 0.0)
         self.user_table = None  # sequential/embedding/user_embedding: gathered but unused by CLSR
         # Share torch's current stream so engine kernels are ordered with the torch ops that fill or read
         # the tables and device-resident feeds (the engine's own stream is non-blocking).
@@ -332,6 +337,7 @@ class Engine:
         self._check(self.lib.clsr_train_step(self.h, C.byref(b), flags, C.byref(out) if wait else None))
         if not wait:
             return None
+        self.last_table_grad_norms = tuple(out.table_grad_norm)
         return {"loss": out.loss, "data_loss": out.data_loss, "regular_loss": out.regular_loss,
                 "contrastive_loss": out.contrastive_loss, "discrepancy_loss": out.discrepancy_loss}
 
@@ -364,6 +370,14 @@ class Engine:
 
     def synchronize(self):
         self._check(self.lib.clsr_synchronize(self.h))
+
+    def clip_report(self):
+        """(table-gradient norms of the last step {table id: norm}, number of shared-history steps so far whose
+        table clip was active -- those deviate from TF's clip on un-deduplicated slices; group=1 is exact)."""
+        norms = (C.c_float * 4)()
+        n = C.c_int64()
+        self._check(self.lib.clsr_clip_report(self.h, norms, C.byref(n)))
+        return {t: float(norms[t]) for t in range(4)}, int(n.value)
 
     @property
     def adam_step(self):

@@ -95,8 +95,9 @@ def _parse_proto(buf):
     return out
 
 
-def read_index(prefix):
-    """Return {tensor_name: (np_dtype, shape tuple, shard_id, offset, size)}."""
+def read_index(prefix, with_header=False):
+    """Return {tensor_name: (np_dtype, shape tuple, shard_id, offset, size, masked crc32c)}
+    (and the number of data shards from the BundleHeaderProto when ``with_header``)."""
     with open(prefix + ".index", "rb") as f:
         buf = f.read()
     if len(buf) < 48 or struct.unpack_from("<Q", buf, len(buf) - 8)[0] != _MAGIC:
@@ -108,12 +109,14 @@ def read_index(prefix):
     idx_off, pos = _varint(foot, pos)
     idx_size, pos = _varint(foot, pos)
     entries = {}
+    num_shards = 1
     for _, handle in _block_entries(buf, idx_off, idx_size):
         boff, p = _varint(handle, 0)
         bsize, p = _varint(handle, p)
         for key, val in _block_entries(buf, boff, bsize):
             if key == b"":
-                continue  # BundleHeaderProto
+                num_shards = _parse_proto(val).get(1, [1])[0] or 1   # BundleHeaderProto.num_shards
+                continue
             pr = _parse_proto(val)
             dtype = pr.get(1, [0])[0]
             dims = []
@@ -122,22 +125,28 @@ def read_index(prefix):
                 for d in shp.get(2, []):
                     dims.append(_parse_proto(d).get(1, [0])[0])
             entries[key.decode()] = (
-                _NP_OF_DT[dtype], tuple(dims), pr.get(3, [0])[0], pr.get(4, [0])[0], pr.get(5, [0])[0])
-    return entries
+                _NP_OF_DT[dtype], tuple(dims), pr.get(3, [0])[0], pr.get(4, [0])[0], pr.get(5, [0])[0],
+                pr.get(6, [0])[0])
+    return (entries, num_shards) if with_header else entries
 
 
-def read_bundle(prefix, names=None):
-    """Load a checkpoint -> {name: np.ndarray}.  ``prefix`` is e.g. ``.../epoch_3``."""
-    entries = read_index(prefix)
+def read_bundle(prefix, names=None, verify_crc=False):
+    """Load a checkpoint -> {name: np.ndarray}.  ``prefix`` is e.g. ``.../epoch_3``.  Multi-shard
+    bundles (``.data-0000i-of-0000N``) are followed through BundleHeaderProto.num_shards.
+    ``verify_crc`` checks every tensor against its stored masked crc32c the way
+    BundleReader::GetValue does (IOError on mismatch)."""
+    entries, num_shards = read_index(prefix, with_header=True)
     out = {}
     datas = {}
-    for name, (dt, shape, shard, off, size) in entries.items():
+    for name, (dt, shape, shard, off, size, crc) in entries.items():
         if names is not None and name not in names:
             continue
         if shard not in datas:
-            path = "%s.data-%05d-of-%05d" % (prefix, shard, 1)
+            path = "%s.data-%05d-of-%05d" % (prefix, shard, num_shards)
             datas[shard] = np.memmap(path, dtype=np.uint8, mode="r")
         raw = np.asarray(datas[shard][off:off + size])
+        if verify_crc and _mask(crc32c(raw)) != crc:
+            raise IOError("checksum does not match for tensor %s in %s" % (name, prefix))
         out[name] = raw.view(dt).reshape(shape).copy()
     return out
 
@@ -157,8 +166,38 @@ def _crc32c_table():
 _CRC_TAB = None
 
 
+_NATIVE_CRC = None
+
+
+def _native_crc():
+    """clsr_crc32c of libclsr_b200.so (slice-by-8, ~GB/s) when the library is built; host-only code,
+    needs no GPU.  The pure-Python loop below is the same function, ~1 MB/s."""
+    global _NATIVE_CRC
+    if _NATIVE_CRC is None:
+        _NATIVE_CRC = False
+        try:
+            import ctypes
+            from . import engine
+            if os.path.exists(engine.LIB_PATH):
+                fn = ctypes.CDLL(engine.LIB_PATH).clsr_crc32c
+                fn.restype, fn.argtypes = ctypes.c_uint32, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32]
+                _NATIVE_CRC = fn
+        except (OSError, AttributeError):
+            _NATIVE_CRC = False
+    return _NATIVE_CRC
+
+
 def crc32c(data, crc=0):
     """Castagnoli CRC (the one TF stores, masked, per tensor and per block)."""
+    fn = _native_crc()
+    if fn:
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        return int(fn(a.ctypes.data if a.size else None, a.size, crc))
+    return crc32c_py(data, crc)
+
+
+def crc32c_py(data, crc=0):
+    """Pure-Python CRC-32C (reference implementation of ``crc32c``; used when the library is not built)."""
     global _CRC_TAB
     if _CRC_TAB is None:
         _CRC_TAB = np.array(_crc32c_table(), dtype=np.uint32)
@@ -194,35 +233,46 @@ def _build_block(items, restart_interval=16):
     return bytes(out)
 
 
-def write_bundle(prefix, tensors, with_crc=False):
+def write_bundle(prefix, tensors, with_crc=True, num_shards=1):
     """Write {name: np.ndarray} as a tensor bundle at ``prefix``.
 
-    ``with_crc`` computes the per-tensor crc32c in pure Python (slow for large tables);
-    TF only verifies it when non-zero is expected, our own reader ignores it.
+    Every BundleEntryProto carries the masked crc32c of its tensor bytes: TF's
+    BundleReader::GetValue compares it unconditionally, so a bundle without it fails
+    ``tf.train.Saver.restore`` with a checksum DataLoss (``with_crc=False`` is for tests only).
+    ``num_shards`` > 1 spreads the tensors over ``.data-0000i-of-0000N`` files (sorted names,
+    round-robin), the layout a sharded tf.train.Saver produces.
     """
     os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
     names = sorted(tensors)
+    num_shards = max(1, int(num_shards))
     items = []
-    # BundleHeaderProto: num_shards=1, endianness little (0), version{producer=1}
-    header = b"\x08\x01" + b"\x1a\x02\x08\x01"
+    # BundleHeaderProto: num_shards, endianness little (0), version{producer=1}
+    header = b"\x08" + _put_varint(num_shards) + b"\x1a\x02\x08\x01"
     items.append((b"", header))
-    off = 0
-    with open(prefix + ".data-00000-of-00001", "wb") as f:
-        for n in names:
+    files = [open("%s.data-%05d-of-%05d" % (prefix, i, num_shards), "wb") for i in range(num_shards)]
+    offs = [0] * num_shards
+    try:
+        for j, n in enumerate(names):
+            sh = j % num_shards
             a = np.ascontiguousarray(tensors[n])
-            raw = a.tobytes()
-            f.write(raw)
+            raw = a.reshape(-1).view(np.uint8) if a.size else np.zeros(0, np.uint8)
+            files[sh].write(raw.tobytes() if a.size else b"")
             shape = b"".join(b"\x12" + _put_varint(len(d)) + d
                              for d in (b"\x08" + _put_varint(int(s)) for s in a.shape))
             ent = b"\x08" + _put_varint(_DT_OF_NP[a.dtype])
             ent += b"\x12" + _put_varint(len(shape)) + shape
-            if off:
-                ent += b"\x20" + _put_varint(off)
-            ent += b"\x28" + _put_varint(len(raw))
+            if sh:
+                ent += b"\x18" + _put_varint(sh)
+            if offs[sh]:
+                ent += b"\x20" + _put_varint(offs[sh])
+            ent += b"\x28" + _put_varint(int(raw.size))
             crc = _mask(crc32c(raw)) if with_crc else 0
             ent += b"\x35" + struct.pack("<I", crc)
             items.append((n.encode(), ent))
-            off += len(raw)
+            offs[sh] += int(raw.size)
+    finally:
+        for f in files:
+            f.close()
     out = bytearray()
 
     def emit(block):

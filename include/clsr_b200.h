@@ -82,6 +82,7 @@ typedef struct clsr_batch {
 /* Outputs of one training step = the fetch list of CLSRModel.train (clsr.py:396-406). */
 typedef struct clsr_losses {
   float loss, data_loss, regular_loss, contrastive_loss, discrepancy_loss;
+  float table_grad_norm[4];  /* L2 norm of each table's gradient as clipped (diagnostic; see clsr_clip_report) */
 } clsr_losses;
 
 #define CLSR_STEP_NO_OPTIMIZER 1u /* stop after gradients (+ scatter-add); do not touch variables */
@@ -119,6 +120,12 @@ int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, cls
  * is_train_stage=False.  pred / alpha: host buffers of `rows` floats (alpha may be NULL). */
 int clsr_predict(clsr_engine* e, const clsr_batch* batch, float* pred, float* alpha);
 int clsr_synchronize(clsr_engine* e);
+/* Clip diagnostics (base_model.py:289-297: per-variable tf.clip_by_norm; for a table the norm runs over the
+ * concatenated, not yet de-duplicated IndexedSlices).  norms4: the four table-gradient norms the last
+ * training step clipped with.  grouped_active_steps: number of steps so far that ran with group > 1 AND
+ * had a table norm above max_grad_norm -- in those the norm was taken over group-summed history / user
+ * slices and the update differs from TF's; group = 1 reproduces TF exactly. */
+int clsr_clip_report(clsr_engine* e, float* norms4, int64_t* grouped_active_steps);
 
 /* ---- standalone hot-path operators (benchmarks / parity tests) -------------------- */
 /* K1+K3: hist_input[r,t,:] = concat(item_table[ih[r,t]], cate_table[ch[r,t]]) (clsr.py:145-147).
@@ -185,6 +192,11 @@ int clsr_set_profiling(clsr_engine* e, int32_t on);
 int clsr_profile_collect(clsr_engine* e);
 int clsr_profile_entry(clsr_engine* e, int32_t i, char* name, int32_t name_cap, double* total_ms,
                        int64_t* calls);
+
+/* ---- host utility ------------------------------------------------------------------- */
+/* CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start).  Used by the tensor-bundle
+ * checkpoint writer: tf.train.Saver.restore (base_model.py:394-410) verifies the per-tensor crc32c. */
+uint32_t clsr_crc32c(const void* data, uint64_t bytes, uint32_t crc);
 
 #ifdef __cplusplus
 }

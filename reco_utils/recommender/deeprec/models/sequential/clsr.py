@@ -7,6 +7,9 @@ reference's constructor, ``train`` / ``eval`` / ``eval_with_user`` / ``eval_with
 ``infer`` signatures and return shapes (:383-408; base_model.py:366-392;
 sequential_base_model.py:294-324).
 """
+import os
+import warnings
+
 import numpy as np
 
 from clsr_b200 import params as P
@@ -42,6 +45,19 @@ class CLSRModel(SequentialBaseModel):
         self.item_embedding_dim = hp.item_embedding_dim
         self.cate_embedding_dim = hp.cate_embedding_dim
         G = self.train_num_ngs + 1
+        # Execution knobs that are not reference hparams (hparam if present, else environment):
+        #   math_mode  1 (default): large GEMMs on tcgen05 tensor cores (split-bf16, fp32 accumulate) and
+        #              the recurrences on mma.sync -- the path bench.py measures; 0: fp32 CUDA cores.
+        #   strict_clip  run every training step ungrouped so tf.clip_by_norm sees TF's un-deduplicated
+        #              IndexedSlices (base_model.py:289-297) even when the clip is active; default off:
+        #              shared-history execution, identical to TF whenever no table norm exceeds
+        #              max_grad_norm (the engine counts the steps where one does and warns).
+        def knob(name, env, default):
+            v = getattr(hp, name, None) if name in hp else None
+            return int(os.environ.get(env, default)) if v is None else int(v)
+        self.math_mode = knob("math_mode", "CLSR_MATH_MODE", 1)
+        self.strict_clip = bool(knob("strict_clip", "CLSR_STRICT_CLIP", 0))
+        self._clip_warned = False
         self.engine = Engine(
             self.item_vocab_length, self.cate_vocab_length, self.user_vocab_length,
             max_rows=hp.batch_size * G, seq_len=hp.max_seq_length, item_dim=hp.item_embedding_dim,
@@ -52,7 +68,8 @@ class CLSRModel(SequentialBaseModel):
             discrepancy_weight=hp.discrepancy_loss_weight,
             contrastive_len_threshold=hp.contrastive_length_threshold,
             contrastive_recent_k=hp.contrastive_recent_k, optimizer=hp.optimizer,
-            learning_rate=hp.learning_rate, clip_norm=bool(hp.is_clip_norm), max_grad_norm=float(hp.max_grad_norm))
+            learning_rate=hp.learning_rate, clip_norm=bool(hp.is_clip_norm), max_grad_norm=float(hp.max_grad_norm),
+            math_mode=self.math_mode)
         if hp.init_method != "tnormal":
             raise NotImplementedError("init_method=%s (only tnormal) on the B200 CLSR path" % hp.init_method)
         self.engine.set_params(P.init_params(
@@ -91,7 +108,16 @@ class CLSRModel(SequentialBaseModel):
         feed_dict[self.embedding_keeps] = self.embedding_keep_prob_train
         feed_dict[self.is_train_stage] = True
         feed, group = self._arrays(feed_dict, True)
+        if self.strict_clip and self.hparams.is_clip_norm:
+            group = 1
         out = self.engine.train_step(feed, group=group, normalized=True)
+        if group > 1 and self.hparams.is_clip_norm and not self._clip_warned:
+            norms = self.engine.last_table_grad_norms
+            if max(norms) > float(self.hparams.max_grad_norm):
+                self._clip_warned = True
+                warnings.warn("a table gradient norm (%.3g) exceeded max_grad_norm=%g in a shared-history step: the "
+                              "clip was taken over group-summed slices and differs from TF's; set CLSR_STRICT_CLIP=1 "
+                              "(or hparam strict_clip) for TF-exact clipping" % (max(norms), self.hparams.max_grad_norm))
         summary = dict(out) if self.hparams.write_tfevents else None
         return [None, [], out["loss"], out["data_loss"], out["regular_loss"], out["contrastive_loss"],
                 out["discrepancy_loss"], summary]

@@ -18,8 +18,12 @@ def small_problem(S=24, G=5, T=50, seed=3, n_items=3000, n_cates=40, n_users=200
         lab[::5] = 1.0
         feed["labels"] = lab
     prm = P.init_params(n_items, n_cates, n_users, seed=seed)
-    # Scale up the 0.01-std initial weights so every block contributes visibly to the outputs
-    # (a freshly initialised model is almost linear and would hide errors).
+    return feed, scale_params(prm, seed, init_scale)
+
+
+def scale_params(prm, seed, init_scale=8.0):
+    """Scale up the 0.01-std initial weights so every block contributes visibly to the outputs
+    (a freshly initialised model is almost linear and would hide errors)."""
     rng = np.random.default_rng(seed + 1)
     for k, v in prm.items():
         if k.endswith("moving_mean"):
@@ -31,8 +35,8 @@ def small_problem(S=24, G=5, T=50, seed=3, n_items=3000, n_cates=40, n_users=200
         elif k.endswith("beta") or "b_nn_" in k:
             prm[k] = (0.1 * rng.standard_normal(v.shape)).astype(np.float32)
         elif "embedding" in k or "w_nn_" in k or "attention_mat" in k:
-            prm[k] = (v * init_scale).astype(np.float32)
-    return feed, prm
+            v *= np.float32(init_scale)
+    return prm
 
 
 def set_lengths(feed, lengths, G):

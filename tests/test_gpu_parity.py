@@ -155,6 +155,44 @@ def test_clip_by_norm_on_slices(cuda_lib):
     assert not bad, bad
 
 
+def test_grouped_clip_deviation_is_detected_and_quantified(cuda_lib):
+    """The product default shares the history work of a training group (group=5); its table clip norm is then
+    taken over group-summed history / user slices, TF's over the un-deduplicated ones (base_model.py:289-297).
+    With an active clip: (1) the engine counts and reports the step, (2) the two norms obey
+    ||sum_g x_g|| <= sqrt(G) * sqrt(sum_g ||x_g||^2) and their measured ratio is recorded, (3) group=1
+    reproduces TF's norms exactly (test_clip_by_norm_on_slices checks the updates)."""
+    import torch
+    from oracle import clsr_oracle as O
+    from clsr_b200.engine import TABLE_VARS
+    G, S, clip = 5, 20, 0.01
+    feed, prm = PU.small_problem(S=S, G=G, seed=5)
+    cfg = PU.oracle_config(G, max_grad_norm=clip)
+    ref = {k: v.copy() for k, v in prm.items()}
+    _, aux = O.train_step(ref, {}, feed, cfg, 1, torch.float64)
+    tf_norm = {t: aux["norms"][name] for t, name in TABLE_VARS.items()}
+    assert max(tf_norm.values()) > clip                     # the clip is active for the oracle
+    eng1 = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, G=G, max_grad_norm=clip)
+    eng1.train_step(feed, group=1)
+    n1, active1 = eng1.clip_report()
+    assert active1 == 0                                      # ungrouped steps are never counted: they are exact
+    for t in tf_norm:
+        assert abs(n1[t] - tf_norm[t]) < 2e-4 * tf_norm[t], (t, n1[t], tf_norm[t])
+    eng5 = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, G=G, max_grad_norm=clip)
+    eng5.train_step(feed, group=G)
+    n5, active5 = eng5.clip_report()
+    assert active5 == 1, "a shared-history step with an active table clip must be counted"
+    ratio = {t: n5[t] / tf_norm[t] for t in tf_norm}
+    print("grouped / TF clip norms per table:", {k: round(v, 4) for k, v in ratio.items()})
+    for t, r in ratio.items():
+        assert r <= np.sqrt(G) * (1 + 1e-4), (t, r)
+    # the two user tables hold only group-shared slices: their grouped norm is a genuinely different number
+    assert any(abs(r - 1.0) > 1e-3 for r in ratio.values())
+    # inactive clip: never counted
+    eng = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, G=G, max_grad_norm=1e6)
+    eng.train_step(feed, group=G)
+    assert eng.clip_report()[1] == 0
+
+
 def test_predict_matches_oracle(cuda_lib):
     """Inference path (BN on moving statistics), eval-style feed with float users / mask."""
     import torch
