@@ -633,10 +633,15 @@ int tc_gemm(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a,
       int kk = K - k0 < 160 ? K - k0 : 160;
       AOp a2 = a;
       EpiOp p2 = ep;
-      if (k0) { a2.A = a.A + k0; p2.flags |= E_ACCUM; p2.bias = nullptr; }
+      // later K slabs accumulate onto C: bias / broadcast terms were added by the first slab
+      if (k0) { a2.A = a.A + k0; p2.flags = (p2.flags | E_ACCUM) & ~(E_ROWBIAS | E_GROUPADD); p2.bias = nullptr; }
       p2.C = ep.C + n0;
       if (ep.bias && !k0) p2.bias = ep.bias + n0;
-      if ((rc = tc_gemm_one(e, name, M, nn, kk, a2, W + (size_t)k0 * ldw + n0, ldw, p2, stats))) return rc;
+      // column statistics are those of the finished sum: only the last K slab accumulates them (counting every
+      // slab's partial result put the sums of BOTH partial and final values into the alpha gate's first
+      // BatchNorm whenever its K = 2H+2D+1 = 161 > 160 input took this path, i.e. for >= 1024 rows)
+      const bool last_k = k0 + 160 >= K;
+      if ((rc = tc_gemm_one(e, name, M, nn, kk, a2, W + (size_t)k0 * ldw + n0, ldw, p2, stats && last_k))) return rc;
     }
     if (N <= 256) break;
   }
@@ -1934,6 +1939,24 @@ int clsr_debug_buffer(clsr_engine* e, const char* name, const float** p, int64_t
     if (p) *p = it->second.first;
     if (n) *n = it->second.second;
     return CLSR_OK;
+  }
+  // "bn/<mlp><layer>/<field>": BatchNorm vectors of the last step, e.g. bn/short0/scale (field: scale, shift, mean, rstd)
+  if (!strncmp(name, "bn/", 3)) {
+    const char* mlps[4] = {"long", "short", "alpha", "logit"};
+    Mlp* ms[4] = {&e->mlp_long, &e->mlp_short, &e->mlp_alpha, &e->mlp_logit};
+    for (int i = 0; i < 4; ++i) {
+      const size_t ln = strlen(mlps[i]);
+      if (strncmp(name + 3, mlps[i], ln) || (name[3 + ln] != '0' && name[3 + ln] != '1') || name[4 + ln] != '/') continue;
+      BnLayer& b = name[3 + ln] == '0' ? ms[i]->bn0 : ms[i]->bn1;
+      const char* f = name + 5 + ln;
+      float* v = !strcmp(f, "scale") ? b.scale : !strcmp(f, "shift") ? b.shift : !strcmp(f, "mean") ? b.mean
+                 : !strcmp(f, "rstd") ? b.rstd : nullptr;
+      if (!v) break;
+      if (p) *p = v;
+      if (n) *n = b.N;
+      return CLSR_OK;
+    }
+    return fail(e, CLSR_ERR_ARG, "no buffer named %s", name);
   }
   auto wi = e->wd_off.find(name);
   if (wi != e->wd_off.end()) {

@@ -114,6 +114,41 @@ def _bn(x, p, prefix, train, cfg, stats):
     return x * inv + (beta - mean * inv)
 
 
+_RELU_MASKS = None  # set by relu_decisions(): {(tag, layer): 0/1 tensor shaped like that layer's activations}
+
+
+class relu_decisions:
+    """Context manager for the parity tests: inside it, the ReLU of MLP layer (tag, i) is applied as
+    ``bn(h) * mask`` with the given 0/1 mask instead of ``relu(bn(h))``.  A unit whose pre-activation lies
+    within rounding distance of zero can come out on either side of the kink in two correct
+    implementations; its forward value is ~0 either way, but its derivative is 0 or 1.  Feeding the
+    decisions of the implementation under test into the oracle separates that effect from real errors.
+    ``flips`` collects, per layer, how many decisions differ from the oracle's own."""
+
+    def __init__(self, masks):
+        self.masks = masks
+        self.flips = {}
+
+    def __enter__(self):
+        global _RELU_MASKS
+        _RELU_MASKS = self
+        return self
+
+    def __exit__(self, *a):
+        global _RELU_MASKS
+        _RELU_MASKS = None
+
+
+def _relu(y, tag, i):
+    ctx = _RELU_MASKS
+    if ctx is None or (tag, i) not in ctx.masks:
+        return torch.relu(y)
+    m = torch.as_tensor(ctx.masks[(tag, i)]).reshape(y.shape)
+    own = y.detach() > 0
+    ctx.flips[(tag, i)] = int((own != (m > 0)).sum())
+    return y * m.to(y.dtype)
+
+
 def _fcn_net(x, p, scope, sizes, train, cfg, stats, inter=None, tag=""):
     """BaseModel._fcn_net (base_model.py:627-708): (xW+b -> BN -> ReLU) per hidden layer,
     then a linear output unit."""
@@ -123,7 +158,7 @@ def _fcn_net(x, p, scope, sizes, train, cfg, stats, inter=None, tag=""):
         if inter is not None:
             inter[tag + "_h%d" % i] = h
         bn = scope + ("batch_normalization/" if i == 0 else "batch_normalization_%d/" % i)
-        h = torch.relu(_bn(h, p, bn, train, cfg, stats))
+        h = _relu(_bn(h, p, bn, train, cfg, stats), tag, i)
     return h @ p[scope + "w_nn_output"] + p[scope + "b_nn_output"]
 
 

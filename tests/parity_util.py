@@ -86,21 +86,49 @@ def oracle_config(G, **kw):
     return OracleConfig(train_num_ngs=G - 1, **kw)
 
 
-def compare_step(eng, feed, prm, G, group, shapes_only=False, metric=None):
+def engine_relu_masks(eng, B, S, T, group):
+    """ReLU decisions of the engine's last step for the eight hidden layers, shaped for the oracle
+    (row-replicated where the engine computed a layer once per sequence)."""
+    c = eng.cfg
+    A0, A1, L0, L1 = c.att0, c.att1, c.fc0, c.fc1
+    spec = [("long", 0, "h0l", (S, T, A0), True), ("long", 1, "h1l", (S, T, A1), True),
+            ("short", 0, "h0s", (B, T, A0), False), ("short", 1, "h1s", (B, T, A1), False),
+            ("alpha", 0, "ha0", (B, A0), False), ("alpha", 1, "ha1", (B, A1), False),
+            ("logit", 0, "hl0", (B, L0), False), ("logit", 1, "hl1", (B, L1), False)]
+    masks = {}
+    for tag, i, buf, shp, per_seq in spec:
+        h = eng.debug(buf, shp)
+        sc = eng.debug("bn/%s%d/scale" % (tag, i), (shp[-1],))
+        sh = eng.debug("bn/%s%d/shift" % (tag, i), (shp[-1],))
+        m = (h.astype(np.float64) * sc + sh) > 0     # sign of the exact fused multiply-add the kernels evaluate
+        if per_seq and group > 1:
+            m = np.repeat(m, group, axis=0)
+        masks[(tag, i)] = m.astype(np.float32)
+    return masks
+
+
+def compare_step(eng, feed, prm, G, group, shapes_only=False, metric=None, dtype=None, mask_flips=False):
     """Run one gradient-only step on the engine and the oracle; return {name: relative error}
     (max-norm by default; ``metric=relerr_l2`` for the backward / gradient entries)."""
     bw_err = metric or relerr
     import torch
     from oracle import clsr_oracle as O
     from clsr_b200.engine import STEP_NO_OPTIMIZER, STEP_NO_BN_UPDATE
-    cfg = oracle_config(G)
     B = feed["users"].shape[0]
     T = feed["mask"].shape[1]
+    cfg = oracle_config(G, max_seq_length=T)
+    dtype = dtype or torch.float64
     S = B // group
     c = eng.cfg
     D, U, H, Q, A0, A1 = c.item_dim + c.cate_dim, c.user_dim, c.hidden, c.user_dim + c.item_dim + c.cate_dim, c.att0, c.att1
     losses = eng.train_step(feed, group=group, flags=STEP_NO_OPTIMIZER | STEP_NO_BN_UPDATE)
-    out, L, dense, slices, ig = O.compute_gradients(prm, feed, cfg, torch.float64, retain=RETAIN)
+    if mask_flips:
+        with O.relu_decisions(engine_relu_masks(eng, B, S, T, group)) as rd:
+            out, L, dense, slices, ig = O.compute_gradients(prm, feed, cfg, dtype, retain=RETAIN)
+        flips = dict(rd.flips)
+    else:
+        out, L, dense, slices, ig = O.compute_gradients(prm, feed, cfg, dtype, retain=RETAIN)
+        flips = {}
     I = {k: (v.detach().numpy() if hasattr(v, "detach") else v) for k, v in out["inter"].items()}
     g = lambda a: a[::group]
     res = {}
@@ -140,4 +168,6 @@ def compare_step(eng, feed, prm, G, group, shapes_only=False, metric=None):
         got[ids] = rows
         res["grad/" + tab] = bw_err(got, dense_ref)
         res["uniq/" + tab] = float(len(ids) != len(np.unique(idx.numpy())))
+    for (tag, i), n in flips.items():
+        res["flips/%s%d" % (tag, i)] = n
     return res, losses

@@ -38,8 +38,15 @@ def _step_vs_oracle(S, T, seed, dtype, tol_logit, tol_loss, tol_dense, tol_table
     eng = PU.make_engine(prm, NI, NC, NU, max_rows=B, T=T, G=G, math_mode=1)
     got = eng.train_step(feed, group=G, flags=STEP_NO_OPTIMIZER | STEP_NO_BN_UPDATE)
     cfg = PU.oracle_config(G, max_seq_length=T)
-    out, L, dense, slices, _ = O.compute_gradients(prm, feed, cfg, dtype)
+    # the engine's ReLU decisions are fed into the oracle (see test_step_matches_oracle_tensor_core_path): a unit
+    # within rounding distance of the kink may legitimately fall on either side; the flips are counted and printed
+    with O.relu_decisions(PU.engine_relu_masks(eng, B, S, T, G)) as rd:
+        out, L, dense, slices, _ = O.compute_gradients(prm, feed, cfg, dtype)
     rep = {}
+    total_units = B * T * 120 + S * T * 120 + B * (120 + 164)
+    nflip = sum(rd.flips.values())
+    print("relu decisions differing from the oracle: %d of %d units (%s)" % (nflip, total_units, rd.flips))
+    assert nflip < 1e-4 * total_units
     # gathered history rows: bit-exact (compare a strided sample of sequences to keep the copy small)
     X = eng.debug("X", (S, T, 40))
     ref_X = out["inter"]["hist"].detach().numpy().reshape(S, G, T, 40)[:, 0]
@@ -52,8 +59,8 @@ def _step_vs_oracle(S, T, seed, dtype, tol_logit, tol_loss, tol_dense, tol_table
         assert rep[k] < tol_loss, (k, got[k], float(L[k]))
     dg = eng.get_dense(3)
     for name, gref in dense.items():
-        if name.endswith("b_nn_output"):
-            continue   # softmax shift invariance: the true gradient is ~0
+        if name.endswith("b_nn_output") or "b_nn_layer" in name:
+            continue   # softmax shift invariance / a bias in front of BatchNorm: the true gradient is 0, what is left is rounding
         rep["grad/" + name.split("sequential/")[-1]] = PU.relerr_l2(dg[name], gref.numpy().reshape(-1))
     worst = max((v, k) for k, v in rep.items() if k.startswith("grad/"))
     assert worst[0] < tol_dense, worst
@@ -79,14 +86,14 @@ def test_taobao_config_step_matches_fp32_oracle(cuda_lib):
     """BASELINE config 2: the batch bench.py times.  fp32 oracle => its own rounding is part of the gap."""
     import torch
     _step_vs_oracle(S=4096, T=50, seed=101, dtype=torch.float32, tol_logit=1e-3, tol_loss=2e-4,
-                    tol_dense=1e-2, tol_table=1e-2)
+                    tol_dense=1e-3, tol_table=2e-4)
 
 
 def test_kuaishou_window_step_matches_fp64_oracle(cuda_lib):
     """BASELINE config 3 shape (T=250) at 512 sequences, fp64 oracle."""
     import torch
     _step_vs_oracle(S=512, T=250, seed=102, dtype=torch.float64, tol_logit=1e-3, tol_loss=2e-4,
-                    tol_dense=2e-2, tol_table=2e-2)
+                    tol_dense=1e-3, tol_table=2e-4)
 
 
 def test_auc_matches_oracle(cuda_lib):
