@@ -10,6 +10,18 @@
 
 namespace clsr {
 
+// View of a (possibly row-sharded) table: global row r lives on rank r % world at local row r / world
+// (round-robin: ids are popularity ranks, sequential_reviews.py:114-140, a block partition would put every hot
+// row on rank 0).  p[r] is rank r's shard mapped into this process (CUDA IPC over NVLink / NVSwitch peer
+// memory); world is a power of two, so owner = id & mask, local row = id >> shift.  An unsharded table is
+// the world = 1 case (mask 0, shift 0).  Gathers read straight from the owning GPU: the transfer IS the gather.
+constexpr int kMaxWorld = 16;
+struct TabView {
+  const float* p[kMaxWorld];
+  int shift, mask;
+  CLSR_DEVINL const float* row(int id, int dim) const { return p[id & mask] + (size_t)(id >> shift) * dim; }
+};
+
 // hist_input[p, :] = concat(item_table[ih[p]], cate_table[ch[p]]); p = s*T + t.
 // Index arrays are addressed as base[(p / T) * seq_stride + p % T] so a [B,T] feed can be read at
 // every G-th row without a compaction pass.  One thread moves one 16-byte vector; the V = (Di+Dc)/4
@@ -19,8 +31,7 @@ namespace clsr {
 template <int UNROLL>
 __global__ void __launch_bounds__(256)
 gather_hist_kernel(const int32_t* __restrict__ ih, const int32_t* __restrict__ ch, int seq_stride, int T,
-                   const float* __restrict__ item_tab, const float* __restrict__ cate_tab, int Di, int Dc,
-                   float* __restrict__ out, long long npos) {
+                   TabView item_tab, TabView cate_tab, int Di, int Dc, float* __restrict__ out, long long npos) {
   const int VI = Di >> 2, V = (Di + Dc) >> 2;
   const long long nvec = npos * V;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -39,9 +50,9 @@ gather_hist_kernel(const int32_t* __restrict__ ih, const int32_t* __restrict__ c
         int t = (int)(p - s * T);
         long long io = s * seq_stride + t;
         if (q < VI) {
-          src[u] = reinterpret_cast<const float4*>(item_tab + (size_t)__ldg(ih + io) * Di) + q;
+          src[u] = reinterpret_cast<const float4*>(item_tab.row(__ldg(ih + io), Di)) + q;
         } else {
-          src[u] = reinterpret_cast<const float4*>(cate_tab + (size_t)__ldg(ch + io) * Dc) + (q - VI);
+          src[u] = reinterpret_cast<const float4*>(cate_tab.row(__ldg(ch + io), Dc)) + (q - VI);
         }
       }
     }
@@ -56,16 +67,15 @@ gather_hist_kernel(const int32_t* __restrict__ ih, const int32_t* __restrict__ c
 }
 
 // out[r, col0 : col0+dim] = table[idx[r*idx_stride], :]   (targets, users)
-__global__ void gather_rows_kernel(const int32_t* __restrict__ idx, int idx_stride,
-                                   const float* __restrict__ tab, int dim, float* __restrict__ out, int ldo,
-                                   int col0, int rows) {
+__global__ void gather_rows_kernel(const int32_t* __restrict__ idx, int idx_stride, TabView tab, int dim,
+                                   float* __restrict__ out, int ldo, int col0, int rows) {
   const int V = dim >> 2;
   long long n = (long long)rows * V;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n;
        g += (long long)gridDim.x * blockDim.x) {
     int r = (int)(g / V), q = (int)(g % V);
     int id = __ldg(idx + (size_t)r * idx_stride);
-    float4 v = __ldg(reinterpret_cast<const float4*>(tab + (size_t)id * dim) + q);
+    float4 v = __ldg(reinterpret_cast<const float4*>(tab.row(id, dim)) + q);
     *reinterpret_cast<float4*>(out + (size_t)r * ldo + col0 + q * 4) = v;
   }
 }
@@ -378,5 +388,226 @@ __global__ void adam_lazy_kernel(float* __restrict__ var, float* __restrict__ m,
   }
 }
 #undef CLSR_ADAM1
+
+// ---- row-sharded tables under the data-parallel step ----------------------------------------------------
+// Every rank de-duplicates its own slices exactly as on one GPU (slot table, compact rows), then pushes each
+// unique compact row ONCE to the rank that owns it: one 16-byte reduction per vector straight into the
+// owner's dense gradient shard over NVLink, plus a `touched` mark.  The owner adds the involved-row terms
+// and applies the optimizer to its 1/world of the rows; nothing is all-gathered, no replica repeats
+// another's scatter, and the TF-faithful full-table sweep is divided by world.
+struct GradView {
+  float* g[kMaxWorld];          // rank r's dense gradient shard [local_rows, dim]
+  int32_t* touched[kMaxWorld];  // rank r's per-row "present in this step" marks
+  int shift, mask;
+};
+
+__global__ void push_compact_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict__ counter,
+                                    const float* __restrict__ cg, int dim, GradView gv) {
+  const int V = dim >> 2;
+  const long long n = (long long)(*counter) * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long c = i / V;
+    const int q = (int)(i - c * V);
+    const int id = uniq[c];
+    const int owner = id & gv.mask;
+    const size_t local = (size_t)(id >> gv.shift);
+    const float4 v = *reinterpret_cast<const float4*>(cg + (size_t)c * dim + q * 4);
+    red_add_v4(gv.g[owner] + local * dim + q * 4, v);
+    if (q == 0) gv.touched[owner][local] = 1;
+  }
+}
+
+// out[0] = number of touched local rows (the owner's share of tf.unique's count)
+__global__ void shard_count_touched_kernel(const int32_t* __restrict__ touched, long long rows, int32_t* __restrict__ out) {
+  int n = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x)
+    n += touched[i] != 0;
+  n = __reduce_add_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
+}
+
+// involved_kernel on the owner's shard: one warp per touched local row (n_uniq: the GLOBAL unique count, for
+// the discrepancy mean).
+__global__ void shard_involved_kernel(const float* __restrict__ tab, const float* __restrict__ other, int dim,
+                                      const int32_t* __restrict__ touched, long long rows, float* __restrict__ g,
+                                      float l2, float disc_w, const int32_t* __restrict__ n_uniq, int count_disc,
+                                      double* __restrict__ sumsq, double* __restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  float ss = 0.f, rr = 0.f, dd = 0.f;
+  const float dcoef = other ? -2.0f * disc_w / ((float)(*n_uniq) * (float)dim) : 0.f;
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
+    if (!touched[r]) continue;
+    const size_t row = (size_t)r * dim;
+    for (int k = lane; k < dim; k += 32) {
+      float x = tab[row + k];
+      float v = l2 * x;
+      rr += x * x;
+      if (other) {
+        float df = x - other[row + k];
+        v += dcoef * df;
+        dd += df * df;
+      }
+      g[row + k] += v;
+      ss += v * v;
+    }
+  }
+  ss = warp_sum(ss); rr = warp_sum(rr); dd = warp_sum(dd);
+  if (lane == 0) {
+    if (ss != 0.f) atomicAdd(sumsq, (double)ss);
+    if (rr != 0.f) atomicAdd(acc, (double)rr);
+    if (other && count_disc && dd != 0.f) atomicAdd(acc + 1, (double)dd);
+  }
+}
+
+// TF's non-lazy Adam over the owner's shard with a dense gradient shard: every row decays and moves, touched
+// rows add their clipped gradient; the gradient rows are zeroed again on the way out.
+template <int UN>
+__global__ void __launch_bounds__(256)
+adam_sweep_shard_kernel(float* __restrict__ var, float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
+                        const int32_t* __restrict__ touched, int dim, long long rows, AdamHyper hp,
+                        const double* __restrict__ sumsq) {
+  const int V = dim >> 2;
+  float scale = 1.f;
+  if (hp.clip > 0.f) {
+    float nrm = (float)sqrt(*sumsq);
+    scale = hp.clip / fmaxf(nrm, hp.clip);
+  }
+  const long long nvec = rows * V;
+  const long long stride = blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x * UN + threadIdx.x; i0 < nvec;
+       i0 += (long long)gridDim.x * blockDim.x * UN) {
+    float4 mv[UN], vv[UN], xv[UN];
+    int c[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long i = i0 + u * stride;
+      const long long ic = i < nvec ? i : nvec - 1;
+      mv[u] = ldg_stream(reinterpret_cast<const float4*>(m) + ic);
+      vv[u] = ldg_stream(reinterpret_cast<const float4*>(v) + ic);
+      xv[u] = ldg_stream(reinterpret_cast<const float4*>(var) + ic);
+      c[u] = __ldg(touched + ic / V);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) continue;
+      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c[u]) {
+        gv = *reinterpret_cast<const float4*>(g + i * 4);
+        *reinterpret_cast<float4*>(g + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        gv.x *= scale; gv.y *= scale; gv.z *= scale; gv.w *= scale;
+      }
+#define CLSR_ADAM1(c_)                                                      \
+  mv[u].c_ = hp.beta1 * mv[u].c_ + (1.f - hp.beta1) * gv.c_;                \
+  vv[u].c_ = hp.beta2 * vv[u].c_ + (1.f - hp.beta2) * gv.c_ * gv.c_;        \
+  xv[u].c_ -= hp.lr_t * mv[u].c_ / (sqrtf(vv[u].c_) + hp.eps);
+      CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
+#undef CLSR_ADAM1
+      stg_stream(reinterpret_cast<float4*>(m) + i, mv[u]);
+      stg_stream(reinterpret_cast<float4*>(v) + i, vv[u]);
+      stg_stream(reinterpret_cast<float4*>(var) + i, xv[u]);
+    }
+  }
+}
+
+// LazyAdam on the owner's shard (only touched rows move), or -- with hp.lr_t == 0 and `apply` = 0 -- just the
+// clean-up of a gradient-only step: one warp per touched row, gradient row zeroed on the way out.
+__global__ void adam_lazy_shard_kernel(float* __restrict__ var, float* __restrict__ m, float* __restrict__ v,
+                                       float* __restrict__ g, const int32_t* __restrict__ touched, int dim,
+                                       long long rows, AdamHyper hp, const double* __restrict__ sumsq, int apply) {
+  float scale = 1.f;
+  if (hp.clip > 0.f) {
+    float nrm = (float)sqrt(*sumsq);
+    scale = hp.clip / fmaxf(nrm, hp.clip);
+  }
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
+    if (!touched[r]) continue;
+    const size_t row = (size_t)r * dim;
+    for (int k = lane; k < dim; k += 32) {
+      const float gv = g[row + k] * scale;
+      g[row + k] = 0.f;
+      if (apply) {
+        const float mv = hp.beta1 * m[row + k] + (1.f - hp.beta1) * gv;
+        const float vv = hp.beta2 * v[row + k] + (1.f - hp.beta2) * gv * gv;
+        m[row + k] = mv; v[row + k] = vv;
+        var[row + k] -= hp.lr_t * mv / (sqrtf(vv) + hp.eps);
+      }
+    }
+  }
+}
+
+// ---- one-shot all-reduce over peer memory ------------------------------------------------------------------
+// The step's small reductions (BatchNorm sums: 2N doubles per layer and direction; loss partial sums; counts)
+// are latency, not bandwidth: an NCCL call costs 10-30 us each and a data-parallel step needs ~20 of them.  Here
+// every rank PUSHES its vector into its slot of every peer's buffer (NVLink stores), publishes a sequence flag,
+// waits until all peers' flags for this sequence number have arrived in its own memory, and sums the slots in
+// rank order -- every rank gets the bit-identical result after one NVLink round trip, inside the kernel that
+// consumes it (the BatchNorm finalize kernels below call it in place).  n = 0 is a barrier.  Two phases
+// (seq & 1) suffice: a peer can only write phase p again after it has passed the next call, which needs this
+// rank's flag, which this rank only publishes after it has read phase p.
+constexpr int kPeerSlots = 512;
+struct PeerComm {
+  double* data[kMaxWorld];                // rank r's buffer: [2][world][kPeerSlots]
+  unsigned long long* flag[kMaxWorld];    // rank r's flags:  [2][world]
+  int rank, world;
+};
+CLSR_DEVINL void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+CLSR_DEVINL unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+CLSR_DEVINL double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+CLSR_DEVINL void st_volatile_f64(double* p, double v) {
+  asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// All threads of ONE CTA call this; vals: n doubles in shared memory, replaced by their sum over ranks.
+CLSR_DEVINL void peer_allreduce_block(const PeerComm& pc, unsigned long long seq, double* vals, int n) {
+  const int ph = (int)(seq & 1ull);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int r = 0; r < pc.world; ++r) {
+    double* dst = pc.data[r] + ((size_t)ph * pc.world + pc.rank) * kPeerSlots;
+    for (int i = tid; i < n; i += nt) st_volatile_f64(dst + i, vals[i]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < pc.world) {
+    st_release_sys(pc.flag[tid] + (size_t)ph * pc.world + pc.rank, seq);
+    const unsigned long long* mine = pc.flag[pc.rank] + (size_t)ph * pc.world + tid;
+    while (ld_acquire_sys(mine) < seq) __nanosleep(20);
+  }
+  __syncthreads();
+  const double* src = pc.data[pc.rank] + (size_t)ph * pc.world * kPeerSlots;
+  for (int i = tid; i < n; i += nt) {
+    double s = 0.0;
+    for (int r = 0; r < pc.world; ++r) s += ld_volatile_f64(src + (size_t)r * kPeerSlots + i);
+    vals[i] = s;
+  }
+  __syncthreads();
+}
+
+// Standalone form for the step's scalars: up to three arrays (doubles, doubles, int32) reduced in one exchange.
+__global__ void peer_allreduce_kernel(PeerComm pc, unsigned long long seq, double* a, int na, double* b, int nb,
+                                      int32_t* c, int nc) {
+  __shared__ double vals[kPeerSlots];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < na; i += blockDim.x) vals[i] = a[i];
+  for (int i = tid; i < nb; i += blockDim.x) vals[na + i] = b[i];
+  for (int i = tid; i < nc; i += blockDim.x) vals[na + nb + i] = (double)c[i];
+  __syncthreads();
+  peer_allreduce_block(pc, seq, vals, na + nb + nc);
+  for (int i = tid; i < na; i += blockDim.x) a[i] = vals[i];
+  for (int i = tid; i < nb; i += blockDim.x) b[i] = vals[na + i];
+  for (int i = tid; i < nc; i += blockDim.x) c[i] = (int32_t)llrint(vals[na + nb + i]);
+}
 
 }  // namespace clsr

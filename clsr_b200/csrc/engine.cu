@@ -139,6 +139,22 @@ struct clsr_engine {
   int (*ncclAllGather_)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*ncclCommDestroy_)(void*) = nullptr;
   const char* (*ncclGetErrorString_)(int) = nullptr;
+  // peer-memory communication (one-shot all-reduce / barrier kernels, embed.cuh) and row-sharded tables
+  bool peer_ready = false;
+  PeerComm pc;
+  unsigned long long peer_seq = 0;
+  double* comm_data = nullptr;
+  unsigned long long* comm_flags = nullptr;
+  std::vector<void*> peer_opened;               // cudaIpcOpenMemHandle'd pointers (closed at destroy)
+  bool sharded = false;
+  long long tab_local_rows[CLSR_NUM_TABLES] = {0, 0, 0, 0};
+  float* sh_val[CLSR_NUM_TABLES] = {nullptr, nullptr, nullptr, nullptr};   // engine-owned shards (sharded mode)
+  float* sh_m[CLSR_NUM_TABLES] = {nullptr, nullptr, nullptr, nullptr};
+  float* sh_v[CLSR_NUM_TABLES] = {nullptr, nullptr, nullptr, nullptr};
+  float* sh_g[CLSR_NUM_TABLES] = {nullptr, nullptr, nullptr, nullptr};
+  int32_t* sh_touched[CLSR_NUM_TABLES] = {nullptr, nullptr, nullptr, nullptr};
+  GradView gview[CLSR_NUM_TABLES];
+  TabView tview[CLSR_NUM_TABLES];
   int32_t *g_ih = nullptr, *g_ch = nullptr, *g_items = nullptr, *g_cates = nullptr, *g_users = nullptr;
   int32_t *l_ih = nullptr, *l_ch = nullptr, *l_users = nullptr;
   float *g_dX = nullptr, *g_dtgt = nullptr, *g_dul = nullptr, *g_dus = nullptr;
@@ -222,8 +238,21 @@ int join_aux(clsr_engine* e, const char* name) {
 
 enum { kNcclInt32 = 2, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
 
+// One exchange over peer memory for up to three small arrays (doubles, doubles, int32); n = 0 everywhere = barrier.
+int peer_reduce(clsr_engine* e, double* a, int na, double* b, int nb, int32_t* c, int nc) {
+  if (e->world <= 1) return 0;
+  if (!e->peer_ready) return fail(e, CLSR_ERR_STATE, "peer communication not set up (clsr_peer_setup_*)");
+  if (na + nb + nc > kPeerSlots) return fail(e, CLSR_ERR_ARG, "peer_reduce: %d values exceed %d", na + nb + nc, kPeerSlots);
+  peer_allreduce_kernel<<<1, 256, 0, e->stream>>>(e->pc, ++e->peer_seq, a, na, b, nb, c, nc);
+  POST(na + nb + nc ? "peer_allreduce" : "peer_barrier");
+  return 0;
+}
+
 int allreduce(clsr_engine* e, void* buf, size_t count, int dtype) {
   if (e->world <= 1) return 0;
+  if (e->peer_ready && count <= (size_t)kPeerSlots && (dtype == kNcclFloat64 || dtype == kNcclInt32))
+    return dtype == kNcclFloat64 ? peer_reduce(e, (double*)buf, (int)count, nullptr, 0, nullptr, 0)
+                                 : peer_reduce(e, nullptr, 0, nullptr, 0, (int32_t*)buf, (int)count);
   int r = e->ncclAllReduce_(buf, buf, count, dtype, kNcclSum, e->comm, e->stream);
   if (r != 0) return fail(e, CLSR_ERR_NCCL, "ncclAllReduce failed: %s", e->ncclGetErrorString_(r));
   MARK("nccl_allreduce");
@@ -497,7 +526,8 @@ int build_weight_maps(clsr_engine* e) {
   e->n_unprep = (int)unprep.size();
   int rc;
   if ((rc = dalloc(e, &e->Wd, e->Wtot))) return rc;
-  if ((rc = dalloc(e, &e->dWd, e->Wtot))) return rc;
+  if ((rc = dalloc(e, &e->Pg, e->Ptot + e->Wtot))) return rc;
+  e->dWd = e->Pg + e->Ptot;   // Ptot is a multiple of 4 floats: dWd stays 16-byte aligned
   if ((rc = dalloc(e, &e->ops_prep, e->n_prep, false))) return rc;
   if ((rc = dalloc(e, &e->ops_unprep, e->n_unprep, false))) return rc;
   CK(cudaMemcpy(e->ops_prep, prep.data(), prep.size() * sizeof(BlockOp), cudaMemcpyHostToDevice));
@@ -816,9 +846,16 @@ EpiOp e_store(float* C, int ldc, const float* bias = nullptr, int flags = 0) {
 
 int bn_fwd(clsr_engine* e, BnLayer& b, double count, int train, int update) {
   if (train && e->world > 1) {  // single-device semantics: statistics over the global batch
+    count *= e->world;
+    if (e->peer_ready && 2 * b.N <= kPeerSlots) {   // all-reduce over NVLink peer memory inside the finalize kernel
+      bn_fwd_finalize_peer_kernel<<<1, 256, 0, e->stream>>>(
+          e->pc, ++e->peer_seq, b.stat_f, b.N, count, e->P + b.gamma, e->P + b.beta, e->cfg.bn_eps, e->cfg.bn_momentum,
+          e->P + b.mmean, e->P + b.mvar, update, b.scale, b.shift, b.mean, b.rstd);
+      POST("bn_fwd_finalize_peer");
+      return 0;
+    }
     int rc = allreduce(e, b.stat_f, 2 * b.N, kNcclFloat64);
     if (rc) return rc;
-    count *= e->world;
   }
   bn_fwd_finalize_kernel<<<cdiv(b.N, 128), 128, 0, e->stream>>>(
       b.stat_f, b.N, count, e->P + b.gamma, e->P + b.beta, e->cfg.bn_eps, e->cfg.bn_momentum,
@@ -827,16 +864,22 @@ int bn_fwd(clsr_engine* e, BnLayer& b, double count, int train, int update) {
   return 0;
 }
 int bn_bwd(clsr_engine* e, BnLayer& b, double count) {
-  if (e->world > 1) {
-    int rc = allreduce(e, b.stat_b, 2 * b.N, kNcclFloat64);
-    if (rc) return rc;
-    count *= e->world;
-  }
   // gamma/beta gradients come from the already global sums: only rank 0 contributes them to the
   // dense-gradient all-reduce
+  const float add_scale = e->rank == 0 ? 1.f : 0.f;
+  if (e->world > 1) {
+    count *= e->world;
+    if (e->peer_ready && 2 * b.N <= kPeerSlots) {
+      bn_bwd_finalize_peer_kernel<<<1, 256, 0, e->stream>>>(e->pc, ++e->peer_seq, b.stat_b, b.N, count, e->P + b.gamma, b.mean,
+                                                            b.rstd, b.al, b.be, b.ga, e->Pg + b.gamma, e->Pg + b.beta, add_scale);
+      POST("bn_bwd_finalize_peer");
+      return 0;
+    }
+    int rc = allreduce(e, b.stat_b, 2 * b.N, kNcclFloat64);
+    if (rc) return rc;
+  }
   bn_bwd_finalize_kernel<<<cdiv(b.N, 128), 128, 0, e->stream>>>(
-      b.stat_b, b.N, count, e->P + b.gamma, b.mean, b.rstd, b.al, b.be, b.ga, e->Pg + b.gamma, e->Pg + b.beta,
-      e->rank == 0 ? 1.f : 0.f);
+      b.stat_b, b.N, count, e->P + b.gamma, b.mean, b.rstd, b.al, b.be, b.ga, e->Pg + b.gamma, e->Pg + b.beta, add_scale);
   POST("bn_bwd_finalize");
   return 0;
 }
@@ -1033,18 +1076,18 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
   {
     long long nvec = M * (D / 4);
     gather_hist_kernel<4><<<grid1d(e, cdiv(nvec, 4), 256, 8), 256, 0, st>>>(
-        c.ih, c.ch, c.seq_stride, T, e->tab[CLSR_TABLE_ITEM], e->tab[CLSR_TABLE_CATE], Di, Dc, X, M);
+        c.ih, c.ch, c.seq_stride, T, e->tview[CLSR_TABLE_ITEM], e->tview[CLSR_TABLE_CATE], Di, Dc, X, M);
     POST("gather_hist");
   }
   float* tgt = e->B("tgt");
-  gather_rows_kernel<<<grid1d(e, (long long)B * Di / 4, 256), 256, 0, st>>>(c.items, 1, e->tab[CLSR_TABLE_ITEM], Di, tgt, D, 0, B);
+  gather_rows_kernel<<<grid1d(e, (long long)B * Di / 4, 256), 256, 0, st>>>(c.items, 1, e->tview[CLSR_TABLE_ITEM], Di, tgt, D, 0, B);
   POST("gather_tgt_item");
-  gather_rows_kernel<<<grid1d(e, (long long)B * Dc / 4, 256), 256, 0, st>>>(c.cates, 1, e->tab[CLSR_TABLE_CATE], Dc, tgt, D, Di, B);
+  gather_rows_kernel<<<grid1d(e, (long long)B * Dc / 4, 256), 256, 0, st>>>(c.cates, 1, e->tview[CLSR_TABLE_CATE], Dc, tgt, D, Di, B);
   POST("gather_tgt_cate");
   float *ul = e->B("ul"), *us = e->B("us");
-  gather_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(c.users, c.user_stride, e->tab[CLSR_TABLE_USER_LONG], U, ul, U, 0, S);
+  gather_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(c.users, c.user_stride, e->tview[CLSR_TABLE_USER_LONG], U, ul, U, 0, S);
   POST("gather_ul");
-  gather_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(c.users, c.user_stride, e->tab[CLSR_TABLE_USER_SHORT], U, us, U, 0, S);
+  gather_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(c.users, c.user_stride, e->tview[CLSR_TABLE_USER_SHORT], U, us, U, 0, S);
   POST("gather_us");
 
   // ---- hoisted input projections of the three recurrences ----
@@ -1414,6 +1457,35 @@ int backward(clsr_engine* e, const StepCtx& c) {
   return 0;
 }
 
+// Replicated-table data parallelism only: staging for the all-gathered sparse-gradient inputs and room for the
+// global unique sets (allocated on first use; the row-sharded mode needs none of it).
+int alloc_replicated_staging(clsr_engine* e) {
+  if (e->g_ih) return 0;
+  const long long W = e->world, Bm = e->Bmax, Sm = e->Smax, T = e->T, M = Sm * T;
+  int rc;
+  if ((rc = dalloc(e, &e->l_ih, M)) || (rc = dalloc(e, &e->l_ch, M)) || (rc = dalloc(e, &e->l_users, Sm))) return rc;
+  if ((rc = dalloc(e, &e->g_ih, W * M)) || (rc = dalloc(e, &e->g_ch, W * M)) || (rc = dalloc(e, &e->g_users, W * Sm)) ||
+      (rc = dalloc(e, &e->g_items, W * Bm)) || (rc = dalloc(e, &e->g_cates, W * Bm)))
+    return rc;
+  if ((rc = dalloc(e, &e->g_dX, W * M * e->D)) || (rc = dalloc(e, &e->g_dtgt, W * Bm * e->D)) ||
+      (rc = dalloc(e, &e->g_dul, W * Sm * e->U)) || (rc = dalloc(e, &e->g_dus, W * Sm * e->U)))
+    return rc;
+  const long long rows3[3] = {e->cfg.n_items, e->cfg.n_cates, e->cfg.n_users};
+  const long long want[3] = {W * (M + Bm), W * (M + Bm), W * Sm};
+  for (int i = 0; i < 3; ++i) {
+    long long cap = want[i] < rows3[i] ? want[i] : rows3[i];
+    if (cap > e->uniq_cap[i]) {
+      e->uniq_cap[i] = cap;
+      if ((rc = dalloc(e, &e->uniq[i], cap))) return rc;
+    }
+  }
+  if ((rc = dalloc(e, &e->cg[0], e->uniq_cap[0] * e->Di)) || (rc = dalloc(e, &e->cg[1], e->uniq_cap[1] * e->Dc)) ||
+      (rc = dalloc(e, &e->cg[2], e->uniq_cap[2] * e->U)) || (rc = dalloc(e, &e->cg[3], e->uniq_cap[2] * e->U)))
+    return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
 // K2 + K13: unique ids per table and scatter-add of every slice gradient into compact rows.
 // Data-parallel runs first all-gather the raw ids and per-position gradients of every rank, so each
 // replica builds the identical global (unique ids, summed rows) set and applies the identical update.
@@ -1426,7 +1498,8 @@ int sparse_grads(clsr_engine* e, const StepCtx& c) {
   int seq_stride = c.seq_stride, user_stride = c.user_stride;
   const float *dX = e->B("dX"), *dtgt = e->B("dtgt"), *dul = e->B("dul"), *dus = e->B("dus");
   int rc;
-  if (e->world > 1) {
+  if (e->world > 1 && !e->sharded) {
+    if ((rc = alloc_replicated_staging(e))) return rc;
     compact_ids_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(c.ih, T, c.seq_stride, M, e->l_ih);
     POST("compact_ids");
     compact_ids_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(c.ch, T, c.seq_stride, M, e->l_ch);
@@ -1478,6 +1551,34 @@ int sparse_grads(clsr_engine* e, const StepCtx& c) {
                                                                           e->slot[2], e->cg[3], S, e->sumsq + 3);
   POST("scatter_us");
   const float l2 = e->cfg.embed_l2, dw = e->cfg.discrepancy_weight;
+  if (e->sharded) {
+    // Row-sharded tables: every unique compact row goes ONCE to its owner (NVLink reductions into the owner's
+    // dense gradient shard + a touched mark); after a barrier the owner counts its touched user rows (the global
+    // tf.unique count of the discrepancy mean is their sum over ranks) and adds the involved-row terms.
+    const int cnt_ix[4] = {1, 2, 3, 3}, slot_ix[4] = {0, 1, 2, 2};
+    for (int t = 0; t < 4; ++t) {
+      push_compact_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->uniq[slot_ix[t]], e->counts + cnt_ix[t], e->cg[t], e->tab_dim[t],
+                                                          e->gview[t]);
+      POST("push_compact");
+    }
+    if ((rc = peer_reduce(e, nullptr, 0, nullptr, 0, nullptr, 0))) return rc;   // every rank's pushes have landed
+    shard_count_touched_kernel<<<e->num_sms, 256, 0, st>>>(e->sh_touched[2], e->tab_local_rows[2], e->counts + 4);
+    POST("shard_count_touched");
+    if ((rc = peer_reduce(e, nullptr, 0, nullptr, 0, e->counts + 4, 1))) return rc;
+    shard_involved_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->sh_val[0], nullptr, Di, e->sh_touched[0], e->tab_local_rows[0],
+                                                          e->sh_g[0], l2, 0.f, e->counts + 4, 0, e->sumsq + 0, e->acc + 5);
+    POST("involved_item");
+    shard_involved_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->sh_val[1], nullptr, Dc, e->sh_touched[1], e->tab_local_rows[1],
+                                                          e->sh_g[1], l2, 0.f, e->counts + 4, 0, e->sumsq + 1, e->acc + 6);
+    POST("involved_cate");
+    shard_involved_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->sh_val[2], e->sh_val[3], U, e->sh_touched[2], e->tab_local_rows[2],
+                                                          e->sh_g[2], l2, dw, e->counts + 4, 0, e->sumsq + 2, e->acc + 7);
+    POST("involved_ul");
+    shard_involved_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->sh_val[3], e->sh_val[2], U, e->sh_touched[2], e->tab_local_rows[3],
+                                                          e->sh_g[3], l2, dw, e->counts + 4, 1, e->sumsq + 3, e->acc + 8);
+    POST("involved_us");
+    return 0;
+  }
   involved_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[0], nullptr, Di, e->uniq[0], e->counts + 1, e->cg[0], l2, 0.f, 0,
                                                   e->sumsq + 0, e->acc + 5);
   POST("involved_item");
@@ -1495,6 +1596,21 @@ int sparse_grads(clsr_engine* e, const StepCtx& c) {
   return 0;
 }
 
+// Sharded mode: zero the touched marks (and, after a gradient-only step, the gradient rows) of the owner's shards.
+int shard_cleanup(clsr_engine* e, bool grads_too) {
+  AdamHyper hz = {0.f, 0.f, 0.f, 1.f, 0.f};
+  for (int t = 0; t < 4; ++t) {
+    const int tt = t == 3 ? 2 : t;   // the two user tables share one touched array
+    if (grads_too) {
+      adam_lazy_shard_kernel<<<e->num_sms * 4, 256, 0, e->stream>>>(e->sh_val[t], e->sh_m[t], e->sh_v[t], e->sh_g[t], e->sh_touched[tt],
+                                                                   e->tab_dim[t], e->tab_local_rows[t], hz, e->sumsq + t, 0);
+      POST("shard_zero_grad");
+    }
+  }
+  for (int t = 0; t < 3; ++t) CK(cudaMemsetAsync(e->sh_touched[t], 0, (size_t)e->tab_local_rows[t] * 4, e->stream));
+  return 0;
+}
+
 int optimizer_step(clsr_engine* e) {
   cudaStream_t st = e->stream;
   const clsr_config& cf = e->cfg;
@@ -1508,6 +1624,20 @@ int optimizer_step(clsr_engine* e) {
   const int slot_ix[4] = {0, 1, 2, 2}, cnt_ix[4] = {1, 2, 3, 3};
   for (int tb = 0; tb < 4; ++tb) {
     if (!e->tab_m[tb] || !e->tab_v[tb]) return fail(e, CLSR_ERR_STATE, "Adam slots of table %d not bound", tb);
+    if (e->sharded) {   // the owner updates its 1/world of the rows from its dense gradient shard
+      const int tt = tb == 3 ? 2 : tb;
+      if (cf.optimizer == 1) {
+        adam_lazy_shard_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->sh_val[tb], e->sh_m[tb], e->sh_v[tb], e->sh_g[tb], e->sh_touched[tt],
+                                                             e->tab_dim[tb], e->tab_local_rows[tb], hp, e->sumsq + tb, 1);
+        POST("adam_lazy");
+      } else {
+        adam_sweep_shard_kernel<2><<<e->num_sms * 16, 256, 0, st>>>(e->sh_val[tb], e->sh_m[tb], e->sh_v[tb], e->sh_g[tb],
+                                                                   e->sh_touched[tt], e->tab_dim[tb], e->tab_local_rows[tb], hp,
+                                                                   e->sumsq + tb);
+        POST("adam_sweep");
+      }
+      continue;
+    }
     if (cf.optimizer == 1) {
       adam_lazy_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[tb], e->tab_m[tb], e->tab_v[tb], e->uniq[slot_ix[tb]],
                                                        e->counts + cnt_ix[tb], e->cg[tb], e->tab_dim[tb], hp, e->sumsq + tb);
@@ -1534,8 +1664,7 @@ int zero_step_state(clsr_engine* e) {
   CK(cudaMemsetAsync(e->counts, 0, 8 * sizeof(int32_t), e->stream));
   CK(cudaMemsetAsync(e->sumsq, 0, 4 * sizeof(double), e->stream));
   CK(cudaMemsetAsync(e->acc, 0, 16 * sizeof(double), e->stream));
-  CK(cudaMemsetAsync(e->Pg, 0, (size_t)e->Ptot * 4, e->stream));
-  CK(cudaMemsetAsync(e->dWd, 0, (size_t)e->Wtot * 4, e->stream));
+  CK(cudaMemsetAsync(e->Pg, 0, (size_t)(e->Ptot + e->Wtot) * 4, e->stream));   // Pg | dWd: one block
   Mlp* ms[4] = {&e->mlp_long, &e->mlp_short, &e->mlp_alpha, &e->mlp_logit};
   for (Mlp* m : ms) {
     BnLayer* bl[2] = {&m->bn0, &m->bn1};
@@ -1649,7 +1778,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
   CKC(dalloc(e, &e->P, e->Ptot));
   CKC(dalloc(e, &e->Pm, e->Ptot));
   CKC(dalloc(e, &e->Pv, e->Ptot));
-  CKC(dalloc(e, &e->Pg, e->Ptot));
+  // Pg is allocated together with dWd (build_weight_maps): [Pg | dWd] is one block for memset / all-reduce
   {
     std::vector<DenseVar> dv;
     for (auto& d : e->dense) dv.push_back(DenseVar{d.off, (int)d.n, d.trainable});
@@ -1731,6 +1860,7 @@ void clsr_destroy(clsr_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->comm && e->ncclCommDestroy_) e->ncclCommDestroy_(e->comm);
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+  for (void* p : e->peer_opened) cudaIpcCloseMemHandle(p);
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_losses) cudaFreeHost(e->h_losses);
   if (e->h_out) cudaFreeHost(e->h_out);
@@ -1795,7 +1925,10 @@ int clsr_dense_write(clsr_engine* e, int32_t which, const float* host_src) {
 int clsr_bind_table(clsr_engine* e, int32_t t, float* values, float* m, float* v) {
   if (!e || t < 0 || t >= CLSR_NUM_TABLES || !values) return fail(e, CLSR_ERR_ARG, "bad table binding");
   if (((uintptr_t)values | (uintptr_t)m | (uintptr_t)v) & 15) return fail(e, CLSR_ERR_ARG, "table pointers must be 16-byte aligned");
+  if (e->sharded) return fail(e, CLSR_ERR_STATE, "tables are row-sharded and engine-owned (clsr_table_local)");
   e->tab[t] = values; e->tab_m[t] = m; e->tab_v[t] = v;
+  memset(&e->tview[t], 0, sizeof(TabView));
+  e->tview[t].p[0] = values;
   return CLSR_OK;
 }
 int clsr_set_adam_step(clsr_engine* e, int64_t s) { if (!e) return CLSR_ERR_ARG; e->adam_step = s; return CLSR_OK; }
@@ -1834,19 +1967,26 @@ int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, cls
   if ((rc = stage_inputs(e, batch, &c, true))) return rc;
   MARK("h2d_inputs");
   if ((rc = zero_step_state(e))) return rc;
+  // sharded tables: peers must have finished the previous step's optimizer (and its touched / gradient clean-up)
+  // before this step's gathers read their rows or its pushes mark them
+  if (e->sharded && (rc = peer_reduce(e, nullptr, 0, nullptr, 0, nullptr, 0))) return rc;
   if ((rc = forward(e, c, 1, (flags & CLSR_STEP_NO_BN_UPDATE) ? 0 : 1))) return rc;
   if ((rc = backward(e, c))) return rc;
   if (e->world > 1) {
-    if ((rc = allreduce(e, e->Pg, (size_t)e->Ptot, kNcclFloat32))) return rc;
-    if ((rc = allreduce(e, e->dWd, (size_t)e->Wtot, kNcclFloat32))) return rc;
-    if ((rc = allreduce(e, e->acc, 5, kNcclFloat64))) return rc;  // data + contrastive partial sums
+    // dense gradients + folded-weight gradients live in one block: one NCCL all-reduce
+    if ((rc = allreduce(e, e->Pg, (size_t)(e->Ptot + e->Wtot), kNcclFloat32))) return rc;
+    if (!e->sharded && (rc = allreduce(e, e->acc, 5, kNcclFloat64))) return rc;  // data + contrastive partial sums
   }
   if ((rc = sparse_grads(e, c))) return rc;
   blockop_kernel<<<e->n_unprep, 256, 0, e->stream>>>(e->ops_unprep, e->Pg, e->dWd);
   POST("unprep_grads");
-  dense_l2_norm_kernel<<<(int)e->dense.size(), 1024, 0, e->stream>>>(e->d_vars, e->P, e->Pg, e->cfg.layer_l2, e->d_norms, e->acc);
+  // replicas hold identical dense variables: in sharded mode only rank 0 contributes their regular-loss term
+  dense_l2_norm_kernel<<<(int)e->dense.size(), 1024, 0, e->stream>>>(e->d_vars, e->P, e->Pg, e->cfg.layer_l2, e->d_norms, e->acc,
+                                                                    (e->sharded && e->rank != 0) ? 0.0 : 1.0);
   POST("dense_l2_norm");
-  loss_finalize_kernel<<<1, 32, 0, e->stream>>>(e->acc, e->counts, e->counts + 3, c.G, e->U, e->cfg.embed_l2,
+  // sharded: loss partial sums (data, contrastive, owner-side row norms) and the clip norms in one exchange
+  if (e->sharded && (rc = peer_reduce(e, e->acc, 11, e->sumsq, 4, nullptr, 0))) return rc;
+  loss_finalize_kernel<<<1, 32, 0, e->stream>>>(e->acc, e->counts, e->counts + (e->sharded ? 4 : 3), c.G, e->U, e->cfg.embed_l2,
                                                 e->cfg.contrastive_weight, e->cfg.discrepancy_weight, e->sumsq,
                                                 e->cfg.clip_norm ? e->cfg.max_grad_norm : 0.f, c.G, e->d_clip_steps,
                                                 e->d_losses);
@@ -1854,6 +1994,7 @@ int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, cls
   if (!(flags & CLSR_STEP_NO_OPTIMIZER)) {
     if ((rc = optimizer_step(e))) return rc;
   }
+  if (e->sharded && (rc = shard_cleanup(e, (flags & CLSR_STEP_NO_OPTIMIZER) != 0))) return rc;
   if ((rc = reset_slots(e))) return rc;
   CK(cudaMemcpyAsync(e->h_losses, e->d_losses, 9 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   if (out) {
@@ -1876,6 +2017,8 @@ int clsr_predict(clsr_engine* e, const clsr_batch* batch, float* pred, float* al
   StepCtx c;
   if ((rc = stage_inputs(e, batch, &c, false))) return rc;
   CK(cudaMemsetAsync(e->counts, 0, 8 * sizeof(int32_t), e->stream));
+  // sharded tables: a collective call -- peers must have finished updating the rows this rank is about to read
+  if (e->sharded && (rc = peer_reduce(e, nullptr, 0, nullptr, 0, nullptr, 0))) return rc;
   if ((rc = forward(e, c, 0, 0))) return rc;
   const int B = c.B;
   sigmoid_kernel<<<grid1d(e, B, 256), 256, 0, e->stream>>>(e->B("logit"), B, e->B("pred"));
@@ -1894,7 +2037,7 @@ int clsr_gather_history(clsr_engine* e, const int32_t* ih, const int32_t* ch, in
   if (!e->tab[0] || !e->tab[1]) return fail(e, CLSR_ERR_STATE, "tables not bound");
   long long nvec = positions * (e->D / 4);
   gather_hist_kernel<4><<<grid1d(e, cdiv(nvec, 4), 256, 8), 256, 0, e->stream>>>(
-      ih, ch, e->T, e->T, e->tab[0], e->tab[1], e->Di, e->Dc, out, positions);
+      ih, ch, e->T, e->T, e->tview[0], e->tview[1], e->Di, e->Dc, out, positions);
   POST("gather_hist");
   return CLSR_OK;
 }
@@ -2032,6 +2175,118 @@ int clsr_profile_entry(clsr_engine* e, int32_t i, char* name, int32_t name_cap, 
   return CLSR_OK;
 }
 
+// ---- peer-memory communication and row-sharded tables ------------------------------------------
+// Blob exchanged between the ranks (through any host channel): a 64-byte header and 13 CUDA IPC handles
+// (communication buffer; per table: values, dense gradient shard, touched marks).
+namespace {
+constexpr int kBlobBytes = 1024;
+constexpr size_t kCommBytes = 2u << 20;   // [data: 2 x world x kPeerSlots doubles | flags at +1 MB]
+struct PeerBlob {
+  int32_t magic, sharded, rank, world;
+  char pad[48];
+  cudaIpcMemHandle_t comm;
+  cudaIpcMemHandle_t tab[CLSR_NUM_TABLES][3];
+};
+static_assert(sizeof(PeerBlob) <= kBlobBytes, "blob size");
+}  // namespace
+
+int clsr_peer_setup_begin(clsr_engine* e, int32_t shard_tables, void* blob_out) {
+  if (!e || !blob_out) return fail(e, CLSR_ERR_ARG, "bad argument");
+  if (e->world <= 1) return fail(e, CLSR_ERR_STATE, "clsr_comm_init first (world > 1)");
+  if (e->comm_data) return fail(e, CLSR_ERR_STATE, "peer communication already set up");
+  if (e->world > kMaxWorld || (e->world & (e->world - 1))) return fail(e, CLSR_ERR_ARG, "world %d: need a power of two <= %d", e->world, kMaxWorld);
+  if ((size_t)2 * e->world * kPeerSlots * 8 > (1u << 20)) return fail(e, CLSR_ERR_ARG, "world too large for the communication buffer");
+  CK(cudaSetDevice(e->cfg.device));
+  char* cb = nullptr;
+  int rc = dalloc(e, &cb, (long long)kCommBytes);
+  if (rc) return rc;
+  e->comm_data = (double*)cb;
+  e->comm_flags = (unsigned long long*)(cb + (1u << 20));
+  PeerBlob b;
+  memset(&b, 0, sizeof b);
+  b.magic = 0x434C5352; b.sharded = shard_tables ? 1 : 0; b.rank = e->rank; b.world = e->world;
+  CK(cudaIpcGetMemHandle(&b.comm, cb));
+  if (shard_tables) {
+    // engine-owned shards: global row r lives on rank r % world at local row r / world
+    for (int t = 0; t < CLSR_NUM_TABLES; ++t) {
+      long long lr = (e->tab_rows[t] - e->rank + e->world - 1) / e->world;
+      if (lr < 1) lr = 1;
+      e->tab_local_rows[t] = lr;
+      const long long n = lr * e->tab_dim[t];
+      if ((rc = dalloc(e, &e->sh_val[t], n)) || (rc = dalloc(e, &e->sh_m[t], n)) || (rc = dalloc(e, &e->sh_v[t], n)) ||
+          (rc = dalloc(e, &e->sh_g[t], n)))
+        return rc;
+      if (t < 3 && (rc = dalloc(e, &e->sh_touched[t], lr))) return rc;
+      if (t == 3) e->sh_touched[3] = e->sh_touched[2];   // the two user tables are indexed by the same ids
+      e->tab[t] = e->sh_val[t]; e->tab_m[t] = e->sh_m[t]; e->tab_v[t] = e->sh_v[t];
+      CK(cudaIpcGetMemHandle(&b.tab[t][0], e->sh_val[t]));
+      CK(cudaIpcGetMemHandle(&b.tab[t][1], e->sh_g[t]));
+      if (t < 3) CK(cudaIpcGetMemHandle(&b.tab[t][2], e->sh_touched[t]));
+    }
+    e->sharded = true;
+  }
+  memset(blob_out, 0, kBlobBytes);
+  memcpy(blob_out, &b, sizeof b);
+  CK(cudaDeviceSynchronize());
+  return CLSR_OK;
+}
+
+int clsr_peer_setup_finish(clsr_engine* e, const void* all_blobs) {
+  if (!e || !all_blobs) return fail(e, CLSR_ERR_ARG, "bad argument");
+  if (!e->comm_data) return fail(e, CLSR_ERR_STATE, "clsr_peer_setup_begin first");
+  if (e->peer_ready) return CLSR_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  int shift = 0;
+  while ((1 << shift) < e->world) ++shift;
+  memset(&e->pc, 0, sizeof e->pc);
+  e->pc.rank = e->rank; e->pc.world = e->world;
+  for (int t = 0; t < CLSR_NUM_TABLES; ++t) {
+    memset(&e->gview[t], 0, sizeof(GradView));
+    if (e->sharded) { memset(&e->tview[t], 0, sizeof(TabView)); e->tview[t].shift = shift; e->tview[t].mask = e->world - 1; }
+    e->gview[t].shift = shift; e->gview[t].mask = e->world - 1;
+  }
+  auto open = [&](const cudaIpcMemHandle_t& h, void** out) -> int {
+    CK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    e->peer_opened.push_back(*out);
+    return 0;
+  };
+  for (int r = 0; r < e->world; ++r) {
+    PeerBlob b;
+    memcpy(&b, (const char*)all_blobs + (size_t)r * kBlobBytes, sizeof b);
+    if (b.magic != 0x434C5352 || b.rank != r || b.world != e->world || b.sharded != (e->sharded ? 1 : 0))
+      return fail(e, CLSR_ERR_ARG, "peer blob %d does not match this group (rank %d world %d sharded %d)", r, b.rank, b.world, b.sharded);
+    void* cb = nullptr;
+    int rc;
+    if (r == e->rank) cb = e->comm_data;
+    else if ((rc = open(b.comm, &cb))) return rc;
+    e->pc.data[r] = (double*)cb;
+    e->pc.flag[r] = (unsigned long long*)((char*)cb + (1u << 20));
+    if (!e->sharded) continue;
+    for (int t = 0; t < CLSR_NUM_TABLES; ++t) {
+      void *pv = e->sh_val[t], *pg = e->sh_g[t], *pt = e->sh_touched[t];
+      if (r != e->rank) {
+        if ((rc = open(b.tab[t][0], &pv)) || (rc = open(b.tab[t][1], &pg))) return rc;
+        if (t < 3) { if ((rc = open(b.tab[t][2], &pt))) return rc; }
+        else pt = e->gview[2].touched[r];
+      }
+      e->tview[t].p[r] = (const float*)pv;
+      e->gview[t].g[r] = (float*)pg;
+      e->gview[t].touched[r] = (int32_t*)pt;
+    }
+  }
+  e->peer_ready = true;
+  return CLSR_OK;
+}
+
+// Local shard of a row-sharded table: which = 0 values, 1 Adam m, 2 Adam v (device pointers, [rows, dim] fp32).
+int clsr_table_local(clsr_engine* e, int32_t t, int32_t which, float** ptr, int64_t* rows) {
+  if (!e || t < 0 || t >= CLSR_NUM_TABLES || which < 0 || which > 2) return fail(e, CLSR_ERR_ARG, "bad argument");
+  if (!e->sharded) return fail(e, CLSR_ERR_STATE, "tables are not sharded");
+  if (ptr) *ptr = which == 0 ? e->sh_val[t] : which == 1 ? e->sh_m[t] : e->sh_v[t];
+  if (rows) *rows = e->tab_local_rows[t];
+  return CLSR_OK;
+}
+
 static void* open_nccl() {
   void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -2073,28 +2328,6 @@ int clsr_comm_init(clsr_engine* e, int32_t rank, int32_t world, const void* id12
   if (r != 0) return fail(e, CLSR_ERR_NCCL, "ncclCommInitRank failed: %s", e->ncclGetErrorString_(r));
   e->world = world;
   e->rank = rank;
-  // staging for the all-gathered sparse-gradient inputs and room for the global unique sets
-  const long long W = world, Bm = e->Bmax, Sm = e->Smax, T = e->T, M = Sm * T;
-  int rc;
-  if ((rc = dalloc(e, &e->l_ih, M)) || (rc = dalloc(e, &e->l_ch, M)) || (rc = dalloc(e, &e->l_users, Sm))) return rc;
-  if ((rc = dalloc(e, &e->g_ih, W * M)) || (rc = dalloc(e, &e->g_ch, W * M)) || (rc = dalloc(e, &e->g_users, W * Sm)) ||
-      (rc = dalloc(e, &e->g_items, W * Bm)) || (rc = dalloc(e, &e->g_cates, W * Bm)))
-    return rc;
-  if ((rc = dalloc(e, &e->g_dX, W * M * e->D)) || (rc = dalloc(e, &e->g_dtgt, W * Bm * e->D)) ||
-      (rc = dalloc(e, &e->g_dul, W * Sm * e->U)) || (rc = dalloc(e, &e->g_dus, W * Sm * e->U)))
-    return rc;
-  const long long rows3[3] = {e->cfg.n_items, e->cfg.n_cates, e->cfg.n_users};
-  const long long want[3] = {W * (M + Bm), W * (M + Bm), W * Sm};
-  for (int i = 0; i < 3; ++i) {
-    long long cap = want[i] < rows3[i] ? want[i] : rows3[i];
-    if (cap > e->uniq_cap[i]) {
-      e->uniq_cap[i] = cap;
-      if ((rc = dalloc(e, &e->uniq[i], cap))) return rc;
-    }
-  }
-  if ((rc = dalloc(e, &e->cg[0], e->uniq_cap[0] * e->Di)) || (rc = dalloc(e, &e->cg[1], e->uniq_cap[1] * e->Dc)) ||
-      (rc = dalloc(e, &e->cg[2], e->uniq_cap[2] * e->U)) || (rc = dalloc(e, &e->cg[3], e->uniq_cap[2] * e->U)))
-    return rc;
   CK(cudaDeviceSynchronize());
   return CLSR_OK;
 }

@@ -5,6 +5,7 @@
 // weight matrices and maps their gradients back onto the TF variables.
 #pragma once
 #include "common.cuh"
+#include "embed.cuh"
 
 namespace clsr {
 
@@ -93,6 +94,62 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stat, int N, d
   ga[n] = -g * r * m1 + g * r * r * m2 * mu;
   dgamma[n] += add_scale * (float)s2;
   dbeta[n] += add_scale * (float)s1;
+}
+
+// Data-parallel forms: the all-reduce of the (sum, sum of squares) / (sum dy, sum dy*xhat) vectors over the ranks
+// happens INSIDE the finalize kernel, over NVLink peer memory (peer_allreduce_block, embed.cuh) -- one launch
+// per BatchNorm layer and direction instead of an NCCL call plus a finalize launch.  `count` is the global row count.
+__global__ void __launch_bounds__(256)
+bn_fwd_finalize_peer_kernel(PeerComm pc, unsigned long long seq, double* __restrict__ stat, int N, double count,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                            float momentum, float* __restrict__ mmean, float* __restrict__ mvar, int update_moving,
+                            float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
+                            float* __restrict__ rstd_o) {
+  __shared__ double vals[kPeerSlots];
+  for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) vals[i] = stat[i];
+  __syncthreads();
+  peer_allreduce_block(pc, seq, vals, 2 * N);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    stat[n] = vals[n]; stat[N + n] = vals[N + n];
+    double m = vals[n] / count;
+    double v = vals[N + n] / count - m * m;
+    if (v < 0.0) v = 0.0;
+    const float mean = (float)m, var = (float)v;
+    if (update_moving) {
+      mmean[n] -= (mmean[n] - mean) * (1.f - momentum);
+      mvar[n] -= (mvar[n] - var) * (1.f - momentum);
+    }
+    float rstd = rsqrtf(var + eps);
+    rstd = rstd * (1.5f - 0.5f * (var + eps) * rstd * rstd);
+    const float sc = rstd * gamma[n];
+    scale[n] = sc;
+    shift[n] = beta[n] - mean * sc;
+    mean_o[n] = mean;
+    rstd_o[n] = rstd;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_peer_kernel(PeerComm pc, unsigned long long seq, double* __restrict__ stat, int N, double count,
+                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                            const float* __restrict__ rstd, float* __restrict__ al, float* __restrict__ be,
+                            float* __restrict__ ga, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                            float add_scale) {
+  __shared__ double vals[kPeerSlots];
+  for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) vals[i] = stat[i];
+  __syncthreads();
+  peer_allreduce_block(pc, seq, vals, 2 * N);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const double s1 = vals[n], s2 = vals[N + n];
+    stat[n] = s1; stat[N + n] = s2;
+    const float m1 = (float)(s1 / count), m2 = (float)(s2 / count);
+    const float g = gamma[n], r = rstd[n], mu = mean[n];
+    al[n] = g * r;
+    be[n] = -g * r * r * m2;
+    ga[n] = -g * r * m1 + g * r * r * m2 * mu;
+    dgamma[n] += add_scale * (float)s2;
+    dbeta[n] += add_scale * (float)s1;
+  }
 }
 
 // ---- output units -------------------------------------------------------------------------------
@@ -345,7 +402,7 @@ struct DenseVar {
 // One CTA per variable: g += l2*w; norms[v] = ||g||^2; acc[10] += 0.5*l2*||w||^2.
 __global__ void dense_l2_norm_kernel(const DenseVar* __restrict__ vars, const float* __restrict__ w,
                                      float* __restrict__ g, float l2, float* __restrict__ norms,
-                                     double* __restrict__ acc) {
+                                     double* __restrict__ acc, double acc_scale) {
   __shared__ float red[2][32];
   const DenseVar v = vars[blockIdx.x];
   float ss = 0.f, ww = 0.f;
@@ -366,7 +423,7 @@ __global__ void dense_l2_norm_kernel(const DenseVar* __restrict__ vars, const fl
     float a = 0.f, b = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; b += red[1][i]; }
     norms[blockIdx.x] = a;
-    if (v.trainable) atomicAdd(acc + 10, 0.5 * (double)l2 * (double)b);
+    if (v.trainable && acc_scale != 0.0) atomicAdd(acc + 10, acc_scale * 0.5 * (double)l2 * (double)b);
   }
 }
 

@@ -61,7 +61,7 @@ EXPORTS = [
     "clsr_shard_create", "clsr_shard_destroy", "clsr_shard_last_error", "clsr_shard_local_rows",
     "clsr_shard_local_values", "clsr_shard_local_grad", "clsr_shard_export", "clsr_shard_attach",
     "clsr_shard_zero_grad", "clsr_shard_gather_history", "clsr_shard_scatter_add_history",
-    "clsr_crc32c", "clsr_clip_report",
+    "clsr_crc32c", "clsr_clip_report", "clsr_peer_setup_begin", "clsr_peer_setup_finish", "clsr_table_local",
 ]
 
 _lib = None
@@ -125,6 +125,9 @@ def load_library(path=None):
         "clsr_shard_scatter_add_history": (C.c_int, [P, P, P, P, I64, P, P]),
         "clsr_crc32c": (U32, [P, C.c_uint64, U32]),
         "clsr_clip_report": (C.c_int, [P, P, C.POINTER(I64)]),
+        "clsr_peer_setup_begin": (C.c_int, [P, I32, P]),
+        "clsr_peer_setup_finish": (C.c_int, [P, P]),
+        "clsr_table_local": (C.c_int, [P, I32, I32, C.POINTER(P), C.POINTER(I64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -180,7 +183,7 @@ class Engine:
                  embed_l2=1e-6, layer_l2=1e-6, contrastive_loss="triplet", triplet_margin=1.0,
                  contrastive_weight=0.1, discrepancy_weight=0.01, contrastive_len_threshold=5,
                  contrastive_recent_k=3, optimizer="adam", learning_rate=1e-3, clip_norm=True,
-                 max_grad_norm=2.0, device=0, math_mode=0, training=True):
+                 max_grad_norm=2.0, device=0, math_mode=0, training=True, alloc_tables=True):
         import torch
         if not torch.cuda.is_available():
             raise EngineError("clsr_b200 needs a CUDA device (no CPU fallback)")
@@ -214,7 +217,11 @@ class Engine:
         self.tables, self.table_m, self.table_v = {}, {}, {}
         shapes = {TABLE_ITEM: (n_items, item_dim), TABLE_CATE: (n_cates, cate_dim),
                   TABLE_USER_LONG: (n_users, user_dim), TABLE_USER_SHORT: (n_users, user_dim)}
+        self._n_rows = {t: s[0] for t, s in shapes.items()}
+        self.sharded, self.world, self.rank = False, 1, 0
         for t, shp in shapes.items():
+            if not alloc_tables:   # tables that only fit row-sharded: comm_init(shard=True) creates the local shards
+                continue
             self.tables[t] = torch.zeros(shp, dtype=torch.float32, device=self.device)
             if training:
                 self.table_m[t] = torch.zeros(shp, dtype=torch.float32, device=self.device)
@@ -283,6 +290,12 @@ class Engine:
         for t, name in TABLE_VARS.items():
             if name in params:
                 src = self.torch.from_numpy(np.ascontiguousarray(params[name], np.float32))
+                if self.sharded:   # full table given: keep this rank's rows
+                    if src.shape[0] != self._n_rows[t]:
+                        raise EngineError("table %s: %d rows != %d" % (name, src.shape[0], self._n_rows[t]))
+                    src = src[self.rank::self.world]
+                    self.tables[t][:src.shape[0]].copy_(src)
+                    continue
                 if tuple(src.shape) != tuple(self.tables[t].shape):
                     raise EngineError("table %s: shape %s != %s" % (name, tuple(src.shape), tuple(self.tables[t].shape)))
                 self.tables[t].copy_(src)
@@ -295,7 +308,7 @@ class Engine:
         out = self.get_dense(0)
         self.synchronize()
         for t, name in TABLE_VARS.items():
-            out[name] = self.tables[t].cpu().numpy()
+            out[name] = self.full_table(t)
         if self.user_table is not None:
             out[EMB + "user_embedding"] = self.user_table
         return out
@@ -351,9 +364,13 @@ class Engine:
                                           alpha.ctypes.data if with_alpha else None))
         return pred, alpha
 
-    def comm_init(self, rank, world, dist=None):
+    def comm_init(self, rank, world, dist=None, shard=True):
         """Join a data-parallel group of ``world`` engines (one process per GPU).  The NCCL unique id is
-        created on rank 0 and broadcast through ``torch.distributed`` (any backend)."""
+        created on rank 0 and broadcast through ``torch.distributed`` (any backend); the CUDA IPC handles of the
+        peer-memory communication buffers (and, with ``shard``, of the row-sharded tables) are all-gathered
+        the same way.  ``shard=True`` (world a power of two): the four tables are row-sharded over the
+        ranks -- rank r keeps global rows r, r + world, ... -- and ``self.tables`` become views of the local shards;
+        whatever the full tables held before the call is kept (each rank keeps its rows)."""
         if world <= 1:
             return
         import torch.distributed as td
@@ -367,6 +384,55 @@ class Engine:
         dist.broadcast_object_list(box, src=0)
         self._check(self.lib.clsr_comm_init(self.h, rank, world, C.create_string_buffer(box[0], 128)))
         self.world, self.rank = world, rank
+        if world & (world - 1):
+            shard = False   # round-robin ownership is mask / shift arithmetic: replicated tables otherwise
+            return
+        blob = C.create_string_buffer(1024)
+        self._check(self.lib.clsr_peer_setup_begin(self.h, 1 if shard else 0, blob))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(blob.raw))
+        self._check(self.lib.clsr_peer_setup_finish(self.h, C.create_string_buffer(b"".join(gathered), 1024 * world)))
+        if shard:
+            self._adopt_shards()
+
+    def _adopt_shards(self):
+        """Replace the full-size torch tables by views of the engine-owned local shards (keeping this rank's rows)."""
+        t = self.torch
+        from .sharded import _DevMem
+        self.sharded = True
+        dims = {TABLE_ITEM: self.cfg.item_dim, TABLE_CATE: self.cfg.cate_dim, TABLE_USER_LONG: self.cfg.user_dim,
+                TABLE_USER_SHORT: self.cfg.user_dim}
+        for tb in dims:
+            dim = dims[tb]
+            views = []
+            for which in range(3):
+                p, n = C.c_void_p(), C.c_int64()
+                self._check(self.lib.clsr_table_local(self.h, tb, which, C.byref(p), C.byref(n)))
+                with t.cuda.device(self.device):
+                    views.append(t.as_tensor(_DevMem(p.value, (n.value, dim)), device=self.device))
+            old = (self.tables.get(tb), self.table_m.get(tb), self.table_v.get(tb))
+            for v, o in zip(views, old):
+                if o is not None:
+                    part = o[self.rank::self.world]
+                    v[:part.shape[0]].copy_(part)
+            self.tables[tb], self.table_m[tb], self.table_v[tb] = views
+        t.cuda.synchronize(self.device)
+
+    def full_table(self, tb, dist=None):
+        """The whole [n_rows, dim] table as a numpy array on every rank (collective in sharded mode; tests / checkpoints)."""
+        if not getattr(self, "sharded", False):
+            return self.tables[tb].cpu().numpy()
+        import torch.distributed as td
+        dist = dist or td
+        self.synchronize()
+        parts = [None] * self.world
+        dist.all_gather_object(parts, self.tables[tb].cpu().numpy())
+        n = self._n_rows[tb]
+        out = np.empty((n, parts[0].shape[1]), np.float32)
+        for r, p in enumerate(parts):
+            rows = len(range(r, n, self.world))
+            out[r::self.world] = p[:rows]
+        return out
 
     def synchronize(self):
         self._check(self.lib.clsr_synchronize(self.h))

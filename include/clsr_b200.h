@@ -143,6 +143,19 @@ int clsr_sparse_grad_view(clsr_engine* e, int32_t table, const int32_t** unique_
 int clsr_nccl_unique_id(void* out128);                        /* 128 bytes */
 int clsr_comm_init(clsr_engine* e, int32_t rank, int32_t world, const void* id128);
 
+/* Peer-memory communication for the data-parallel step (after clsr_comm_init, world a power of two): every
+ * rank exports a blob, the blobs of all ranks (rank-major, CLSR_PEER_BLOB_BYTES each) are exchanged through any
+ * host channel and attached.  From then on the step's small reductions (BatchNorm sums, loss partial sums,
+ * counts, barriers) are one-shot all-reduces over NVLink peer memory inside the consuming kernels.
+ * shard_tables != 0 additionally row-shards the four tables over the ranks (global row r on rank r % world at
+ * local row r / world, engine-owned memory: fill / read the local shard through clsr_table_local): history and
+ * target gathers read straight from the owning GPU, every rank pushes its de-duplicated gradient rows to
+ * their owners (16-byte NVLink reductions), and each owner applies the optimizer to its 1/world of the rows. */
+#define CLSR_PEER_BLOB_BYTES 1024
+int clsr_peer_setup_begin(clsr_engine* e, int32_t shard_tables, void* blob_out);
+int clsr_peer_setup_finish(clsr_engine* e, const void* all_blobs);
+int clsr_table_local(clsr_engine* e, int32_t table, int32_t which, float** dev_ptr, int64_t* rows);
+
 /* ---- row-sharded embedding tables (BASELINE configs 4-5) ------------------
  * For tables that outgrow one GPU: global row r lives on rank r % world at local row r / world.
  * The reference has no counterpart (tf.nn.embedding_lookup on one device,

@@ -31,7 +31,9 @@ def main():
     kw = dict(seq_len=50, train_group=G, optimizer=os.environ.get("OPT", "adam"), device=local)
     eng = Engine(NI, NC, NU, max_rows=per * G, **kw)
     eng.set_params(prm)
-    eng.comm_init(rank, world, dist)
+    shard = os.environ.get("SHARD", "1") == "1"   # row-sharded tables + peer-memory reductions, or replicated tables
+    eng.comm_init(rank, world, dist, shard=shard)
+    assert eng.sharded == shard
     rows = slice(rank * per * G, (rank + 1) * per * G)
     losses = [eng.train_step({k: v[rows] for k, v in f.items()}, group=G) for f in feeds]
     mine = eng.get_params()
@@ -62,7 +64,7 @@ def main():
     spread = float((hi - lo).abs().max())
     if rank == 0:
         print("DP_RESULT " + json.dumps({"ok": ok and spread < 1e-5, "replica_spread": spread, "report": report,
-                                         "last_loss": losses[-1]}))
+                                         "last_loss": losses[-1], "sharded": shard, "world": world}))
     dist.destroy_process_group()
 
 

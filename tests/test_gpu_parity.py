@@ -279,9 +279,12 @@ def test_errors_are_loud(cuda_lib):
         eng.train_step(feed, group=5)                         # 20 rows > max_rows
 
 
-def test_data_parallel_matches_single_gpu(cuda_lib):
-    """2 ranks (one per GPU), NCCL collectives inside the step: same losses and final variables as
-    one GPU on the concatenated batch; replicas agree to rounding (atomic scatter order differs)."""
+@pytest.mark.parametrize("shard,optimizer", [(1, "adam"), (1, "lazyadam"), (0, "adam")])
+def test_data_parallel_matches_single_gpu(cuda_lib, shard, optimizer):
+    """2 ranks (one per GPU): same losses and final variables as one GPU on the concatenated batch.
+    shard=1: row-sharded tables (gathers from the owning GPU, de-duplicated gradient rows pushed to their owners
+    over NVLink, optimizer on the owner's rows) and one-shot peer-memory all-reduces inside the BatchNorm
+    finalize kernels; shard=0: replicated tables, all-gathered sparse gradients."""
     import json
     import os
     import subprocess
@@ -292,8 +295,8 @@ def test_data_parallel_matches_single_gpu(cuda_lib):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29611", os.path.join(root, "tests", "dp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, SHARD=str(shard), OPT=optimizer))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("DP_RESULT ")][-1]
     res = json.loads(line[len("DP_RESULT "):])
-    assert res["ok"], res
+    assert res["ok"] and res["sharded"] == bool(shard), res
