@@ -33,6 +33,11 @@ WORKLOADS = {
     "taobao": dict(T=50, n_items=4_000_000, n_cates=9_400, n_users=1_000_000, time_unit="s", seqs=4096),
     "kuaishou": dict(T=250, n_items=4_000_000, n_cates=9_400, n_users=1_000_000, time_unit="ms", seqs=4096),
     "small": dict(T=50, n_items=64_005, n_cates=2_182, n_users=36_653, time_unit="s", seqs=500),
+    # BASELINE.json configs[3] / configs[4]: tables that only fit row-sharded (device-side initialisation)
+    "synth50m": dict(T=50, n_items=50_000_000, n_cates=9_400, n_users=1_000_000, time_unit="s", seqs=4096,
+                     dims=dict(Di=112, Dc=16, U=128, H=128, A0=80, A1=40, L0=100, L1=64), device_init=True),
+    "synth200m": dict(T=200, n_items=200_000_000, n_cates=9_400, n_users=1_000_000, time_unit="s", seqs=4096,
+                      dims=dict(Di=224, Dc=32, U=256, H=256, A0=80, A1=40, L0=100, L1=64), device_init=True),
 }
 DIMS = dict(Di=32, Dc=8, U=40, H=40, A0=80, A1=40, L0=100, L1=64)
 G = 5  # 1 + train_num_ngs
@@ -53,6 +58,8 @@ def parse():
                     help="CPU arm: sequences per CPU step (500 = BASELINE config 1, the reference's own batch size)")
     ap.add_argument("--math", default="tc", choices=["tc", "simt"],
                     help="tc: large GEMMs on tcgen05 (split-bf16, fp32 accumulate); simt: fp32 CUDA cores everywhere")
+    ap.add_argument("--dp", default="sharded", choices=["sharded", "replicated"],
+                    help="N > 1: row-sharded tables + peer-memory reductions (default) or replicated tables + NCCL all-gathers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-3 (T=250) side measurement and the standalone gather")
     ap.add_argument("--profile-out", default="")
@@ -146,7 +153,7 @@ def ncu_traffic(name):
     return None
 
 
-def kernel_models(S, B, T, w, d=DIMS):
+def kernel_models(S, B, T, w, d=DIMS, shards=1):
     """Algorithmic HBM bytes and FLOPs of one launch of the named kernels (kernel table).
     bytes: every operand read / written once; flops: 2*M*N*K of the contraction (the split-bf16 MMAs issue 3x that)."""
     M, MB = S * T, B * T
@@ -154,6 +161,7 @@ def kernel_models(S, B, T, w, d=DIMS):
     Q, NX = U + D, 3 * U + 9 * H
     rows_state = (w["n_items"] * d["Di"] + w["n_cates"] * d["Dc"] + 2 * w["n_users"] * U) * 4 * 6 + \
                  (w["n_items"] + w["n_cates"] + 2 * w["n_users"]) * 4
+    rows_state //= shards   # row-sharded tables: every rank sweeps its 1/world of the rows
     f4 = 4
     m = {
         "gather_hist": (M * (8 + 2 * D * f4), None),                     # T*8 + 2*T*D*e per sequence
@@ -233,15 +241,26 @@ def measure(a, w, S, optimizer, rank, world, local, dist, steps, warmup, windows
     from clsr_b200 import params as P, synth
     from clsr_b200.engine import Engine, normalize_feed, TABLE_VARS
     B, T = S * G, w["T"]
+    d = w.get("dims", DIMS)
+    dev_init = bool(w.get("device_init"))
     eng = Engine(w["n_items"], w["n_cates"], w["n_users"], max_rows=B, seq_len=T, train_group=G,
-                 optimizer=optimizer, device=local, math_mode=1 if a.math == "tc" else 0)
-    dense = P.init_params(1, 1, 1, seed=42, tables=False)
+                 item_dim=d["Di"], cate_dim=d["Dc"], user_dim=d["U"], hidden=d["H"], att_sizes=(d["A0"], d["A1"]),
+                 layer_sizes=(d["L0"], d["L1"]), optimizer=optimizer, device=local, math_mode=1 if a.math == "tc" else 0,
+                 alloc_tables=not (dev_init and world > 1))
+    dense = P.init_params(1, 1, 1, Di=d["Di"], Dc=d["Dc"], U=d["U"], H=d["H"], att_sizes=(d["A0"], d["A1"]),
+                          layer_sizes=(d["L0"], d["L1"]), seed=42, tables=False)
     eng.set_dense(dense)
-    tabs = make_tables(w, 42)
-    for t, name in TABLE_VARS.items():
-        eng.tables[t].copy_(tabs[name])
+    tabs = None
+    if not dev_init:
+        tabs = make_tables(w, 42, d)
+        for t, name in TABLE_VARS.items():
+            eng.tables[t].copy_(tabs[name])
     if world > 1:
-        eng.comm_init(rank, world, dist)
+        eng.comm_init(rank, world, dist, shard=(a.dp == "sharded"))
+    if dev_init:   # tables too large to stage through the host: truncated-normal(0.01) drawn on the device, per shard
+        gen = torch.Generator(device="cuda").manual_seed(42 + rank)
+        for t in TABLE_VARS:
+            torch.nn.init.trunc_normal_(eng.tables[t], std=0.01, a=-0.02, b=0.02, generator=gen)
     src = synth.SyntheticSource(w["n_items"], w["n_cates"], w["n_users"], T, seed=42 + 1000 * rank,
                                 time_unit=w["time_unit"])
     NB = 4
@@ -295,7 +314,7 @@ def measure(a, w, S, optimizer, rank, world, local, dist, steps, warmup, windows
     # ---- standalone history gather (K1+K3 through clsr_gather_history), zipf and uniform ids ----
     if extras and world == 1:
         res["gather"] = {}
-        D = DIMS["Di"] + DIMS["Dc"]
+        D = d["Di"] + d["Dc"]
         for kind in ("zipf", "uniform"):
             try:
                 if kind == "zipf":   # 32 batches' worth of the workload's windows
@@ -380,11 +399,12 @@ def run_b200(a):
     prof = res["prof"]
     h2d = 5 * S * T * 4 + S * 4 + 3 * B * 4
     hbm_peak, tensor_peak, peak_src = peaks()
+    wd = w.get("dims", DIMS)
     per_kernel = {k: {"ms": v[0] / max(v[1], 1), "calls_per_step": v[1] / a.steps,
                       "share": v[0] / max(sum(x[0] for x in prof.values()), 1e-9)} for k, v in prof.items()}
     step_ms = lambda k: per_kernel[k]["ms"] * per_kernel[k]["calls_per_step"]
     top = max(per_kernel, key=step_ms)
-    models = kernel_models(S, B, T, w)
+    models = kernel_models(S, B, T, w, w.get("dims", DIMS), world if a.dp == "sharded" else 1)
 
     def roof(name):
         k = per_kernel.get(name)
@@ -417,17 +437,20 @@ def run_b200(a):
         if "achieved" in gk:
             gk.update(peak=hbm_peak, frac=gk["achieved"] / hbm_peak, peak_source=peak_src)
     out = {
-        "metric": "user-sequences/sec (CLSR training step, seq_len=%d, emb_dim=40)" % T,
+        "metric": "user-sequences/sec (CLSR training step, seq_len=%d, emb_dim=%d)" % (T, wd["Di"] + wd["Dc"]),
         "value": S * world * a.steps / (ms / 1e3), "unit": "user-sequences/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3 (split-bf16 tcgen05 MMA, fp32 accumulate) + f32" if a.math == "tc" else "f32", "data": "synthetic",
-        "config": {"workload": "Taobao-shaped synthetic: seq_len=%d emb_dim=40 (32+8) batch=%d user-sequences "
+        "config": {"workload": "Taobao-shaped synthetic: seq_len=%d emb_dim=%d (%d+%d) batch=%d user-sequences "
                                "(%d rows) per GPU, %d items / %d cates / %d users, zipf ids, optimizer=%s"
-                               % (T, S, B, w["n_items"], w["n_cates"], w["n_users"], a.optimizer),
+                               % (T, wd["Di"] + wd["Dc"], wd["Di"], wd["Dc"], S, B, w["n_items"], w["n_cates"], w["n_users"], a.optimizer),
                    "l2": "not flushed: each step streams >2 GB of activations and (adam) 5 GB of table state, "
                          "far above the 126 MB L2; 4 distinct batches rotate",
-                   "parallelism": "dp%d" % world},
+                   "parallelism": "dp%d" % world + ("" if world == 1 else
+                                                    (" row-sharded tables (NVLink peer-memory gathers / gradient pushes), peer-memory "
+                                                     "all-reduces in the BatchNorm kernels" if a.dp == "sharded" else
+                                                     " replicated tables, NCCL all-gathered sparse gradients"))},
         "timing": {"windows": len(ms_all), "window_ms": [round(x, 4) for x in ms_all], "reported": "median window",
                    "window_ms_e2e": [round(x, 4) for x in e2e_all], "per_kernel_events": "off in the timed windows"},
         "e2e": {"value": S * world * a.steps / (ms_e2e / 1e3), "unit": "user-sequences/s",
@@ -453,13 +476,13 @@ def run_b200(a):
     if side:
         out["configs"] = side
     try:
-        out["step_roofline"] = step_roofline(T, S * a.steps / (ms / 1e3), hbm_peak, tensor_peak)
+        out["step_roofline"] = step_roofline(T, S * a.steps / (ms / 1e3), hbm_peak, tensor_peak, wd)
     except Exception as ex:  # informational only
         out["step_roofline"] = {"error": str(ex)}
     if a.profile_out:
         with open(a.profile_out, "w") as f:
             json.dump({"per_kernel": per_kernel, "ms_per_step": ms / a.steps}, f, indent=1)
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and tabs is not None:
         out["cpu_baseline"] = cpu_arm(a, w, dense, tabs, steps=8, warmup=2)
     print(json.dumps(out))
     if world > 1:

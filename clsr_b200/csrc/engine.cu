@@ -72,6 +72,7 @@ struct clsr_engine {
   long long launches = 0;
   long long adam_step = 0;
   int num_sms = 148;
+  int rnn_wglob = 0;   // SIMT recurrences read their weights from global memory (they do not fit shared memory)
   int smem_optin = 49152;
   int tc_smem_max = 49152;
   int tc_dw_smem_max = 49152;
@@ -1120,17 +1121,19 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
                                                       e->B("cp"), e->B("mp"), e->B("R"));
       e->launches++;
     } else {
-    size_t smg = (size_t)(U * 2 * U + U * U + 3 * U * RNN_LD) * 4;
+    // shared memory: resident recurrent weights + state tiles, or (wide states) the state tiles only
+    const int wg = e->rnn_wglob;
+    size_t smg = (size_t)((wg ? 0 : U * 2 * U + U * U) + 3 * U * RNN_LD) * 4;
     gru_fwd_kernel<<<nblk, RNN_THREADS, smg, e->aux[0]>>>(PX, NX, e->oG1, e->oC1, us, W("Wgh1"), W("Wch1"), e->d_len, S, T, U,
-                                                       e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"));
+                                                       e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"), wg);
     e->launches++;
-    size_t smg2 = (size_t)(H * 2 * H + H * H + 3 * H * RNN_LD) * 4;
+    size_t smg2 = (size_t)((wg ? 0 : H * 2 * H + H * H) + 3 * H * RNN_LD) * 4;
     gru_fwd_kernel<<<nblk, RNN_THREADS, smg2, e->aux[1]>>>(PX, NX, e->oG2, e->oC2, nullptr, W("Wgh2"), W("Wch2"), e->d_len, S, T, H,
-                                                        e->B("g2"), e->B("c2"), e->B("hp2"), e->B("rh2"), e->B("fs"));
+                                                        e->B("g2"), e->B("c2"), e->B("hp2"), e->B("rh2"), e->B("fs"), wg);
     e->launches++;
-    size_t sml = (size_t)(H * 4 * H + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
+    size_t sml = (size_t)((wg ? 0 : H * 4 * H) + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
     lstm_fwd_kernel<<<nblk, RNN_THREADS, sml, st>>>(PX, NX, e->oL, e->oTN, e->oTL, W("Km"), e->d_len, S, T, H,
-                                                    e->B("G4"), e->B("cp"), e->B("mp"), e->B("R"));
+                                                    e->B("G4"), e->B("cp"), e->B("mp"), e->B("R"), wg);
     e->launches++;
     }
     if ((rc = join_aux(e, "rnn_fwd(gru_sti|gru_causal2|time4lstm)"))) return rc;
@@ -1363,17 +1366,18 @@ int backward(clsr_engine* e, const StepCtx& c) {
                                                             e->B("dfs"), e->d_len, S, T, dPX, NX, e->oG2, e->oC2, nullptr);
       e->launches++;
     } else {
-    size_t sml = (size_t)(H * 4 * H + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
+    const int wg = e->rnn_wglob;
+    size_t sml = (size_t)((wg ? 0 : H * 4 * H) + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
     lstm_bwd_kernel<<<nblk, RNN_THREADS, sml, st>>>(PX, NX, e->oL, e->oTN, e->oTL, e->B("G4"), e->B("cp"), W("KmT"), dR,
-                                                    e->d_len, S, T, H, dPX);
+                                                    e->d_len, S, T, H, dPX, wg);
     e->launches++;
-    size_t smg = (size_t)(2 * U * U + U * U + 5 * U * RNN_LD) * 4;
+    size_t smg = (size_t)((wg ? 0 : 2 * U * U + U * U) + 5 * U * RNN_LD) * 4;
     gru_bwd_kernel<<<nblk, RNN_THREADS, smg, e->aux[0]>>>(e->B("g1"), e->B("c1"), e->B("hp1"), W("Wgh1T"), W("Wch1T"), e->B("dsti"),
-                                                       e->d_len, S, T, U, dPX, NX, e->oG1, e->oC1, e->B("dus"));
+                                                       e->d_len, S, T, U, dPX, NX, e->oG1, e->oC1, e->B("dus"), wg);
     e->launches++;
-    size_t smg2 = (size_t)(2 * H * H + H * H + 5 * H * RNN_LD) * 4;
+    size_t smg2 = (size_t)((wg ? 0 : 2 * H * H + H * H) + 5 * H * RNN_LD) * 4;
     gru_bwd_kernel<<<nblk, RNN_THREADS, smg2, e->aux[1]>>>(e->B("g2"), e->B("c2"), e->B("hp2"), W("Wgh2T"), W("Wch2T"), e->B("dfs"),
-                                                        e->d_len, S, T, H, dPX, NX, e->oG2, e->oC2, nullptr);
+                                                        e->d_len, S, T, H, dPX, NX, e->oG2, e->oC2, nullptr, wg);
     e->launches++;
     }
     if ((rc = join_aux(e, "rnn_bwd(time4lstm|gru_sti|gru_causal2)"))) return rc;
@@ -1740,14 +1744,15 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
   e->tab_dim[0] = e->Di; e->tab_dim[1] = e->Dc; e->tab_dim[2] = U; e->tab_dim[3] = U;
 
   {
+    const int UH = U > H ? U : H;
     size_t sml = (size_t)(H * 4 * H + 6 * H * RNN_LD) * 4;
-    size_t smg = (size_t)(3 * (U > H ? U : H) * (U > H ? U : H) + 5 * (U > H ? U : H) * RNN_LD) * 4;
+    size_t smg = (size_t)(3 * UH * UH + 5 * UH * RNN_LD) * 4;
     size_t smax = sml > smg ? sml : smg;
     if (smax > (size_t)prop.sharedMemPerBlockOptin) {
-      fail(nullptr, CLSR_ERR_ARG, "hidden size %d needs %zu B of shared memory for resident recurrent weights (max %zu)",
-           H, smax, (size_t)prop.sharedMemPerBlockOptin);
-      clsr_destroy(e);
-      return CLSR_ERR_ARG;
+      // wide states (BASELINE configs 4-5): the recurrent weights stay in global memory (L1 / L2 resident)
+      e->rnn_wglob = 1;
+      sml = (size_t)(6 * H * RNN_LD) * 4;
+      smg = (size_t)(5 * UH * RNN_LD) * 4;
     }
     CKCU(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml));
     CKCU(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml));

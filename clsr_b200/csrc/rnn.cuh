@@ -47,19 +47,23 @@ gru_fwd_kernel(const float* __restrict__ PX, int ldpx, int colg, int colc,
                const float* __restrict__ h0, const float* __restrict__ Wgh, const float* __restrict__ Wch,
                const int* __restrict__ len, int S, int T, int U, float* __restrict__ gates,
                float* __restrict__ cand, float* __restrict__ hprev, float* __restrict__ rh,
-               float* __restrict__ hfinal) {
+               float* __restrict__ hfinal, int wglob) {
+  // wglob: the recurrent weights do not fit shared memory next to the state tiles (wide states, BASELINE
+  // configs 4-5): they are read from global memory instead (identical for every CTA and step: L1 / L2 resident)
   extern __shared__ __align__(16) float sm[];
-  float* sWg = sm;                    // [U][2U]
-  float* sWc = sWg + U * 2 * U;       // [U][U]
-  float* hT = sWc + U * U;            // [U][LD]
+  const float* sWg = wglob ? Wgh : sm;                    // [U][2U]
+  const float* sWc = wglob ? Wch : sm + U * 2 * U;        // [U][U]
+  float* hT = wglob ? sm : sm + U * 2 * U + U * U;        // [U][LD]
   float* rhT = hT + U * RNN_LD;
   float* uT = rhT + U * RNN_LD;
   __shared__ int slen[RNN_NSEQ];
   const int tid = threadIdx.x;
   const int s0 = blockIdx.x * RNN_NSEQ;
   const int U2 = 2 * U;
-  for (int i = tid; i < U * U2; i += RNN_THREADS) sWg[i] = Wgh[i];
-  for (int i = tid; i < U * U; i += RNN_THREADS) sWc[i] = Wch[i];
+  if (!wglob) {
+    for (int i = tid; i < U * U2; i += RNN_THREADS) sm[i] = Wgh[i];
+    for (int i = tid; i < U * U; i += RNN_THREADS) sm[U * U2 + i] = Wch[i];
+  }
   for (int i = tid; i < U * RNN_NSEQ; i += RNN_THREADS) {
     int q = i / U, k = i % U;
     int s = s0 + q;
@@ -149,20 +153,22 @@ gru_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ cand,
                const float* __restrict__ hprev, const float* __restrict__ WghT,
                const float* __restrict__ WchT, const float* __restrict__ dh_final,
                const int* __restrict__ len, int S, int T, int U, float* __restrict__ dPX, int ldpx, int colg,
-               int colc, float* __restrict__ dh0) {
+               int colc, float* __restrict__ dh0, int wglob) {
   extern __shared__ __align__(16) float sm[];
   const int U2 = 2 * U;
-  float* sWgT = sm;                    // [2U][U]
-  float* sWcT = sWgT + U2 * U;         // [U][U]
-  float* dhT = sWcT + U * U;           // [U][LD]
+  const float* sWgT = wglob ? WghT : sm;                  // [2U][U]
+  const float* sWcT = wglob ? WchT : sm + U2 * U;         // [U][U]
+  float* dhT = wglob ? sm : sm + U2 * U + U * U;          // [U][LD]
   float* dhaT = dhT + U * RNN_LD;      // [U][LD]
   float* dpcT = dhaT + U * RNN_LD;     // [U][LD]
   float* dpgT = dpcT + U * RNN_LD;     // [2U][LD]
   __shared__ int slen[RNN_NSEQ];
   const int tid = threadIdx.x;
   const int s0 = blockIdx.x * RNN_NSEQ;
-  for (int i = tid; i < U2 * U; i += RNN_THREADS) sWgT[i] = WghT[i];
-  for (int i = tid; i < U * U; i += RNN_THREADS) sWcT[i] = WchT[i];
+  if (!wglob) {
+    for (int i = tid; i < U2 * U; i += RNN_THREADS) sm[i] = WghT[i];
+    for (int i = tid; i < U * U; i += RNN_THREADS) sm[U2 * U + i] = WchT[i];
+  }
   for (int i = tid; i < U * RNN_NSEQ; i += RNN_THREADS) {
     int q = i / U, k = i % U;
     int s = s0 + q;
@@ -258,17 +264,18 @@ __global__ void __launch_bounds__(RNN_THREADS)
 lstm_fwd_kernel(const float* __restrict__ PX, int ldpx, int colL, int colTN, int colTL,
                 const float* __restrict__ Km, const int* __restrict__ len, int S, int T, int H,
                 float* __restrict__ gates4, float* __restrict__ cprev, float* __restrict__ mprev,
-                float* __restrict__ R) {
+                float* __restrict__ R, int wglob) {
   extern __shared__ __align__(16) float sm[];
   const int H4 = 4 * H;
-  float* sK = sm;                      // [H][4H]
-  float* mT = sK + H * H4;             // [H][LD]
+  const float* sK = wglob ? Km : sm;           // [H][4H]
+  float* mT = wglob ? sm : sm + H * H4;        // [H][LD]
   float* cT = mT + H * RNN_LD;         // [H][LD]
   float* preT = cT + H * RNN_LD;       // [4H][LD]
   __shared__ int slen[RNN_NSEQ];
   const int tid = threadIdx.x;
   const int s0 = blockIdx.x * RNN_NSEQ;
-  for (int i = tid; i < H * H4; i += RNN_THREADS) sK[i] = Km[i];
+  if (!wglob)
+    for (int i = tid; i < H * H4; i += RNN_THREADS) sm[i] = Km[i];
   for (int i = tid; i < H * RNN_LD; i += RNN_THREADS) { mT[i] = 0.f; cT[i] = 0.f; }
   const int tmax = rnn_setup_len(len, s0, S, slen);
   const int nt1 = (RNN_NSEQ / 4) * H4;
@@ -333,17 +340,18 @@ __global__ void __launch_bounds__(RNN_THREADS)
 lstm_bwd_kernel(const float* __restrict__ PX, int ldpx, int colL, int colTN, int colTL,
                 const float* __restrict__ gates4, const float* __restrict__ cprev,
                 const float* __restrict__ KmT, const float* __restrict__ dR, const int* __restrict__ len,
-                int S, int T, int H, float* __restrict__ dPX) {
+                int S, int T, int H, float* __restrict__ dPX, int wglob) {
   extern __shared__ __align__(16) float sm[];
   const int H4 = 4 * H;
-  float* sKT = sm;                     // [4H][H]
-  float* dmT = sKT + H4 * H;           // [H][LD]
+  const float* sKT = wglob ? KmT : sm;         // [4H][H]
+  float* dmT = wglob ? sm : sm + H4 * H;       // [H][LD]
   float* dcT = dmT + H * RNN_LD;       // [H][LD]
   float* dpT = dcT + H * RNN_LD;       // [4H][LD]
   __shared__ int slen[RNN_NSEQ];
   const int tid = threadIdx.x;
   const int s0 = blockIdx.x * RNN_NSEQ;
-  for (int i = tid; i < H4 * H; i += RNN_THREADS) sKT[i] = KmT[i];
+  if (!wglob)
+    for (int i = tid; i < H4 * H; i += RNN_THREADS) sm[i] = KmT[i];
   for (int i = tid; i < H * RNN_LD; i += RNN_THREADS) { dmT[i] = 0.f; dcT[i] = 0.f; }
   const int tmax = rnn_setup_len(len, s0, S, slen);
   const int ntm = (RNN_NSEQ / 4) * H;

@@ -10,14 +10,18 @@ RETAIN = ["logit", "afl", "afs", "hist_mean", "hist_recent", "sti", "fs", "rnn_o
 
 
 def small_problem(S=24, G=5, T=50, seed=3, n_items=3000, n_cates=40, n_users=200, init_scale=8.0,
-                  edge_lengths=True):
+                  edge_lengths=True, dims=None):
+    """dims: (item_dim, cate_dim, user_dim = hidden) for the wide configurations (BASELINE configs 4-5)."""
     src = synth.SyntheticSource(n_items=n_items, n_cates=n_cates, n_users=n_users, T=T, seed=seed)
     feed = src.batch(S, G - 1) if G > 1 else src.batch(S, 0)
     if G == 1:
         lab = np.zeros((S, 1), np.float32)
         lab[::5] = 1.0
         feed["labels"] = lab
-    prm = P.init_params(n_items, n_cates, n_users, seed=seed)
+    if dims:
+        prm = P.init_params(n_items, n_cates, n_users, Di=dims[0], Dc=dims[1], U=dims[2], H=dims[2], seed=seed)
+    else:
+        prm = P.init_params(n_items, n_cates, n_users, seed=seed)
     return feed, scale_params(prm, seed, init_scale)
 
 
@@ -116,7 +120,9 @@ def compare_step(eng, feed, prm, G, group, shapes_only=False, metric=None, dtype
     from clsr_b200.engine import STEP_NO_OPTIMIZER, STEP_NO_BN_UPDATE
     B = feed["users"].shape[0]
     T = feed["mask"].shape[1]
-    cfg = oracle_config(G, max_seq_length=T)
+    c = eng.cfg
+    cfg = oracle_config(G, max_seq_length=T, item_embedding_dim=c.item_dim, cate_embedding_dim=c.cate_dim,
+                        user_embedding_dim=c.user_dim, hidden_size=c.hidden)
     dtype = dtype or torch.float64
     S = B // group
     c = eng.cfg

@@ -72,6 +72,27 @@ def _check_tc(res, max_flip_frac=1e-4):
     assert not bad, (bad, flips)
 
 
+@pytest.mark.parametrize("dims,math_mode", [((112, 16, 128), 0), ((112, 16, 128), 1), ((224, 32, 256), 1)])
+def test_wide_model_matches_oracle(cuda_lib, dims, math_mode):
+    """BASELINE configs 4 / 5 widths (emb_dim 128 = 112 + 16, 256 = 224 + 32; hidden = user_dim = emb_dim): the
+    graph is dimension-generic (clsr.py:137-277); here the recurrences run with their weights in global memory
+    and the K > 160 / N > 240 GEMMs take the slab / fp32 paths."""
+    G, S, T = 5, 56, 20
+    init_scale = 8.0 * (40.0 / (dims[0] + dims[1])) ** 0.5   # keep pre-activations O(1) at the wider fan-in
+    feed, prm = PU.small_problem(S=S, G=G, T=T, seed=41, dims=dims, init_scale=init_scale)
+    feed = PU.set_lengths(feed, [1, T, 3, 5, 6, 2], G)
+    eng = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, T=T, G=G, item_dim=dims[0], cate_dim=dims[1],
+                         user_dim=dims[2], hidden=dims[2], math_mode=math_mode)
+    eng.set_debug_sync(True)
+    if math_mode:
+        res, _ = PU.compare_step(eng, feed, prm, G, G, metric=PU.relerr_l2, mask_flips=True)
+        _check_tc(res)
+    else:
+        res, _ = PU.compare_step(eng, feed, prm, G, G)
+        _check(res)
+    assert res["fwd/X"] == 0.0 and res["fwd/tgt"] == 0.0
+
+
 def test_bpr_contrastive_loss(cuda_lib):
     """contrastive_loss='bpr' (clsr.py:53-57), the create_hparams default."""
     import torch
