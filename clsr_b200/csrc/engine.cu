@@ -660,8 +660,11 @@ int tc_gemm(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a,
   for (int n0 = 0; n0 < N; n0 += 240) {          // column slabs (one UMMA is at most 256 wide)
     int nn = N - n0 < 240 ? N - n0 : 240;
     if (N <= 256) nn = N;
-    for (int k0 = 0; k0 < K; k0 += 160) {        // K slabs accumulate through the epilogue
-      int kk = K - k0 < 160 ? K - k0 : 160;
+    // K slabs accumulate through the epilogue; wide outputs take 128-deep slabs so that W (K x N, split) and one
+    // operand stage still fit shared memory
+    const int ksl = (K > 160 && nn > 128) ? 128 : 160;
+    for (int k0 = 0; k0 < K; k0 += ksl) {
+      int kk = K - k0 < ksl ? K - k0 : ksl;
       AOp a2 = a;
       EpiOp p2 = ep;
       // later K slabs accumulate onto C: bias / broadcast terms were added by the first slab
@@ -671,7 +674,7 @@ int tc_gemm(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a,
       // column statistics are those of the finished sum: only the last K slab accumulates them (counting every
       // slab's partial result put the sums of BOTH partial and final values into the alpha gate's first
       // BatchNorm whenever its K = 2H+2D+1 = 161 > 160 input took this path, i.e. for >= 1024 rows)
-      const bool last_k = k0 + 160 >= K;
+      const bool last_k = k0 + ksl >= K;
       if ((rc = tc_gemm_one(e, name, M, nn, kk, a2, W + (size_t)k0 * ldw + n0, ldw, p2, stats && last_k))) return rc;
     }
     if (N <= 256) break;
