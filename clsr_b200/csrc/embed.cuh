@@ -437,20 +437,26 @@ __global__ void shard_involved_kernel(const float* __restrict__ tab, const float
   const int wpb = blockDim.x >> 5;
   float ss = 0.f, rr = 0.f, dd = 0.f;
   const float dcoef = other ? -2.0f * disc_w / ((float)(*n_uniq) * (float)dim) : 0.f;
-  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
-    if (!touched[r]) continue;
-    const size_t row = (size_t)r * dim;
-    for (int k = lane; k < dim; k += 32) {
-      float x = tab[row + k];
-      float v = l2 * x;
-      rr += x * x;
-      if (other) {
-        float df = x - other[row + k];
-        v += dcoef * df;
-        dd += df * df;
+  // a warp scans 32 consecutive marks with one coalesced load and then walks the touched rows among them
+  for (long long r0 = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * 32; r0 < rows; r0 += (long long)gridDim.x * wpb * 32) {
+    const long long rl = r0 + lane;
+    unsigned m = __ballot_sync(0xffffffffu, rl < rows && touched[rl] != 0);
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const size_t row = (size_t)(r0 + b) * dim;
+      for (int k = lane; k < dim; k += 32) {
+        float x = tab[row + k];
+        float v = l2 * x;
+        rr += x * x;
+        if (other) {
+          float df = x - other[row + k];
+          v += dcoef * df;
+          dd += df * df;
+        }
+        g[row + k] += v;
+        ss += v * v;
       }
-      g[row + k] += v;
-      ss += v * v;
     }
   }
   ss = warp_sum(ss); rr = warp_sum(rr); dd = warp_sum(dd);
@@ -523,17 +529,22 @@ __global__ void adam_lazy_shard_kernel(float* __restrict__ var, float* __restric
     scale = hp.clip / fmaxf(nrm, hp.clip);
   }
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
-    if (!touched[r]) continue;
-    const size_t row = (size_t)r * dim;
-    for (int k = lane; k < dim; k += 32) {
-      const float gv = g[row + k] * scale;
-      g[row + k] = 0.f;
-      if (apply) {
-        const float mv = hp.beta1 * m[row + k] + (1.f - hp.beta1) * gv;
-        const float vv = hp.beta2 * v[row + k] + (1.f - hp.beta2) * gv * gv;
-        m[row + k] = mv; v[row + k] = vv;
-        var[row + k] -= hp.lr_t * mv / (sqrtf(vv) + hp.eps);
+  for (long long r0 = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * 32; r0 < rows; r0 += (long long)gridDim.x * wpb * 32) {
+    const long long rl = r0 + lane;
+    unsigned msk = __ballot_sync(0xffffffffu, rl < rows && touched[rl] != 0);
+    while (msk) {
+      const int b = __ffs(msk) - 1;
+      msk &= msk - 1;
+      const size_t row = (size_t)(r0 + b) * dim;
+      for (int k = lane; k < dim; k += 32) {
+        const float gv = g[row + k] * scale;
+        g[row + k] = 0.f;
+        if (apply) {
+          const float mv = hp.beta1 * m[row + k] + (1.f - hp.beta1) * gv;
+          const float vv = hp.beta2 * v[row + k] + (1.f - hp.beta2) * gv * gv;
+          m[row + k] = mv; v[row + k] = vv;
+          var[row + k] -= hp.lr_t * mv / (sqrtf(vv) + hp.eps);
+        }
       }
     }
   }
