@@ -129,6 +129,7 @@ struct clsr_engine {
   size_t h_stage_bytes = 0;
   cudaEvent_t h2d_done = nullptr;  // the staging buffer may be rewritten once this has fired
   float* h_out = nullptr;  // pinned [2*Bmax]
+  int staged_S = 0, staged_G = 1;   // shape of the batch clsr_build_batch left in the staged-feed block
   int32_t* d_err = nullptr;   // [1] id-range flags of the last device-resident feed (stage_device_feed_kernel)
   int32_t* h_err = nullptr;   // pinned mirror, copied after every step
 
@@ -1964,6 +1965,8 @@ int clsr_synchronize(clsr_engine* e) {
   return check_feed_flags(e);
 }
 
+static int train_after_stage(clsr_engine* e, const StepCtx& c, uint32_t flags, clsr_losses* out);
+
 int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, clsr_losses* out) {
   if (!e) return CLSR_ERR_ARG;
   int rc;
@@ -1974,6 +1977,12 @@ int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, cls
   MARK("(step begin)");
   if ((rc = stage_inputs(e, batch, &c, true))) return rc;
   MARK("h2d_inputs");
+  return train_after_stage(e, c, flags, out);
+}
+
+// Everything after the feed is staged (by stage_inputs or by clsr_build_batch).
+static int train_after_stage(clsr_engine* e, const StepCtx& c, uint32_t flags, clsr_losses* out) {
+  int rc;
   if ((rc = zero_step_state(e))) return rc;
   // sharded tables: peers must have finished the previous step's optimizer (and its touched / gradient clean-up)
   // before this step's gathers read their rows or its pushes mark them
@@ -2015,28 +2024,259 @@ int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, cls
   return CLSR_OK;
 }
 
-int clsr_predict(clsr_engine* e, const clsr_batch* batch, float* pred, float* alpha) {
-  if (!e) return CLSR_ERR_ARG;
+// Inference forward on the staged feed; leaves sigmoid(logit) in the "pred" buffer and alpha in "alpha".
+static int predict_forward(clsr_engine* e, const clsr_batch* batch, StepCtx* c) {
   int rc;
   CK(cudaSetDevice(e->cfg.device));
   if ((rc = check_batch(e, batch, false))) return rc;
-  if (!pred) return fail(e, CLSR_ERR_ARG, "null pred buffer");
   e->launches = 0;
-  StepCtx c;
-  if ((rc = stage_inputs(e, batch, &c, false))) return rc;
+  if ((rc = stage_inputs(e, batch, c, false))) return rc;
   CK(cudaMemsetAsync(e->counts, 0, 8 * sizeof(int32_t), e->stream));
   // sharded tables: a collective call -- peers must have finished updating the rows this rank is about to read
   if (e->sharded && (rc = peer_reduce(e, nullptr, 0, nullptr, 0, nullptr, 0))) return rc;
-  if ((rc = forward(e, c, 0, 0))) return rc;
-  const int B = c.B;
-  sigmoid_kernel<<<grid1d(e, B, 256), 256, 0, e->stream>>>(e->B("logit"), B, e->B("pred"));
+  if ((rc = forward(e, *c, 0, 0))) return rc;
+  sigmoid_kernel<<<grid1d(e, c->B, 256), 256, 0, e->stream>>>(e->B("logit"), c->B, e->B("pred"));
   POST("sigmoid");
+  return 0;
+}
+
+int clsr_predict(clsr_engine* e, const clsr_batch* batch, float* pred, float* alpha) {
+  if (!e) return CLSR_ERR_ARG;
+  if (!pred) return fail(e, CLSR_ERR_ARG, "null pred buffer");
+  int rc;
+  StepCtx c;
+  if ((rc = predict_forward(e, batch, &c))) return rc;
+  const int B = c.B;
   CK(cudaMemcpyAsync(e->h_out, e->B("pred"), (size_t)B * 4, cudaMemcpyDeviceToHost, e->stream));
   if (alpha) CK(cudaMemcpyAsync(e->h_out + e->Bmax, e->B("alpha"), (size_t)B * 4, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   if ((rc = check_feed_flags(e))) return rc;
   memcpy(pred, e->h_out, (size_t)B * 4);
   if (alpha) memcpy(alpha, e->h_out + e->Bmax, (size_t)B * 4);
+  return CLSR_OK;
+}
+
+int clsr_predict_device(clsr_engine* e, const clsr_batch* batch, float* dev_pred, float* dev_alpha) {
+  if (!e) return CLSR_ERR_ARG;
+  if (!dev_pred) return fail(e, CLSR_ERR_ARG, "null pred buffer");
+  int rc;
+  StepCtx c;
+  if ((rc = predict_forward(e, batch, &c))) return rc;
+  CK(cudaMemcpyAsync(dev_pred, e->B("pred"), (size_t)c.B * 4, cudaMemcpyDeviceToDevice, e->stream));
+  if (dev_alpha) CK(cudaMemcpyAsync(dev_alpha, e->B("alpha"), (size_t)c.B * 4, cudaMemcpyDeviceToDevice, e->stream));
+  return CLSR_OK;
+}
+
+// ---- batch construction on the GPU --------------------------------------------------------
+// Reference: SASequentialIterator._convert_data (sequential_iterator.py:519-704) pads, replicates x(1+num_ngs)
+// and samples in-batch negatives row by row in Python between two sess.run calls.  Here a parsed file is uploaded
+// once as columnar device arrays and a batch is built by one kernel straight into the staged-feed block the step
+// reads; the host only sends the line indices of the batch.
+struct clsr_dataset {
+  int device = 0, T = 0;
+  long long n = 0;
+  float *label = nullptr, *tfa = nullptr, *ttn = nullptr;
+  int32_t *user = nullptr, *item = nullptr, *cate = nullptr, *length = nullptr, *ih = nullptr, *ch = nullptr;
+  int32_t* lines = nullptr;   // device copy of the current batch's line indices
+  long long lines_cap = 0;
+};
+
+namespace {
+
+// staged-block pointers for S sequences / B rows (same layout as stage_inputs)
+void staged_ctx(clsr_engine* e, int S, int G, StepCtx* c) {
+  const int T = e->T, B = S * G;
+  const size_t seq_i = (size_t)S * T * 4;
+  c->B = B; c->G = G; c->S = S; c->T = T;
+  char* d = (char*)e->in_ih;
+  c->ih = (const int32_t*)d; d += seq_i;
+  c->ch = (const int32_t*)d; d += seq_i;
+  c->mask = (const int32_t*)d; d += seq_i;
+  c->tfa = (const float*)d; d += seq_i;
+  c->ttn = (const float*)d; d += seq_i;
+  c->users = (const int32_t*)d; d += (size_t)S * 4;
+  c->items = (const int32_t*)d; d += (size_t)B * 4;
+  c->cates = (const int32_t*)d; d += (size_t)B * 4;
+  c->labels = (const float*)d;
+  c->seq_stride = T;
+  c->user_stride = 1;
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {   // splitmix64 finaliser
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void build_batch_kernel(const float* __restrict__ dl, const int32_t* __restrict__ du, const int32_t* __restrict__ di,
+                                   const int32_t* __restrict__ dc, const int32_t* __restrict__ dlen,
+                                   const int32_t* __restrict__ dih, const int32_t* __restrict__ dch,
+                                   const float* __restrict__ dtfa, const float* __restrict__ dttn,
+                                   const int32_t* __restrict__ lines, int S, int G, int T, unsigned long long seed,
+                                   int32_t* __restrict__ o_ih, int32_t* __restrict__ o_ch, int32_t* __restrict__ o_mask,
+                                   float* __restrict__ o_tfa, float* __restrict__ o_ttn, int32_t* __restrict__ o_users,
+                                   int32_t* __restrict__ o_items, int32_t* __restrict__ o_cates, float* __restrict__ o_labels) {
+  const long long M = (long long)S * T, B = (long long)S * G;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
+    const int s = (int)(i / T), t = (int)(i - (long long)s * T);
+    const size_t src = (size_t)lines[s] * T + t;
+    o_ih[i] = dih[src]; o_ch[i] = dch[src]; o_tfa[i] = dtfa[src]; o_ttn[i] = dttn[src];
+    o_mask[i] = t < dlen[lines[s]] ? 1 : 0;
+  }
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+    const int s = (int)(b / G), g = (int)(b - (long long)s * G);
+    const int line = lines[s];
+    if (g == 0) {
+      o_users[s] = du[line];
+      o_items[b] = di[line]; o_cates[b] = dc[line];
+      o_labels[b] = G > 1 ? 1.0f : dl[line];
+    } else {
+      // a negative = the positive item of another line of this batch, never this line's own item
+      // (sequential_iterator.py:612-634: random.randint until it differs); counter-based draws
+      const int own = di[line];
+      int pick = -1;
+      for (int k = 0; k < 64 && pick < 0; ++k) {
+        const int j = (int)(mix64(seed ^ ((unsigned long long)b << 8) ^ (unsigned long long)k) % (unsigned long long)S);
+        if (di[lines[j]] != own) pick = j;
+      }
+      for (int j = 0; j < S && pick < 0; ++j)   // 64 misses: the batch is dominated by one item; scan for any other
+        if (di[lines[(s + 1 + j) % S]] != own) pick = (s + 1 + j) % S;
+      if (pick < 0) pick = s;                   // every line has the same item (the reference would not terminate)
+      o_items[b] = di[lines[pick]]; o_cates[b] = dc[lines[pick]];
+      o_labels[b] = 0.0f;
+    }
+  }
+}
+
+}  // namespace
+
+int clsr_dataset_create(clsr_engine* e, int64_t n_lines, const float* label, const int32_t* user, const int32_t* item,
+                        const int32_t* cate, const int32_t* length, const int32_t* item_hist, const int32_t* cate_hist,
+                        const float* tfa, const float* ttn, clsr_dataset** out) {
+  if (!e || !out || n_lines <= 0 || !label || !user || !item || !cate || !length || !item_hist || !cate_hist || !tfa || !ttn)
+    return fail(e, CLSR_ERR_ARG, "bad argument");
+  *out = nullptr;
+  const int T = e->T;
+  // ids are validated once, here: batches built from the cache need no per-step check
+  auto bad = [](const int32_t* p, size_t n, long long limit) {
+    uint32_t mx = 0;
+    for (size_t i = 0; i < n; ++i) { const uint32_t v = (uint32_t)p[i]; mx = v > mx ? v : mx; }
+    return (long long)mx >= limit;
+  };
+  if (bad(user, n_lines, e->cfg.n_users) || bad(item, n_lines, e->cfg.n_items) || bad(cate, n_lines, e->cfg.n_cates) ||
+      bad(item_hist, (size_t)n_lines * T, e->cfg.n_items) || bad(cate_hist, (size_t)n_lines * T, e->cfg.n_cates))
+    return fail(e, CLSR_ERR_ARG, "dataset holds an id outside its table");
+  for (int64_t i = 0; i < n_lines; ++i)
+    if (length[i] < 0 || length[i] > T) return fail(e, CLSR_ERR_ARG, "history length outside [0, %d]", T);
+  CK(cudaSetDevice(e->cfg.device));
+  clsr_dataset* d = new clsr_dataset();
+  d->device = e->cfg.device; d->T = T; d->n = n_lines;
+  const size_t n = (size_t)n_lines, nt = n * T;
+  struct { void** p; const void* src; size_t bytes; } cols[] = {
+      {(void**)&d->label, label, n * 4}, {(void**)&d->user, user, n * 4}, {(void**)&d->item, item, n * 4},
+      {(void**)&d->cate, cate, n * 4}, {(void**)&d->length, length, n * 4}, {(void**)&d->ih, item_hist, nt * 4},
+      {(void**)&d->ch, cate_hist, nt * 4}, {(void**)&d->tfa, tfa, nt * 4}, {(void**)&d->ttn, ttn, nt * 4}};
+  for (auto& c : cols) {
+    cudaError_t err = cudaMalloc(c.p, c.bytes);
+    if (err == cudaSuccess) err = cudaMemcpy(*c.p, c.src, c.bytes, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+      clsr_dataset_destroy(d);
+      return fail(e, CLSR_ERR_CUDA, "dataset upload failed: %s", cudaGetErrorString(err));
+    }
+  }
+  *out = d;
+  return CLSR_OK;
+}
+
+void clsr_dataset_destroy(clsr_dataset* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  void* ps[] = {d->label, d->user, d->item, d->cate, d->length, d->ih, d->ch, d->tfa, d->ttn, d->lines};
+  for (void* p : ps)
+    if (p) cudaFree(p);
+  delete d;
+}
+
+int clsr_build_batch(clsr_engine* e, clsr_dataset* d, const int32_t* host_lines, int32_t count, int32_t num_ngs, uint64_t seed) {
+  if (!e || !d || !host_lines || count <= 0 || num_ngs < 0) return fail(e, CLSR_ERR_ARG, "bad argument");
+  const int G = num_ngs + 1, S = count;
+  if ((long long)S * G > e->Bmax) return fail(e, CLSR_ERR_ARG, "rows %lld exceed max_rows %d", (long long)S * G, e->Bmax);
+  if (d->T != e->T || d->device != e->cfg.device) return fail(e, CLSR_ERR_ARG, "dataset belongs to another engine shape / device");
+  for (int i = 0; i < count; ++i)
+    if (host_lines[i] < 0 || host_lines[i] >= d->n) return fail(e, CLSR_ERR_ARG, "line index %d outside the dataset", host_lines[i]);
+  CK(cudaSetDevice(e->cfg.device));
+  if (d->lines_cap < count) {
+    if (d->lines) CK(cudaFree(d->lines));
+    d->lines = nullptr;
+    CK(cudaMalloc((void**)&d->lines, (size_t)e->Bmax * 4));
+    d->lines_cap = e->Bmax;
+  }
+  CK(cudaEventSynchronize(e->h2d_done));
+  memcpy(e->h_stage, host_lines, (size_t)count * 4);
+  CK(cudaMemcpyAsync(d->lines, e->h_stage, (size_t)count * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaEventRecord(e->h2d_done, e->stream));
+  StepCtx c;
+  staged_ctx(e, S, G, &c);
+  build_batch_kernel<<<grid1d(e, (long long)S * e->T, 256, 4), 256, 0, e->stream>>>(
+      d->label, d->user, d->item, d->cate, d->length, d->ih, d->ch, d->tfa, d->ttn, d->lines, S, G, e->T, seed,
+      const_cast<int32_t*>(c.ih), const_cast<int32_t*>(c.ch), const_cast<int32_t*>(c.mask), const_cast<float*>(c.tfa),
+      const_cast<float*>(c.ttn), const_cast<int32_t*>(c.users), const_cast<int32_t*>(c.items), const_cast<int32_t*>(c.cates),
+      const_cast<float*>(c.labels));
+  POST("build_batch");
+  e->staged_S = S; e->staged_G = G;
+  return CLSR_OK;
+}
+
+int clsr_train_step_staged(clsr_engine* e, uint32_t flags, clsr_losses* out) {
+  if (!e) return CLSR_ERR_ARG;
+  if (e->staged_S <= 0) return fail(e, CLSR_ERR_STATE, "no staged batch (clsr_build_batch)");
+  if ((e->staged_S * e->staged_G) % e->cfg.train_group) return fail(e, CLSR_ERR_ARG, "rows not a multiple of train_group");
+  for (int t = 0; t < CLSR_NUM_TABLES; ++t)
+    if (!e->tab[t]) return fail(e, CLSR_ERR_STATE, "table %d not bound", t);
+  CK(cudaSetDevice(e->cfg.device));
+  StepCtx c;
+  staged_ctx(e, e->staged_S, e->staged_G, &c);
+  return train_after_stage(e, c, flags, out);
+}
+
+// Inference on the staged batch; pred / alpha / users / labels: device buffers of `rows` elements (any may be NULL).
+int clsr_predict_staged(clsr_engine* e, float* dev_pred, float* dev_alpha, int32_t* dev_users, float* dev_labels) {
+  if (!e) return CLSR_ERR_ARG;
+  if (e->staged_S <= 0) return fail(e, CLSR_ERR_STATE, "no staged batch (clsr_build_batch)");
+  CK(cudaSetDevice(e->cfg.device));
+  int rc;
+  StepCtx c;
+  staged_ctx(e, e->staged_S, e->staged_G, &c);
+  CK(cudaMemsetAsync(e->counts, 0, 8 * sizeof(int32_t), e->stream));
+  if (e->sharded && (rc = peer_reduce(e, nullptr, 0, nullptr, 0, nullptr, 0))) return rc;
+  if ((rc = forward(e, c, 0, 0))) return rc;
+  sigmoid_kernel<<<grid1d(e, c.B, 256), 256, 0, e->stream>>>(e->B("logit"), c.B, e->B("pred"));
+  POST("sigmoid");
+  if (dev_pred) CK(cudaMemcpyAsync(dev_pred, e->B("pred"), (size_t)c.B * 4, cudaMemcpyDeviceToDevice, e->stream));
+  if (dev_alpha) CK(cudaMemcpyAsync(dev_alpha, e->B("alpha"), (size_t)c.B * 4, cudaMemcpyDeviceToDevice, e->stream));
+  if (dev_labels) CK(cudaMemcpyAsync(dev_labels, c.labels, (size_t)c.B * 4, cudaMemcpyDeviceToDevice, e->stream));
+  if (dev_users) {
+    if (c.G != 1) return fail(e, CLSR_ERR_ARG, "users are per sequence: only for ungrouped (evaluation) batches");
+    CK(cudaMemcpyAsync(dev_users, c.users, (size_t)c.S * 4, cudaMemcpyDeviceToDevice, e->stream));
+  }
+  return CLSR_OK;
+}
+
+// Copy one array of the staged feed to the host (tests): which = 0 item_history, 1 cate_history, 2 mask,
+// 3 time_from_first_action, 4 time_to_now, 5 users, 6 items, 7 cates, 8 labels.
+int clsr_staged_feed_read(clsr_engine* e, int32_t which, void* host_dst, int64_t bytes) {
+  if (!e || !host_dst || which < 0 || which > 8) return fail(e, CLSR_ERR_ARG, "bad argument");
+  if (e->staged_S <= 0) return fail(e, CLSR_ERR_STATE, "no staged batch");
+  StepCtx c;
+  staged_ctx(e, e->staged_S, e->staged_G, &c);
+  const void* src[9] = {c.ih, c.ch, c.mask, c.tfa, c.ttn, c.users, c.items, c.cates, c.labels};
+  const size_t seq = (size_t)c.S * c.T * 4, row = (size_t)c.B * 4;
+  const size_t have[9] = {seq, seq, seq, seq, seq, (size_t)c.S * 4, row, row, row};
+  if ((size_t)bytes > have[which]) return fail(e, CLSR_ERR_ARG, "array %d holds %zu bytes", which, have[which]);
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(host_dst, src[which], (size_t)bytes, cudaMemcpyDeviceToHost));
   return CLSR_OK;
 }
 

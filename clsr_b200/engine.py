@@ -62,6 +62,8 @@ EXPORTS = [
     "clsr_shard_local_values", "clsr_shard_local_grad", "clsr_shard_export", "clsr_shard_attach",
     "clsr_shard_zero_grad", "clsr_shard_gather_history", "clsr_shard_scatter_add_history",
     "clsr_crc32c", "clsr_clip_report", "clsr_peer_setup_begin", "clsr_peer_setup_finish", "clsr_table_local",
+    "clsr_predict_device", "clsr_eval_metrics_compute", "clsr_dataset_create", "clsr_dataset_destroy",
+    "clsr_build_batch", "clsr_train_step_staged", "clsr_predict_staged", "clsr_staged_feed_read",
 ]
 
 _lib = None
@@ -128,6 +130,13 @@ def load_library(path=None):
         "clsr_peer_setup_begin": (C.c_int, [P, I32, P]),
         "clsr_peer_setup_finish": (C.c_int, [P, P]),
         "clsr_table_local": (C.c_int, [P, I32, I32, C.POINTER(P), C.POINTER(I64)]),
+        "clsr_predict_device": (C.c_int, [P, C.POINTER(Batch), P, P]),
+        "clsr_dataset_create": (C.c_int, [P, I64, P, P, P, P, P, P, P, P, P, C.POINTER(P)]),
+        "clsr_dataset_destroy": (None, [P]),
+        "clsr_build_batch": (C.c_int, [P, P, P, I32, I32, C.c_uint64]),
+        "clsr_train_step_staged": (C.c_int, [P, U32, C.POINTER(Losses)]),
+        "clsr_predict_staged": (C.c_int, [P, P, P, P, P]),
+        "clsr_staged_feed_read": (C.c_int, [P, I32, P, I64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -139,6 +148,24 @@ def load_library(path=None):
 
 class EngineError(RuntimeError):
     pass
+
+
+class DeviceDataset:
+    """Handle of a device-resident columnar file cache (clsr_dataset)."""
+
+    def __init__(self, engine, h, n):
+        self.engine, self.h, self.n = engine, h, n
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.engine.lib.clsr_dataset_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 FEED_KEYS = ("users", "items", "cates", "item_history", "item_cate_history", "mask",
@@ -363,6 +390,75 @@ class Engine:
         self._check(self.lib.clsr_predict(self.h, C.byref(b), pred.ctypes.data,
                                           alpha.ctypes.data if with_alpha else None))
         return pred, alpha
+
+    def predict_device(self, feed, group=1, on_device=False, normalized=False, with_alpha=False):
+        """predict() with the results left on the device: (pred, alpha) float32 CUDA tensors (alpha None unless
+        asked for); asynchronous on the engine's stream (= torch's current stream)."""
+        if not on_device and not normalized:
+            feed = normalize_feed(feed, need_labels=False)
+        b = self._batch(feed, group, on_device, need_labels=False)
+        t = self.torch
+        pred = t.empty(b.rows, dtype=t.float32, device=self.device)
+        alpha = t.empty(b.rows, dtype=t.float32, device=self.device) if with_alpha else None
+        self._keep = feed
+        self._check(self.lib.clsr_predict_device(self.h, C.byref(b), pred.data_ptr(),
+                                                 alpha.data_ptr() if with_alpha else None))
+        return pred, alpha
+
+    # -- batches built on the device (SURVEY 8f rank 2) --
+    def create_dataset(self, label, user, item, cate, length, item_hist, cate_hist, tfa, ttn):
+        """Upload one parsed file (columnar host arrays, histories [n, T] left-aligned) as a device-resident cache."""
+        a = lambda x, dt: np.ascontiguousarray(np.asarray(x), dt)
+        cols = [a(label, np.float32), a(user, np.int32), a(item, np.int32), a(cate, np.int32), a(length, np.int32),
+                a(item_hist, np.int32), a(cate_hist, np.int32), a(tfa, np.float32), a(ttn, np.float32)]
+        n = cols[0].shape[0]
+        assert cols[5].shape == (n, self.seq_len), cols[5].shape
+        h = C.c_void_p()
+        self._check(self.lib.clsr_dataset_create(self.h, n, *[c.ctypes.data for c in cols], C.byref(h)))
+        return DeviceDataset(self, h, n)
+
+    def build_batch(self, ds, lines, num_ngs, seed=0):
+        """Build the feed of the given line indices on the device (num_ngs > 0: training batch with in-batch negatives)."""
+        lines = np.ascontiguousarray(lines, np.int32)
+        self._check(self.lib.clsr_build_batch(self.h, ds.h, lines.ctypes.data, len(lines), int(num_ngs),
+                                              int(seed) & 0xFFFFFFFFFFFFFFFF))
+        self._staged = (len(lines), num_ngs + 1)
+
+    def train_step_staged(self, flags=0, wait=True):
+        out = Losses()
+        self._check(self.lib.clsr_train_step_staged(self.h, flags, C.byref(out) if wait else None))
+        if not wait:
+            return None
+        self.last_table_grad_norms = tuple(out.table_grad_norm)
+        return {"loss": out.loss, "data_loss": out.data_loss, "regular_loss": out.regular_loss,
+                "contrastive_loss": out.contrastive_loss, "discrepancy_loss": out.discrepancy_loss}
+
+    def predict_staged(self, with_alpha=False, with_users=True):
+        """Inference on the staged batch: (pred, alpha, users, labels) CUDA tensors (asynchronous)."""
+        t = self.torch
+        S, G = self._staged
+        B = S * G
+        pred = t.empty(B, dtype=t.float32, device=self.device)
+        alpha = t.empty(B, dtype=t.float32, device=self.device) if with_alpha else None
+        users = t.empty(S, dtype=t.int32, device=self.device) if (with_users and G == 1) else None
+        labels = t.empty(B, dtype=t.float32, device=self.device)
+        self._check(self.lib.clsr_predict_staged(self.h, pred.data_ptr(), alpha.data_ptr() if with_alpha else None,
+                                                 users.data_ptr() if users is not None else None, labels.data_ptr()))
+        return pred, alpha, users, labels
+
+    def staged_feed(self):
+        """The staged batch as host arrays keyed like a feed (tests)."""
+        S, G = self._staged
+        T, B = self.seq_len, S * G
+        spec = [("item_history", np.int32, (S, T)), ("item_cate_history", np.int32, (S, T)), ("mask", np.int32, (S, T)),
+                ("time_from_first_action", np.float32, (S, T)), ("time_to_now", np.float32, (S, T)),
+                ("users", np.int32, (S,)), ("items", np.int32, (B,)), ("cates", np.int32, (B,)), ("labels", np.float32, (B,))]
+        out = {}
+        for i, (k, dt, shp) in enumerate(spec):
+            a = np.empty(shp, dt)
+            self._check(self.lib.clsr_staged_feed_read(self.h, i, a.ctypes.data, a.nbytes))
+            out[k] = a
+        return out
 
     def comm_init(self, rank, world, dist=None, shard=True):
         """Join a data-parallel group of ``world`` engines (one process per GPU).  The NCCL unique id is

@@ -206,6 +206,46 @@ int clsr_profile_collect(clsr_engine* e);
 int clsr_profile_entry(clsr_engine* e, int32_t i, char* name, int32_t name_cap, double* total_ms,
                        int64_t* calls);
 
+/* ---- batch construction on the GPU -----------------------------------------------
+ * Replaces SASequentialIterator._convert_data (sequential_iterator.py:519-704: pad, replicate x(1+num_ngs), draw
+ * in-batch negatives, row by row in Python).  clsr_dataset_create uploads one parsed file as columnar arrays
+ * (host pointers: per line label, user, item, cate, history length and the last T events of the item / category /
+ * time-feature histories, left-aligned, [n_lines, T]); ids are validated against the tables here, once.
+ * clsr_build_batch builds the feed of `count` lines (host array of line indices) on the device, straight into the
+ * block the step reads: num_ngs = 0 gives the evaluation batch (one row per line, the file's labels); num_ngs > 0
+ * the training batch (row 0 of each group = the line's positive, rows 1.. = positive items of other lines of the
+ * batch, never the line's own item, drawn by a counter-based generator from `seed`).  clsr_train_step_staged /
+ * clsr_predict_staged then run on that batch with no host feed at all. */
+typedef struct clsr_dataset clsr_dataset;
+int clsr_dataset_create(clsr_engine* e, int64_t n_lines, const float* label, const int32_t* user, const int32_t* item,
+                        const int32_t* cate, const int32_t* length, const int32_t* item_hist, const int32_t* cate_hist,
+                        const float* time_from_first_action, const float* time_to_now, clsr_dataset** out);
+void clsr_dataset_destroy(clsr_dataset* d);
+int clsr_build_batch(clsr_engine* e, clsr_dataset* d, const int32_t* host_lines, int32_t count, int32_t num_ngs,
+                     uint64_t seed);
+int clsr_train_step_staged(clsr_engine* e, uint32_t flags, clsr_losses* out);
+int clsr_predict_staged(clsr_engine* e, float* dev_pred, float* dev_alpha, int32_t* dev_users, float* dev_labels);
+int clsr_staged_feed_read(clsr_engine* e, int32_t which, void* host_dst, int64_t bytes);
+
+/* ---- evaluation on the GPU ----------------------------------------------------
+ * clsr_predict_device: clsr_predict with the predictions left in device memory (pred / alpha: device buffers of
+ * `rows` floats, alpha may be NULL; asynchronous on the engine stream) -- run_eval / run_weighted_eval
+ * (sequential_base_model.py:204-292) accumulate a whole file there instead of in Python lists.
+ * clsr_eval_metrics_compute: cal_metric + cal_weighted_metric (deeprec_utils.py:554-810) over n rows held on the
+ * device: auc and logloss over all rows; mean_mrr, ndcg@k, hit@k, group_auc over impressions of `group`
+ * consecutive rows (0: skip); wauc = per-user AUC weighted by the user's share of the rows (users may be NULL:
+ * skip).  status: bit 0 / 1 / 2 = all rows / a user / an impression hold a single label class (sklearn raises
+ * ValueError there and so does the Python wrapper). */
+typedef struct clsr_eval_metrics {
+  double auc, logloss, mean_mrr, group_auc, wauc;
+  double ndcg[8], hit[8];
+  int64_t n, n_pos, n_groups, n_users;
+  int32_t status;
+} clsr_eval_metrics;
+int clsr_predict_device(clsr_engine* e, const clsr_batch* batch, float* dev_pred, float* dev_alpha);
+int clsr_eval_metrics_compute(int32_t device, const float* preds, const float* labels, const int32_t* users, int64_t n,
+                              int32_t group, const int32_t* ks, int32_t nk, clsr_eval_metrics* out, void* cuda_stream);
+
 /* ---- host utility ------------------------------------------------------------------- */
 /* CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start).  Used by the tensor-bundle
  * checkpoint writer: tf.train.Saver.restore (base_model.py:394-410) verifies the per-tensor crc32c. */

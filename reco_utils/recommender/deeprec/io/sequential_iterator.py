@@ -16,6 +16,7 @@ from reco_utils.recommender.deeprec.io.iterator import BaseIterator, Placeholder
 __all__ = ["SequentialIterator", "SASequentialIterator"]
 
 GROUP_KEY = "_clsr_b200_group"  # private feed_dict entry: rows per shared-history group
+DEVICE_BATCH_KEY = "_clsr_b200_device_batch"  # private feed_dict entry: (device dataset, line indices, num_ngs, seed)
 
 
 class _Columns:
@@ -58,6 +59,11 @@ class SequentialIterator(BaseIterator):
         self.batch_size = hparams.batch_size
         self.iter_data = dict()
         self._columns = dict()
+        # Batches built on the GPU (clsr_build_batch): set by the model around its own fit / eval loops; the
+        # generator then yields a token {DEVICE_BATCH_KEY: ...} instead of host arrays.  Off by default, so code
+        # that reads the feed arrays itself sees exactly what the reference's iterator yields.
+        self.device_engine = None
+        self._device_ds = dict()
         self.time_unit = hparams.time_unit
         self.graph = graph
         T = self.max_seq_length
@@ -129,9 +135,24 @@ class SequentialIterator(BaseIterator):
         if batch_num_ngs > 0:
             order = order[np.random.permutation(len(order))]
         for a in range(0, len(order), self.batch_size):
+            if self.device_engine is not None:
+                sel = order[a:a + self.batch_size]
+                if batch_num_ngs and len(sel) < 5:   # the reference drops training batches of < 5 instances (:552-554)
+                    yield None
+                    continue
+                yield {DEVICE_BATCH_KEY: (self._dataset_on_device(infile, cols), sel.astype(np.int32), batch_num_ngs,
+                                          int(np.random.randint(0, 2 ** 62))), GROUP_KEY: batch_num_ngs + 1}
+                continue
             res = self._assemble(cols, order[a:a + self.batch_size], batch_num_ngs)
             batch_input = self.gen_feed_dict(res)
             yield batch_input if batch_input else None
+
+    def _dataset_on_device(self, infile, cols):
+        key = (infile, id(self.device_engine))
+        if key not in self._device_ds:
+            self._device_ds[key] = self.device_engine.create_dataset(
+                cols.label, cols.user, cols.item, cols.cate, cols.length, cols.ih, cols.ch, cols.tfa, cols.ttn)
+        return self._device_ds[key]
 
     def _assemble(self, cols, sel, batch_num_ngs):
         n = len(sel)

@@ -15,7 +15,7 @@ import numpy as np
 from clsr_b200 import params as P
 from clsr_b200.engine import Engine, detect_group, normalize_feed
 from reco_utils.recommender.deeprec.deeprec_utils import load_dict
-from reco_utils.recommender.deeprec.io.sequential_iterator import GROUP_KEY
+from reco_utils.recommender.deeprec.io.sequential_iterator import DEVICE_BATCH_KEY, GROUP_KEY
 from reco_utils.recommender.deeprec.models.sequential.sequential_base_model import SequentialBaseModel
 
 __all__ = ["CLSRModel"]
@@ -57,6 +57,10 @@ class CLSRModel(SequentialBaseModel):
             return int(os.environ.get(env, default)) if v is None else int(v)
         self.math_mode = knob("math_mode", "CLSR_MATH_MODE", 1)
         self.strict_clip = bool(knob("strict_clip", "CLSR_STRICT_CLIP", 0))
+        #   gpu_batches  (default 1) fit / run_eval / run_weighted_eval build their batches on the GPU from a
+        #              device-resident copy of the parsed file (padding, x(1+num_ngs) grouping, in-batch negative
+        #              sampling: sequential_iterator.py:519-704) instead of assembling host arrays per step.
+        self.gpu_batches = bool(knob("gpu_batches", "CLSR_GPU_BATCHES", 1))
         self._clip_warned = False
         self.engine = Engine(
             self.item_vocab_length, self.cate_vocab_length, self.user_vocab_length,
@@ -107,10 +111,16 @@ class CLSRModel(SequentialBaseModel):
         feed_dict[self.layer_keeps] = self.keep_prob_train
         feed_dict[self.embedding_keeps] = self.embedding_keep_prob_train
         feed_dict[self.is_train_stage] = True
-        feed, group = self._arrays(feed_dict, True)
-        if self.strict_clip and self.hparams.is_clip_norm:
-            group = 1
-        out = self.engine.train_step(feed, group=group, normalized=True)
+        if DEVICE_BATCH_KEY in feed_dict:
+            ds, lines, num_ngs, seed = feed_dict[DEVICE_BATCH_KEY]
+            self.engine.build_batch(ds, lines, num_ngs, seed)
+            group = num_ngs + 1
+            out = self.engine.train_step_staged()
+        else:
+            feed, group = self._arrays(feed_dict, True)
+            if self.strict_clip and self.hparams.is_clip_norm:
+                group = 1
+            out = self.engine.train_step(feed, group=group, normalized=True)
         if group > 1 and self.hparams.is_clip_norm and not self._clip_warned:
             norms = self.engine.last_table_grad_norms
             if max(norms) > float(self.hparams.max_grad_norm):
@@ -136,10 +146,36 @@ class CLSRModel(SequentialBaseModel):
                     print("step {0:d} , total_loss: {1:.4f}, data_loss: {2:.4f}".format(step, step_loss, step_data_loss))
         return epoch_loss
 
+    def _device_loops(self):
+        """Context manager: the iterator yields device-batch tokens inside the model's own loops."""
+        model = self
+
+        class _Ctx:
+            def __enter__(self):
+                if model.gpu_batches and not (model.strict_clip and model.hparams.is_clip_norm):
+                    model.iterator.device_engine = model.engine
+
+            def __exit__(self, *a):
+                model.iterator.device_engine = None
+                return False
+        return _Ctx()
+
+    def fit(self, train_file, valid_file, valid_num_ngs, eval_metric="group_auc"):
+        with self._device_loops():
+            return super().fit(train_file, valid_file, valid_num_ngs, eval_metric)
+
     def _predict(self, feed_dict, with_alpha=False):
         feed_dict[self.layer_keeps] = self.keep_prob_test
         feed_dict[self.embedding_keeps] = self.embedding_keep_prob_test
         feed_dict[self.is_train_stage] = False
+        if DEVICE_BATCH_KEY in feed_dict:
+            ds, lines, num_ngs, seed = feed_dict[DEVICE_BATCH_KEY]
+            self.engine.build_batch(ds, lines, num_ngs, seed)
+            p, a, u, y = self.engine.predict_staged(with_alpha=with_alpha)
+            self.engine.synchronize()
+            feed_dict[self.iterator.labels] = y.cpu().numpy().reshape(-1, 1)
+            feed = {"users": u.cpu().numpy() if u is not None else None}
+            return feed, p.cpu().numpy().reshape(-1, 1), (a.cpu().numpy().reshape(-1, 1) if with_alpha else None)
         feed, group = self._arrays(feed_dict, False)
         if GROUP_KEY in feed_dict and feed_dict[GROUP_KEY] == 1:
             group = 1
@@ -161,3 +197,71 @@ class CLSRModel(SequentialBaseModel):
     def infer(self, sess, feed_dict):
         _, pred, _ = self._predict(feed_dict)
         return [pred]
+
+    # ---- evaluation with device-resident predictions and GPU metrics -------------------------------------
+    def _eval_on_device(self, filename, num_ngs, weighted, calc_mean_alpha=False, manual_alpha=False):
+        """run_eval / run_weighted_eval (sequential_base_model.py:204-292) without the per-batch device -> host
+        copies and the host metric loops: predictions of the whole file stay on the GPU and
+        clsr_eval_metrics_compute returns auc / logloss / mean_mrr / ndcg@k / hit@k / group_auc / wauc."""
+        import torch
+        from clsr_b200 import metrics_gpu as MG
+        from reco_utils.recommender.deeprec.deeprec_utils import cal_mean_alpha_metric
+        preds, alphas, users, labels = [], [], [], []
+        it = self.iterator
+        was = it.device_engine
+        if self.gpu_batches:
+            it.device_engine = self.engine
+        try:
+            batches = list(it.load_data_from_file(filename, min_seq_length=self.min_seq_length, batch_num_ngs=0))
+        finally:
+            it.device_engine = was
+        for feed_dict in batches:
+            if not feed_dict:
+                continue
+            if DEVICE_BATCH_KEY in feed_dict:   # batch built on the device; users / labels never visit the host
+                ds, lines, _, seed = feed_dict[DEVICE_BATCH_KEY]
+                self.engine.build_batch(ds, lines, 0, seed)
+                p, a, u, y = self.engine.predict_staged(with_alpha=calc_mean_alpha)
+                preds.append(p)
+                if calc_mean_alpha:
+                    alphas.append(a)
+                users.append(u)
+                labels.append(y)
+                continue
+            feed_dict[self.layer_keeps] = self.keep_prob_test
+            feed_dict[self.embedding_keeps] = self.embedding_keep_prob_test
+            feed_dict[self.is_train_stage] = False
+            feed, _ = self._arrays(feed_dict, False)
+            p, a = self.engine.predict_device(feed, group=1, normalized=True, with_alpha=calc_mean_alpha)
+            preds.append(p)
+            if calc_mean_alpha:
+                alphas.append(a)
+            users.append(feed["users"].reshape(-1))
+            labels.append(np.asarray(feed_dict[it.labels], np.float32).reshape(-1))
+        preds = torch.cat(preds)
+        if isinstance(users[0], torch.Tensor):
+            users, labels = torch.cat(users), torch.cat(labels)
+        else:
+            users, labels = np.concatenate(users), np.concatenate(labels)
+        hp = self.hparams
+        res = MG.metric_dict(preds, labels, users, num_ngs + 1, hp.metrics, hp.pairwise_metrics,
+                             hp.weighted_metrics if weighted else None)
+        if calc_mean_alpha:
+            al = torch.cat(alphas).cpu().numpy()
+            lab = labels.cpu().numpy() if isinstance(labels, torch.Tensor) else labels
+            res.update(cal_mean_alpha_metric(al[0] if manual_alpha else al, lab))
+        return res
+
+    def run_eval(self, filename, num_ngs):
+        from clsr_b200 import metrics_gpu as MG
+        hp = self.hparams
+        if MG.supported(hp.metrics, hp.pairwise_metrics, None):
+            return self._eval_on_device(filename, num_ngs, weighted=False)
+        return super().run_eval(filename, num_ngs)
+
+    def run_weighted_eval(self, filename, num_ngs, calc_mean_alpha=False, manual_alpha=False):
+        from clsr_b200 import metrics_gpu as MG
+        hp = self.hparams
+        if MG.supported(hp.metrics, hp.pairwise_metrics, hp.weighted_metrics):
+            return self._eval_on_device(filename, num_ngs, True, calc_mean_alpha, manual_alpha)
+        return super().run_weighted_eval(filename, num_ngs, calc_mean_alpha, manual_alpha)

@@ -321,3 +321,124 @@ def test_data_parallel_matches_single_gpu(cuda_lib, shard, optimizer):
     line = [l for l in r.stdout.splitlines() if l.startswith("DP_RESULT ")][-1]
     res = json.loads(line[len("DP_RESULT "):])
     assert res["ok"] and res["sharded"] == bool(shard), res
+
+
+def test_gpu_metrics_match_reference_golden(cuda_lib):
+    """clsr_eval_metrics_compute against the values the reference's own cal_metric / cal_weighted_metric produced
+    (tests/golden/golden_host.npz, generated by importing /root/reference's deeprec_utils) and against this
+    repo's host implementation on a larger case with tied scores and users of very different sizes."""
+    import json
+    import os
+    import torch
+    from clsr_b200 import metrics_gpu as MG
+    from reco_utils.recommender.deeprec.deeprec_utils import cal_metric, cal_weighted_metric
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_host.npz"))
+    want = json.loads(str(gold["metrics_json"]))
+    y, p, users = gold["metric_y"], gold["metric_p"], gold["metric_users"]
+    got = MG.metric_dict(torch.from_numpy(p.astype(np.float32)).cuda(), y, users, 10, ["auc", "logloss"],
+                         ["mean_mrr", "ndcg@2;4;6", "hit@2;4;6", "group_auc"], ["wauc"])
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert abs(float(got[k]) - v) <= 1e-4 + 1e-9, (k, got[k], v)   # both rounded to 4 decimals (fp32 preds here)
+    # larger: 200k rows, groups of 100 (test_num_ngs = 99), quantised scores => many ties, skewed user sizes
+    rng = np.random.default_rng(5)
+    n, G = 200_000, 100
+    p = (np.round(rng.random(n) * 500) / 500).astype(np.float32)
+    y = np.zeros(n, np.float32)
+    y[::G] = 1.0
+    users = np.repeat(rng.zipf(1.3, n // G).clip(1, 5000), G).astype(np.int32)
+    r = MG.compute(torch.from_numpy(p).cuda(), y, users, G, [2, 4, 6])
+    host = cal_metric(list(y), list(p), ["auc", "logloss"])
+    assert abs(r.auc - host["auc"]) < 1e-4 and abs(r.logloss - host["logloss"]) < 1e-4
+    hw = cal_weighted_metric(list(users), list(p), list(y), ["wauc"])
+    assert abs(r.wauc - hw["wauc"]) < 1e-4, (r.wauc, hw)
+    assert r.n_users == len(np.unique(users)) and r.n_pos == n // G and r.status == 0
+    # per-impression metrics with the documented tie order (stable ascending argsort, reversed)
+    order = np.argsort(p.reshape(-1, G), axis=1, kind="stable")[:, ::-1]
+    rank = np.argmax(order == 0, axis=1) + 1                      # the positive is row 0 of every group
+    assert abs(r.mean_mrr - np.mean(1.0 / rank)) < 1e-9
+    for q, k in enumerate([2, 4, 6]):
+        assert abs(r.hit[q] - np.mean(rank <= k)) < 1e-9
+        assert abs(r.ndcg[q] - np.mean(np.where(rank <= k, 1.0 / np.log2(rank + 1.0), 0.0))) < 1e-9
+    pg, yg = p.reshape(-1, G).astype(np.float64), y.reshape(-1, G)
+    gauc = np.mean(((pg[:, 1:] < pg[:, :1]).sum(1) + 0.5 * (pg[:, 1:] == pg[:, :1]).sum(1)) / (G - 1))
+    assert abs(r.group_auc - gauc) < 1e-9
+    # a user with a single class is reported (sklearn raises there)
+    r2 = MG.compute(torch.from_numpy(p[:G]).cuda(), np.zeros(G, np.float32), users[:G], 0, [])
+    assert r2.status & 1
+
+
+def test_device_batches_match_reference_golden(cuda_lib):
+    """clsr_build_batch against the feeds the reference's own iterator produced (tests/golden/golden_host.npz):
+    the evaluation batch is reproduced exactly; of the training batch everything but the sampled negatives is
+    (the reference draws them with Python's unseeded `random`), and the negatives obey its rule -- another
+    line's positive item of the same batch, never the line's own (sequential_iterator.py:612-634).  A step on the
+    device-built batch equals a step on the same feed passed from the host."""
+    import os
+    import test_host_golden as HG
+    from clsr_b200.engine import Engine
+    from reco_utils.recommender.deeprec.io.sequential_iterator import SASequentialIterator, _Columns
+    gold = np.load(os.path.join(HG.GOLD, "golden_host.npz"), allow_pickle=False)
+    it = SASequentialIterator(HG.make_hparams(), None)
+    n_items, n_cates, n_users = len(it.itemdict) + 1, len(it.catedict) + 1, len(it.userdict) + 1
+    eng = Engine(n_items, n_cates, n_users, max_rows=100, seq_len=50, train_group=5)
+    prm = PU.scale_params(__import__("clsr_b200.params", fromlist=["init_params"]).init_params(n_items, n_cates, n_users, seed=2), 2)
+    eng.set_params(prm)
+    make = lambda c: eng.create_dataset(c.label, c.user, c.item, c.cate, c.length, c.ih, c.ch, c.tfa, c.ttn)
+    # -- evaluation batch: exact --
+    cols = it._load(os.path.join(HG.DATA, "valid_data"))
+    ds = make(cols)
+    n0 = gold["eval0/items"].shape[0]
+    eng.build_batch(ds, np.arange(n0), 0)
+    got = eng.staged_feed()
+    names = {"item_history": "item_history", "item_cate_history": "item_cate_history", "mask": "mask",
+             "time_from_first_action": "time_from_first_action", "time_to_now": "time_to_now", "users": "users",
+             "items": "items", "cates": "cates", "labels": "label"}
+    for k, gk in names.items():
+        want = gold["eval0/" + gk].reshape(got[k].shape)
+        if got[k].dtype.kind == "f":
+            np.testing.assert_allclose(got[k], want, rtol=1e-6, atol=1e-7, err_msg=k)
+        else:
+            assert np.array_equal(got[k], want.astype(got[k].dtype)), k
+    # -- training batch: 12 lines x (1 + 4) --
+    lines = it.parse_file(os.path.join(HG.DATA, "train_data"))[:12]
+    tcols = _Columns(lines, 50)
+    tds = make(tcols)
+    eng.build_batch(tds, np.arange(12), 4, seed=99)
+    got = eng.staged_feed()
+    G = 5
+    for k in ("item_history", "item_cate_history", "mask", "time_from_first_action", "time_to_now", "users"):
+        want = gold["train/" + k][::G].reshape(got[k].shape)
+        if got[k].dtype.kind == "f":
+            np.testing.assert_allclose(got[k], want, rtol=1e-6, atol=1e-7, err_msg=k)
+        else:
+            assert np.array_equal(got[k], want.astype(got[k].dtype)), k
+    items, cates = got["items"].reshape(12, G), got["cates"].reshape(12, G)
+    assert np.array_equal(items[:, 0], gold["train/items"][::G]) and np.array_equal(cates[:, 0], gold["train/cates"][::G])
+    assert np.array_equal(got["labels"].reshape(12, G), np.tile([1.0, 0, 0, 0, 0], (12, 1)))
+    cate_of = dict(zip(items[:, 0].tolist(), cates[:, 0].tolist()))
+    for s in range(12):
+        for g in range(1, G):
+            assert items[s, g] in cate_of and items[s, g] != items[s, 0] and cates[s, g] == cate_of[items[s, g]]
+    assert len({tuple(r) for r in items[:, 1:].tolist()}) > 1          # not one constant draw
+    eng.build_batch(tds, np.arange(12), 4, seed=100)
+    assert not np.array_equal(eng.staged_feed()["items"], got["items"])  # the seed matters
+    # -- a step on the device-built batch == a step on the same feed from the host --
+    from clsr_b200.engine import STEP_NO_OPTIMIZER, STEP_NO_BN_UPDATE
+    eng.build_batch(tds, np.arange(12), 4, seed=99)
+    a = eng.train_step_staged(flags=STEP_NO_OPTIMIZER | STEP_NO_BN_UPDATE)
+    rep = lambda x: np.repeat(x, G, axis=0)
+    feed = {"users": rep(got["users"]), "items": got["items"], "cates": got["cates"], "item_history": rep(got["item_history"]),
+            "item_cate_history": rep(got["item_cate_history"]), "mask": rep(got["mask"]),
+            "time_from_first_action": rep(got["time_from_first_action"]), "time_to_now": rep(got["time_to_now"]),
+            "labels": got["labels"].reshape(-1, 1)}
+    b = eng.train_step(feed, group=G, flags=STEP_NO_OPTIMIZER | STEP_NO_BN_UPDATE)
+    for k in a:
+        assert abs(a[k] - b[k]) <= 1e-6 * max(abs(b[k]), 1e-6), (k, a[k], b[k])
+    # evaluation through the staged path: predictions equal predict() on the host feed
+    eng.build_batch(ds, np.arange(n0), 0)
+    p, _, u, y = eng.predict_staged()
+    ef = eng.staged_feed()
+    hp, _ = eng.predict({k: (ef[k] if k != "labels" else ef[k].reshape(-1, 1)) for k in ef}, group=1)
+    assert np.allclose(p.cpu().numpy(), hp, rtol=1e-6, atol=1e-7)
+    assert np.array_equal(u.cpu().numpy(), ef["users"]) and np.array_equal(y.cpu().numpy(), ef["labels"])
