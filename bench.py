@@ -246,7 +246,7 @@ def measure(a, w, S, optimizer, rank, world, local, dist, steps, warmup, windows
     eng = Engine(w["n_items"], w["n_cates"], w["n_users"], max_rows=B, seq_len=T, train_group=G,
                  item_dim=d["Di"], cate_dim=d["Dc"], user_dim=d["U"], hidden=d["H"], att_sizes=(d["A0"], d["A1"]),
                  layer_sizes=(d["L0"], d["L1"]), optimizer=optimizer, device=local, math_mode=1 if a.math == "tc" else 0,
-                 alloc_tables=not (dev_init and world > 1))
+                 alloc_tables=not (dev_init and world > 1), max_seqs=S)
     dense = P.init_params(1, 1, 1, Di=d["Di"], Dc=d["Dc"], U=d["U"], H=d["H"], att_sizes=(d["A0"], d["A1"]),
                           layer_sizes=(d["L0"], d["L1"]), seed=42, tables=False)
     eng.set_dense(dense)

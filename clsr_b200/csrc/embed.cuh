@@ -57,9 +57,18 @@ gather_hist_kernel(const int32_t* __restrict__ ih, const int32_t* __restrict__ c
       }
     }
     float4 v[UNROLL];
+    // local table: rows are touched once, stream them past L1; sharded table: L1-allocating loads, so that the
+    // hot (low, frequency-sorted) ids and the padding row -- a third of all positions, all owned by rank 0 -- are
+    // re-read from this SM's L1 instead of crossing NVLink every time
+    if (item_tab.mask) {
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
-      if (src[u]) v[u] = ldg_stream(src[u]);
+      for (int u = 0; u < UNROLL; ++u)
+        if (src[u]) v[u] = __ldg(src[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (src[u]) v[u] = ldg_stream(src[u]);
+    }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
       if (src[u]) stg_stream(reinterpret_cast<float4*>(out) + gi[u], v[u]);
@@ -388,6 +397,182 @@ __global__ void adam_lazy_kernel(float* __restrict__ var, float* __restrict__ m,
   }
 }
 #undef CLSR_ADAM1
+
+// ---- several small per-table launches folded into one (the step is a long chain of short kernels: every launch
+// saved is a few microseconds of tail + ramp) ---------------------------------------------------------------------
+constexpr int kMaxSeg = 5;
+struct GatherRowsSeg { const int32_t* idx; int idx_stride; TabView tab; int dim; float* out; int ldo, col0, rows; };
+struct GatherRowsMulti { GatherRowsSeg s[4]; int n; };
+__global__ void gather_rows_multi_kernel(const __grid_constant__ GatherRowsMulti a) {
+  for (int k = 0; k < a.n; ++k) {
+    const GatherRowsSeg& g = a.s[k];
+    const int V = g.dim >> 2;
+    const long long n = (long long)g.rows * V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const int r = (int)(i / V), q = (int)(i % V);
+      const int id = __ldg(g.idx + (size_t)r * g.idx_stride);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(g.tab.row(id, g.dim)) + q);
+      *reinterpret_cast<float4*>(g.out + (size_t)r * g.ldo + g.col0 + q * 4) = v;
+    }
+  }
+}
+
+struct UniqueSeg { const int32_t* ids; long long n; int T, seq_stride; int32_t* slot; int32_t* uniq; int32_t* counter; };
+struct UniqueMulti { UniqueSeg s[kMaxSeg]; int n; };
+__global__ void mark_unique_multi_kernel(const __grid_constant__ UniqueMulti a) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < a.n; ++k) {
+    const UniqueSeg& u = a.s[k];
+    const long long nround = (u.n + stride - 1) / stride * stride;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+      bool claim = false;
+      int id = 0;
+      if (i < u.n) {
+        const long long sq = i / u.T;
+        id = __ldg(u.ids + sq * u.seq_stride + (i - sq * u.T));
+        if (u.slot[id] == -1) claim = atomicCAS(&u.slot[id], -1, -2) == -1;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, claim);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(u.counter, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (claim) {
+          const int c = base + __popc(m & ((1u << lane) - 1u));
+          u.uniq[c] = id;
+          u.slot[id] = c;
+        }
+      }
+    }
+  }
+}
+
+struct CompactSeg { float* g; const int32_t* counter; int dim; const int32_t* uniq; int32_t* slot; };
+struct CompactMulti { CompactSeg s[4]; int n; };
+__global__ void zero_compact_multi_kernel(const __grid_constant__ CompactMulti a) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < a.n; ++k) {
+    const long long n = (long long)(*a.s[k].counter) * a.s[k].dim / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      reinterpret_cast<float4*>(a.s[k].g)[i] = z;
+  }
+}
+__global__ void reset_slots_multi_kernel(const __grid_constant__ CompactMulti a) {
+  for (int k = 0; k < a.n; ++k) {
+    const int n = *a.s[k].counter;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) a.s[k].slot[a.s[k].uniq[c]] = -1;
+  }
+}
+
+struct ScatterRowsSeg { const float* d; int ldd, col0, dim; const int32_t* idx; int idx_stride; const int32_t* slot; float* g; int rows; double* sumsq; };
+struct ScatterRowsMulti { ScatterRowsSeg s[4]; int n; };
+__global__ void scatter_rows_multi_kernel(const __grid_constant__ ScatterRowsMulti a) {
+  for (int k = 0; k < a.n; ++k) {
+    const ScatterRowsSeg& r = a.s[k];
+    const int V = r.dim >> 2;
+    const long long n = (long long)r.rows * V;
+    float ss = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const int row = (int)(i / V), q = (int)(i % V);
+      const float4 v = *reinterpret_cast<const float4*>(r.d + (size_t)row * r.ldd + r.col0 + q * 4);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      const int id = __ldg(r.idx + (size_t)row * r.idx_stride);
+      red_add_v4(r.g + (size_t)r.slot[id] * r.dim + q * 4, v);
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0 && ss != 0.f) atomicAdd(r.sumsq, (double)ss);
+  }
+}
+
+struct InvolvedSeg { const float* tab; const float* other; int dim; const int32_t* uniq; const int32_t* counter; float* g;
+                     float l2, disc_w; int count_disc; double* sumsq; double* acc; };
+struct InvolvedMulti { InvolvedSeg s[4]; int n; };
+__global__ void involved_multi_kernel(const __grid_constant__ InvolvedMulti a) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int k = 0; k < a.n; ++k) {
+    const InvolvedSeg& v = a.s[k];
+    const int n = *v.counter;
+    float ss = 0.f, rr = 0.f, dd = 0.f;
+    const float dcoef = v.other ? -2.0f * v.disc_w / ((float)n * (float)v.dim) : 0.f;
+    for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < n; c += gridDim.x * wpb) {
+      const size_t row = (size_t)v.uniq[c] * v.dim;
+      for (int j = lane; j < v.dim; j += 32) {
+        const float x = v.tab[row + j];
+        float t = v.l2 * x;
+        rr += x * x;
+        if (v.other) {
+          const float df = x - v.other[row + j];
+          t += dcoef * df;
+          dd += df * df;
+        }
+        v.g[(size_t)c * v.dim + j] += t;
+        ss += t * t;
+      }
+    }
+    ss = warp_sum(ss); rr = warp_sum(rr); dd = warp_sum(dd);
+    if (lane == 0) {
+      if (ss != 0.f) atomicAdd(v.sumsq, (double)ss);
+      if (rr != 0.f) atomicAdd(v.acc, (double)rr);
+      if (v.other && v.count_disc && dd != 0.f) atomicAdd(v.acc + 1, (double)dd);
+    }
+  }
+}
+
+// TF's non-lazy Adam over all four tables in one launch (same inner loop as adam_sweep_kernel).
+struct SweepSeg { float* var; float* m; float* v; const int32_t* slot; const float* g; int dim; long long rows; const double* sumsq; };
+struct SweepMulti { SweepSeg s[4]; int n; };
+template <int UN>
+__global__ void __launch_bounds__(256)
+adam_sweep_multi_kernel(const __grid_constant__ SweepMulti a, AdamHyper hp) {
+  for (int k = 0; k < a.n; ++k) {
+    const SweepSeg& w = a.s[k];
+    const int V = w.dim >> 2;
+    float scale = 1.f;
+    if (hp.clip > 0.f) {
+      const float nrm = (float)sqrt(*w.sumsq);
+      scale = hp.clip / fmaxf(nrm, hp.clip);
+    }
+    const long long nvec = w.rows * V;
+    const long long stride = blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x * UN + threadIdx.x; i0 < nvec;
+         i0 += (long long)gridDim.x * blockDim.x * UN) {
+      float4 mv[UN], vv[UN], xv[UN];
+      int c[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const long long i = i0 + u * stride;
+        const long long ic = i < nvec ? i : nvec - 1;
+        mv[u] = ldg_stream(reinterpret_cast<const float4*>(w.m) + ic);
+        vv[u] = ldg_stream(reinterpret_cast<const float4*>(w.v) + ic);
+        xv[u] = ldg_stream(reinterpret_cast<const float4*>(w.var) + ic);
+        c[u] = __ldg(w.slot + ic / V);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const long long i = i0 + u * stride;
+        if (i >= nvec) continue;
+        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c[u] >= 0) {
+          const int q = (int)(i - (i / V) * V);
+          gv = *reinterpret_cast<const float4*>(w.g + (size_t)c[u] * w.dim + q * 4);
+          gv.x *= scale; gv.y *= scale; gv.z *= scale; gv.w *= scale;
+        }
+#define CLSR_ADAM1(c_)                                                      \
+  mv[u].c_ = hp.beta1 * mv[u].c_ + (1.f - hp.beta1) * gv.c_;                \
+  vv[u].c_ = hp.beta2 * vv[u].c_ + (1.f - hp.beta2) * gv.c_ * gv.c_;        \
+  xv[u].c_ -= hp.lr_t * mv[u].c_ / (sqrtf(vv[u].c_) + hp.eps);
+        CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
+#undef CLSR_ADAM1
+        stg_stream(reinterpret_cast<float4*>(w.m) + i, mv[u]);
+        stg_stream(reinterpret_cast<float4*>(w.v) + i, vv[u]);
+        stg_stream(reinterpret_cast<float4*>(w.var) + i, xv[u]);
+      }
+    }
+  }
+}
 
 // ---- row-sharded tables under the data-parallel step ----------------------------------------------------
 // Every rank de-duplicates its own slices exactly as on one GPU (slot table, compact rows), then pushes each

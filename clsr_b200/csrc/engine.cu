@@ -62,7 +62,7 @@ struct clsr_engine {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t aux[2] = {nullptr, nullptr};   // side streams: the three recurrences run concurrently
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_memset = nullptr;
   bool debug_sync = false;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -1085,15 +1085,18 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
     POST("gather_hist");
   }
   float* tgt = e->B("tgt");
-  gather_rows_kernel<<<grid1d(e, (long long)B * Di / 4, 256), 256, 0, st>>>(c.items, 1, e->tview[CLSR_TABLE_ITEM], Di, tgt, D, 0, B);
-  POST("gather_tgt_item");
-  gather_rows_kernel<<<grid1d(e, (long long)B * Dc / 4, 256), 256, 0, st>>>(c.cates, 1, e->tview[CLSR_TABLE_CATE], Dc, tgt, D, Di, B);
-  POST("gather_tgt_cate");
   float *ul = e->B("ul"), *us = e->B("us");
-  gather_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(c.users, c.user_stride, e->tview[CLSR_TABLE_USER_LONG], U, ul, U, 0, S);
-  POST("gather_ul");
-  gather_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(c.users, c.user_stride, e->tview[CLSR_TABLE_USER_SHORT], U, us, U, 0, S);
-  POST("gather_us");
+  {
+    // target item / category rows and the two user rows: one launch
+    GatherRowsMulti gm;
+    gm.n = 4;
+    gm.s[0] = GatherRowsSeg{c.items, 1, e->tview[CLSR_TABLE_ITEM], Di, tgt, D, 0, B};
+    gm.s[1] = GatherRowsSeg{c.cates, 1, e->tview[CLSR_TABLE_CATE], Dc, tgt, D, Di, B};
+    gm.s[2] = GatherRowsSeg{c.users, c.user_stride, e->tview[CLSR_TABLE_USER_LONG], U, ul, U, 0, S};
+    gm.s[3] = GatherRowsSeg{c.users, c.user_stride, e->tview[CLSR_TABLE_USER_SHORT], U, us, U, 0, S};
+    gather_rows_multi_kernel<<<grid1d(e, (long long)B * Di / 4, 256), 256, 0, st>>>(gm);
+    POST("gather_rows(tgt|users)");
+  }
 
   // ---- hoisted input projections of the three recurrences ----
   float *TNL = e->B("TNL"), *PX = e->B("PX");
@@ -1246,6 +1249,14 @@ int backward(clsr_engine* e, const StepCtx& c) {
   auto dW = [&](const char* n) { return e->dWd + e->wd_off.at(n); };
   float *tgt = e->B("tgt"), *X = e->B("X");
 
+  // dPX (every position's pre-activation gradients; the BPTT kernels only write the live ones) is cleared on a
+  // side stream while the head and the short attention run: the fill is pure HBM traffic, they are not
+  float *PX = e->B("PX"), *dPX = e->B("dPX");
+  CK(cudaEventRecord(e->ev_fork, st));
+  CK(cudaStreamWaitEvent(e->aux[0], e->ev_fork, 0));
+  CK(cudaMemsetAsync(dPX, 0, (size_t)M * NX * 4, e->aux[0]));
+  CK(cudaEventRecord(e->ev_memset, e->aux[0]));
+
   // ---- data loss + prediction MLP ----
   softmax_loss_kernel<<<grid1d(e, B / e->cfg.train_group, 128), 128, 0, st>>>(
       e->B("logit"), c.labels, e->cfg.train_group, B, B * e->world, e->B("dlogit"), e->B("pred"), e->acc);
@@ -1352,9 +1363,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
   if ((rc = dw_group_flush(e, "dW_short_group"))) return rc;
 
   // ---- BPTT through the three recurrences ----
-  float *PX = e->B("PX"), *dPX = e->B("dPX");
-  CK(cudaMemsetAsync(dPX, 0, (size_t)M * NX * 4, st));
-  MARK("memset_dPX");
+  CK(cudaStreamWaitEvent(st, e->ev_memset, 0));
   const int nblk = cdiv(S, RNN_NSEQ);
   {
     // the three BPTT kernels write disjoint column ranges of dPX: run them side by side
@@ -1528,36 +1537,37 @@ int sparse_grads(clsr_engine* e, const StepCtx& c) {
     seq_stride = T; user_stride = 1;
     B *= e->world; S *= e->world; M *= e->world;
   }
-  mark_unique_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(ih, M, T, seq_stride, e->slot[0], e->uniq[0], e->counts + 1);
-  POST("unique_item_hist");
-  mark_unique_kernel<<<grid1d(e, B, 256), 256, 0, st>>>(items, B, 1, 1, e->slot[0], e->uniq[0], e->counts + 1);
-  POST("unique_item_tgt");
-  mark_unique_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(ch, M, T, seq_stride, e->slot[1], e->uniq[1], e->counts + 2);
-  POST("unique_cate_hist");
-  mark_unique_kernel<<<grid1d(e, B, 256), 256, 0, st>>>(cates, B, 1, 1, e->slot[1], e->uniq[1], e->counts + 2);
-  POST("unique_cate_tgt");
-  mark_unique_kernel<<<grid1d(e, S, 256), 256, 0, st>>>(users, S, 1, user_stride, e->slot[2], e->uniq[2], e->counts + 3);
-  POST("unique_users");
-  const int cnt_ix[4] = {1, 2, 3, 3};
-  for (int t = 0; t < 4; ++t) {
-    zero_compact_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->cg[t], e->counts + cnt_ix[t], e->tab_dim[t]);
+  {
+    // tf.unique of the five id arrays (history + target items, history + target categories, users): one launch
+    UniqueMulti um;
+    um.n = 5;
+    um.s[0] = UniqueSeg{ih, M, T, seq_stride, e->slot[0], e->uniq[0], e->counts + 1};
+    um.s[1] = UniqueSeg{items, B, 1, 1, e->slot[0], e->uniq[0], e->counts + 1};
+    um.s[2] = UniqueSeg{ch, M, T, seq_stride, e->slot[1], e->uniq[1], e->counts + 2};
+    um.s[3] = UniqueSeg{cates, B, 1, 1, e->slot[1], e->uniq[1], e->counts + 2};
+    um.s[4] = UniqueSeg{users, S, 1, user_stride, e->slot[2], e->uniq[2], e->counts + 3};
+    mark_unique_multi_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(um);
+    POST("unique(items|cates|users)");
+    CompactMulti cm;
+    cm.n = 4;
+    const int cnt_ix0[4] = {1, 2, 3, 3};
+    for (int t = 0; t < 4; ++t) cm.s[t] = CompactSeg{e->cg[t], e->counts + cnt_ix0[t], e->tab_dim[t], nullptr, nullptr};
+    zero_compact_multi_kernel<<<e->num_sms * 2, 256, 0, st>>>(cm);
     POST("zero_compact");
   }
   scatter_hist_kernel<<<e->num_sms * 4, 256, (size_t)D * 4, st>>>(dX, ih, ch, seq_stride, T, e->slot[0], e->slot[1],
                                                                 e->cg[0], e->cg[1], Di, Dc, M, e->sumsq);
   POST("scatter_hist");
-  scatter_rows_kernel<<<grid1d(e, (long long)B * Di / 4, 256), 256, 0, st>>>(dtgt, D, 0, Di, items, 1, e->slot[0],
-                                                                           e->cg[0], B, e->sumsq + 0);
-  POST("scatter_tgt_item");
-  scatter_rows_kernel<<<grid1d(e, (long long)B * Dc / 4, 256), 256, 0, st>>>(dtgt, D, Di, Dc, cates, 1, e->slot[1],
-                                                                           e->cg[1], B, e->sumsq + 1);
-  POST("scatter_tgt_cate");
-  scatter_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(dul, U, 0, U, users, user_stride,
-                                                                          e->slot[2], e->cg[2], S, e->sumsq + 2);
-  POST("scatter_ul");
-  scatter_rows_kernel<<<grid1d(e, (long long)S * U / 4, 256), 256, 0, st>>>(dus, U, 0, U, users, user_stride,
-                                                                          e->slot[2], e->cg[3], S, e->sumsq + 3);
-  POST("scatter_us");
+  {
+    ScatterRowsMulti sm;
+    sm.n = 4;
+    sm.s[0] = ScatterRowsSeg{dtgt, D, 0, Di, items, 1, e->slot[0], e->cg[0], B, e->sumsq + 0};
+    sm.s[1] = ScatterRowsSeg{dtgt, D, Di, Dc, cates, 1, e->slot[1], e->cg[1], B, e->sumsq + 1};
+    sm.s[2] = ScatterRowsSeg{dul, U, 0, U, users, user_stride, e->slot[2], e->cg[2], S, e->sumsq + 2};
+    sm.s[3] = ScatterRowsSeg{dus, U, 0, U, users, user_stride, e->slot[2], e->cg[3], S, e->sumsq + 3};
+    scatter_rows_multi_kernel<<<grid1d(e, (long long)B * Di / 4, 256), 256, 0, st>>>(sm);
+    POST("scatter_rows(tgt|users)");
+  }
   const float l2 = e->cfg.embed_l2, dw = e->cfg.discrepancy_weight;
   if (e->sharded) {
     // Row-sharded tables: every unique compact row goes ONCE to its owner (NVLink reductions into the owner's
@@ -1587,20 +1597,18 @@ int sparse_grads(clsr_engine* e, const StepCtx& c) {
     POST("involved_us");
     return 0;
   }
-  involved_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[0], nullptr, Di, e->uniq[0], e->counts + 1, e->cg[0], l2, 0.f, 0,
-                                                  e->sumsq + 0, e->acc + 5);
-  POST("involved_item");
-  involved_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[1], nullptr, Dc, e->uniq[1], e->counts + 2, e->cg[1], l2, 0.f, 0,
-                                                  e->sumsq + 1, e->acc + 6);
-  POST("involved_cate");
-  // acc[7] = long rows^2, acc[8] = short rows^2, acc[9] = sum (long-short)^2 (written by the
-  // short-table call only: its acc base is acc+8, its discrepancy slot acc+8+1).
-  involved_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[2], e->tab[3], U, e->uniq[2], e->counts + 3, e->cg[2], l2, dw, 0,
-                                                  e->sumsq + 2, e->acc + 7);
-  POST("involved_ul");
-  involved_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->tab[3], e->tab[2], U, e->uniq[2], e->counts + 3, e->cg[3], l2, dw, 1,
-                                                  e->sumsq + 3, e->acc + 8);
-  POST("involved_us");
+  {
+    // acc[5] item rows^2, acc[6] cate rows^2, acc[7] long rows^2, acc[8] short rows^2, acc[9] sum (long-short)^2
+    // (written by the short-table segment only: its acc base is acc+8, its discrepancy slot acc+8+1)
+    InvolvedMulti im;
+    im.n = 4;
+    im.s[0] = InvolvedSeg{e->tab[0], nullptr, Di, e->uniq[0], e->counts + 1, e->cg[0], l2, 0.f, 0, e->sumsq + 0, e->acc + 5};
+    im.s[1] = InvolvedSeg{e->tab[1], nullptr, Dc, e->uniq[1], e->counts + 2, e->cg[1], l2, 0.f, 0, e->sumsq + 1, e->acc + 6};
+    im.s[2] = InvolvedSeg{e->tab[2], e->tab[3], U, e->uniq[2], e->counts + 3, e->cg[2], l2, dw, 0, e->sumsq + 2, e->acc + 7};
+    im.s[3] = InvolvedSeg{e->tab[3], e->tab[2], U, e->uniq[2], e->counts + 3, e->cg[3], l2, dw, 1, e->sumsq + 3, e->acc + 8};
+    involved_multi_kernel<<<e->num_sms * 2, 256, 0, st>>>(im);
+    POST("involved(4 tables)");
+  }
   return 0;
 }
 
@@ -1630,8 +1638,21 @@ int optimizer_step(clsr_engine* e) {
   POST("dense_adam");
   AdamHyper hp = {lr_t, cf.beta1, cf.beta2, cf.adam_eps, cf.clip_norm ? cf.max_grad_norm : 0.f};
   const int slot_ix[4] = {0, 1, 2, 2}, cnt_ix[4] = {1, 2, 3, 3};
-  for (int tb = 0; tb < 4; ++tb) {
+  for (int tb = 0; tb < 4; ++tb)
     if (!e->tab_m[tb] || !e->tab_v[tb]) return fail(e, CLSR_ERR_STATE, "Adam slots of table %d not bound", tb);
+  if (!e->sharded && cf.optimizer == 0) {
+    // TF's non-lazy sweep of all four tables in one launch (UN = 2 vectors in flight per thread, 16 CTAs per SM:
+    // 0.9 of the measured HBM peak)
+    SweepMulti sw;
+    sw.n = 4;
+    for (int tb = 0; tb < 4; ++tb)
+      sw.s[tb] = SweepSeg{e->tab[tb], e->tab_m[tb], e->tab_v[tb], e->slot[slot_ix[tb]], e->cg[tb], e->tab_dim[tb], e->tab_rows[tb],
+                          e->sumsq + tb};
+    adam_sweep_multi_kernel<2><<<e->num_sms * 16, 256, 0, st>>>(sw, hp);
+    POST("adam_sweep");
+    return 0;
+  }
+  for (int tb = 0; tb < 4; ++tb) {
     if (e->sharded) {   // the owner updates its 1/world of the rows from its dense gradient shard
       const int tt = tb == 3 ? 2 : tb;
       if (cf.optimizer == 1) {
@@ -1661,10 +1682,11 @@ int optimizer_step(clsr_engine* e) {
 }
 
 int reset_slots(clsr_engine* e) {
-  for (int i = 0; i < 3; ++i) {
-    reset_slots_kernel<<<e->num_sms, 256, 0, e->stream>>>(e->uniq[i], e->counts + 1 + i, e->slot[i]);
-    POST("reset_slots");
-  }
+  CompactMulti cm;
+  cm.n = 3;
+  for (int i = 0; i < 3; ++i) cm.s[i] = CompactSeg{nullptr, e->counts + 1 + i, 0, e->uniq[i], e->slot[i]};
+  reset_slots_multi_kernel<<<e->num_sms, 256, 0, e->stream>>>(cm);
+  POST("reset_slots");
   return 0;
 }
 
@@ -1735,6 +1757,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
     CKCU(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
   }
   CKCU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CKCU(cudaEventCreateWithFlags(&e->ev_memset, cudaEventDisableTiming));
 
   e->T = cfg->seq_len; e->Di = cfg->item_dim; e->Dc = cfg->cate_dim; e->D = e->Di + e->Dc; e->U = cfg->user_dim;
   e->H = cfg->hidden; e->Q = e->U + e->D; e->A0 = cfg->att0; e->A1 = cfg->att1; e->L0 = cfg->fc0; e->L1 = cfg->fc1;
@@ -1743,7 +1766,8 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
   e->oG1 = 0; e->oC1 = 2 * U; e->oG2 = 3 * U; e->oC2 = 3 * U + 2 * H; e->oL = 3 * U + 3 * H;
   e->oO = e->oL + 3 * H; e->oTN = e->oL + 4 * H; e->oTL = e->oL + 5 * H; e->NX = e->oL + 6 * H;
   e->Bmax = cfg->max_rows;
-  e->Smax = cfg->max_rows;  // group = 1 must always fit
+  // per-sequence buffers: sized for ungrouped batches of max_rows unless the caller bounds the sequences
+  e->Smax = (cfg->max_seqs > 0 && cfg->max_seqs < cfg->max_rows) ? cfg->max_seqs : cfg->max_rows;
   e->tab_rows[0] = cfg->n_items; e->tab_rows[1] = cfg->n_cates; e->tab_rows[2] = cfg->n_users; e->tab_rows[3] = cfg->n_users;
   e->tab_dim[0] = e->Di; e->tab_dim[1] = e->Dc; e->tab_dim[2] = U; e->tab_dim[3] = U;
 
@@ -1882,6 +1906,7 @@ void clsr_destroy(clsr_engine* e) {
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
   }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_memset) cudaEventDestroy(e->ev_memset);
   delete e;
 }
 
@@ -2203,6 +2228,7 @@ int clsr_build_batch(clsr_engine* e, clsr_dataset* d, const int32_t* host_lines,
   if (!e || !d || !host_lines || count <= 0 || num_ngs < 0) return fail(e, CLSR_ERR_ARG, "bad argument");
   const int G = num_ngs + 1, S = count;
   if ((long long)S * G > e->Bmax) return fail(e, CLSR_ERR_ARG, "rows %lld exceed max_rows %d", (long long)S * G, e->Bmax);
+  if (S > e->Smax) return fail(e, CLSR_ERR_ARG, "sequences %d exceed max_seqs %d", S, e->Smax);
   if (d->T != e->T || d->device != e->cfg.device) return fail(e, CLSR_ERR_ARG, "dataset belongs to another engine shape / device");
   for (int i = 0; i < count; ++i)
     if (host_lines[i] < 0 || host_lines[i] >= d->n) return fail(e, CLSR_ERR_ARG, "line index %d outside the dataset", host_lines[i]);

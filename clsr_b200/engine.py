@@ -31,7 +31,7 @@ class Config(C.Structure):
         ("contrastive_recent_k", C.c_int32), ("optimizer", C.c_int32), ("learning_rate", C.c_float),
         ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float), ("clip_norm", C.c_int32),
         ("max_grad_norm", C.c_float), ("bn_momentum", C.c_float), ("bn_eps", C.c_float),
-        ("math_mode", C.c_int32),
+        ("math_mode", C.c_int32), ("max_seqs", C.c_int32),
     ]
 
 
@@ -210,7 +210,7 @@ class Engine:
                  embed_l2=1e-6, layer_l2=1e-6, contrastive_loss="triplet", triplet_margin=1.0,
                  contrastive_weight=0.1, discrepancy_weight=0.01, contrastive_len_threshold=5,
                  contrastive_recent_k=3, optimizer="adam", learning_rate=1e-3, clip_norm=True,
-                 max_grad_norm=2.0, device=0, math_mode=0, training=True, alloc_tables=True):
+                 max_grad_norm=2.0, device=0, math_mode=0, training=True, alloc_tables=True, max_seqs=0):
         import torch
         if not torch.cuda.is_available():
             raise EngineError("clsr_b200 needs a CUDA device (no CPU fallback)")
@@ -229,7 +229,7 @@ class Engine:
             contrastive_len_threshold=contrastive_len_threshold, contrastive_recent_k=contrastive_recent_k,
             optimizer=0 if optimizer == "adam" else 1, learning_rate=learning_rate, beta1=0.9, beta2=0.999,
             adam_eps=1e-8, clip_norm=1 if clip_norm else 0, max_grad_norm=max_grad_norm, bn_momentum=0.95,
-            bn_eps=1e-4, math_mode=math_mode)
+            bn_eps=1e-4, math_mode=math_mode, max_seqs=int(max_seqs or 0))
         self.device = torch.device("cuda", device)
         self.h = C.c_void_p()
         rc = self.lib.clsr_create(C.byref(self.cfg), C.byref(self.h))

@@ -58,6 +58,7 @@ typedef struct clsr_config {
   float max_grad_norm;
   float bn_momentum, bn_eps; /* 0.95 / 1e-4 (base_model.py:676-677) */
   int32_t math_mode;         /* 0 = fp32 SIMT everywhere, 1 = bf16 tcgen05 for the large GEMMs */
+  int32_t max_seqs;          /* capacity in sequences (rows / group); 0 = max_rows (ungrouped batches of max_rows fit) */
 } clsr_config;
 
 /* One feed_dict (sequential_iterator.py:718-731), as plain arrays.  `group` declares that
