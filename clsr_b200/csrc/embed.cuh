@@ -75,6 +75,119 @@ gather_hist_kernel(const int32_t* __restrict__ ih, const int32_t* __restrict__ c
   }
 }
 
+// ---- bulk-copy (TMA) form of the history gather -----------------------------------------------------------------
+// One thread per position issues two cp.async.bulk copies (item row, category row: global -> shared, completion
+// counted in bytes on an mbarrier) straight into the position's slot of a [TILE, D] shared-memory tile, so the tile
+// IS the contiguous output block; one elected thread then writes the whole tile back with a single bulk store
+// (shared -> global).  Two tiles are in flight per CTA: the row reads of tile k+1 are issued before tile k is
+// waited for.  No registers hold data, the SM issues 2 copy instructions per position instead of ~20 load / store /
+// address instructions, and several hundred row reads per SM are outstanding at any time.
+CLSR_DEVINL uint32_t cvta_s(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+CLSR_DEVINL void g_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cvta_s(bar)), "r"(count));
+}
+CLSR_DEVINL void g_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cvta_s(bar)), "r"(bytes) : "memory");
+}
+CLSR_DEVINL void g_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "G_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra G_WAIT_DONE;\n"
+      "bra G_WAIT_LOOP;\n"
+      "G_WAIT_DONE:\n"
+      "}\n" ::"r"(cvta_s(bar)),
+      "r"(parity)
+      : "memory");
+}
+CLSR_DEVINL void g_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cvta_s(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(cvta_s(bar))
+               : "memory");
+}
+CLSR_DEVINL void g_bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(cvta_s(smem_src)), "r"(bytes)
+               : "memory");
+}
+
+constexpr int kGatherTile = 128;   // positions per tile = threads per CTA
+
+// `hot`: the lowest item ids (ids are popularity ranks, sequential_reviews.py:114-140; id 0 pads every window -- a third
+// of all positions) and category 0 are kept in shared memory per CTA and copied from there by the position's thread:
+// thousands of bulk reads of one row would otherwise queue on a single L2 slice (or one peer's NVLink port).
+__global__ void __launch_bounds__(kGatherTile)
+gather_hist_tma_kernel(const int32_t* __restrict__ ih, const int32_t* __restrict__ ch, int seq_stride, int T,
+                       TabView item_tab, TabView cate_tab, int Di, int Dc, int hot, float* __restrict__ out,
+                       long long npos) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  const int D = Di + Dc;
+  const uint32_t row_bytes = (uint32_t)D * 4, tile_bytes = row_bytes * kGatherTile;
+  float* tile[2] = {reinterpret_cast<float*>(gsm), reinterpret_cast<float*>(gsm + tile_bytes)};
+  float* hot_item = reinterpret_cast<float*>(gsm + 2 * (size_t)tile_bytes);   // [hot][Di]
+  float* hot_cate = hot_item + (size_t)hot * Di;                               // [Dc]: category 0
+  uint64_t* bar = reinterpret_cast<uint64_t*>(hot_cate + ((Dc + 3) & ~3));
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    g_mbar_init(&bar[0], kGatherTile);   // every thread arrives once per tile, announcing the bytes of its own bulk reads
+    g_mbar_init(&bar[1], kGatherTile);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < hot * Di; i += kGatherTile) hot_item[i] = __ldg(item_tab.row(i / Di, Di) + (i % Di));
+  for (int i = tid; i < Dc; i += kGatherTile) hot_cate[i] = __ldg(cate_tab.row(0, Dc) + i);
+  __syncthreads();
+  const long long ntiles = (npos + kGatherTile - 1) / kGatherTile;
+  auto issue = [&](long long tl, int buf) {
+    const long long p0 = tl * kGatherTile;
+    const int n = (int)(npos - p0 < kGatherTile ? npos - p0 : kGatherTile);
+    int idi = 0, idc = 0;
+    if (tid < n) {
+      const long long p = p0 + tid;
+      const long long sq = p / T;
+      const long long io = sq * seq_stride + (p - sq * T);
+      idi = __ldg(ih + io); idc = __ldg(ch + io);
+    }
+    const bool bi = tid < n && idi >= hot, bc = tid < n && idc != 0;
+    float* dst = tile[buf] + (size_t)tid * D;
+    if (tid < n && !bi) {
+      const float4* srcv = reinterpret_cast<const float4*>(hot_item + (size_t)idi * Di);
+      for (int q = 0; q < (Di >> 2); ++q) reinterpret_cast<float4*>(dst)[q] = srcv[q];
+    }
+    if (tid < n && !bc) {
+      const float4* srcv = reinterpret_cast<const float4*>(hot_cate);
+      for (int q = 0; q < (Dc >> 2); ++q) reinterpret_cast<float4*>(dst + Di)[q] = srcv[q];
+    }
+    // generic-proxy writes of the hot rows are ordered before the bulk store by this fence + the arrive below
+    if (tid < n && (!bi || !bc)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    g_mbar_expect_tx(&bar[buf], (bi ? (uint32_t)Di * 4 : 0u) + (bc ? (uint32_t)Dc * 4 : 0u));
+    if (bi) g_bulk_g2s(dst, item_tab.row(idi, Di), (uint32_t)Di * 4, &bar[buf]);
+    if (bc) g_bulk_g2s(dst + Di, cate_tab.row(idc, Dc), (uint32_t)Dc * 4, &bar[buf]);
+  };
+  int it = 0;
+  long long tl = blockIdx.x;
+  if (tl < ntiles) issue(tl, 0);
+  for (; tl < ntiles; tl += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const long long nxt = tl + gridDim.x;
+    if (nxt < ntiles) {
+      // the other buffer was handed to a bulk store one iteration ago: it may be refilled once that store has READ it
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncthreads();
+      issue(nxt, buf ^ 1);
+    }
+    if (tid == 0) {   // only the storing thread waits for the tile
+      g_mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
+      const long long p0 = tl * kGatherTile;
+      const int n = (int)(npos - p0 < kGatherTile ? npos - p0 : kGatherTile);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      g_bulk_s2g(out + (size_t)p0 * D, tile[buf], (uint32_t)n * row_bytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // out[r, col0 : col0+dim] = table[idx[r*idx_stride], :]   (targets, users)
 __global__ void gather_rows_kernel(const int32_t* __restrict__ idx, int idx_stride, TabView tab, int dim,
                                    float* __restrict__ out, int ldo, int col0, int rows) {
@@ -201,11 +314,14 @@ scatter_hist_kernel(const float* __restrict__ dX, const int32_t* __restrict__ ih
                     const int32_t* __restrict__ ch, int seq_stride, int T,
                     const int32_t* __restrict__ slot_i, const int32_t* __restrict__ slot_c,
                     float* __restrict__ gi, float* __restrict__ gc, int Di, int Dc, long long npos,
-                    double* __restrict__ sumsq) {
-  extern __shared__ float pad_acc[];  // [Di + Dc]
+                    double* __restrict__ sumsq, int hot) {
+  // hot: the lowest item ids (popularity ranks; id 0 = padding) and category 0 are summed per CTA in shared memory
+  // and leave the SM once per CTA -- thousands of reductions onto one row would serialise in L2
+  extern __shared__ float pad_acc[];  // [hot][Di] + [Dc]
   __shared__ float red[2][8];
   const int VI = Di >> 2, V = (Di + Dc) >> 2;
-  for (int i = threadIdx.x; i < Di + Dc; i += blockDim.x) pad_acc[i] = 0.f;
+  const int nacc = hot * Di + Dc;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) pad_acc[i] = 0.f;
   __syncthreads();
   const long long nvec = npos * V;
   float ssi = 0.f, ssc = 0.f;
@@ -217,23 +333,37 @@ scatter_hist_kernel(const float* __restrict__ dX, const int32_t* __restrict__ ih
     long long io = s * seq_stride + (p - s * T);
     float4 v = ldg_stream(reinterpret_cast<const float4*>(dX) + g);
     float sq = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    int id;
-    if (q < VI) { id = __ldg(ih + io); ssi += sq; } else { id = __ldg(ch + io); ssc += sq; }
-    if (id == 0) {
-      float* a = pad_acc + q * 4;
-      atomicAdd(a + 0, v.x); atomicAdd(a + 1, v.y); atomicAdd(a + 2, v.z); atomicAdd(a + 3, v.w);
-    } else if (q < VI) {
-      red_add_v4(gi + (size_t)slot_i[id] * Di + q * 4, v);
+    if (q < VI) {
+      const int id = __ldg(ih + io);
+      ssi += sq;
+      if (id < hot) {
+        float* a = pad_acc + id * Di + q * 4;
+        atomicAdd(a + 0, v.x); atomicAdd(a + 1, v.y); atomicAdd(a + 2, v.z); atomicAdd(a + 3, v.w);
+      } else {
+        red_add_v4(gi + (size_t)slot_i[id] * Di + q * 4, v);
+      }
     } else {
-      red_add_v4(gc + (size_t)slot_c[id] * Dc + (q - VI) * 4, v);
+      const int id = __ldg(ch + io);
+      ssc += sq;
+      if (id == 0) {
+        float* a = pad_acc + hot * Di + (q - VI) * 4;
+        atomicAdd(a + 0, v.x); atomicAdd(a + 1, v.y); atomicAdd(a + 2, v.z); atomicAdd(a + 3, v.w);
+      } else {
+        red_add_v4(gc + (size_t)slot_c[id] * Dc + (q - VI) * 4, v);
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < Di + Dc; i += blockDim.x) {
-    float v = pad_acc[i];
-    if (v != 0.f) {
-      if (i < Di) atomicAdd(gi + (size_t)slot_i[0] * Di + i, v);
-      else atomicAdd(gc + (size_t)slot_c[0] * Dc + (i - Di), v);
+  for (int i = threadIdx.x * 4; i < nacc; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(pad_acc + i);
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+    if (i < hot * Di) {
+      const int id = i / Di, c = i - id * Di;
+      const int sl = slot_i[id];
+      if (sl >= 0) red_add_v4(gi + (size_t)sl * Di + c, v);
+    } else {
+      const int sl = slot_c[0];
+      if (sl >= 0) red_add_v4(gc + (size_t)sl * Dc + (i - hot * Di), v);
     }
   }
   ssi = warp_sum(ssi); ssc = warp_sum(ssc);

@@ -72,6 +72,7 @@ struct clsr_engine {
   long long launches = 0;
   long long adam_step = 0;
   int num_sms = 148;
+  bool gather_attr_set = false;
   int rnn_wglob = 0;   // SIMT recurrences read their weights from global memory (they do not fit shared memory)
   int smem_optin = 49152;
   int tc_smem_max = 49152;
@@ -293,6 +294,46 @@ inline int grid1d(clsr_engine* e, long long n, int block, int per_sm = 8) {
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
+}
+
+// item rows pre-summed per CTA in shared memory by the scatter-add (16 KB of rows, at most 64)
+int scatter_hot_rows(const clsr_engine* e) {
+  int hot = (16 * 1024) / (e->Di * 4);
+  if (hot > 64) hot = 64;
+  if ((long long)hot > e->tab_rows[0]) hot = (int)e->tab_rows[0];
+  return hot < 1 ? 1 : hot;
+}
+
+// K1 + K3: history gather.  Bulk-copy (TMA) kernel when two [128, D] tiles fit shared memory (always for the
+// model widths in use); CLSR_GATHER_LDG=1 selects the register-path kernel (A/B).
+int launch_gather_hist(clsr_engine* e, const int32_t* ih, const int32_t* ch, int seq_stride, float* out, long long npos) {
+  static const bool ldg = getenv("CLSR_GATHER_LDG") != nullptr;
+  const int D = e->D;
+  int hot = (8 * 1024) / (e->Di * 4);   // lowest item ids kept in shared memory per CTA (8 KB)
+  if (hot > 64) hot = 64;
+  if ((long long)hot > e->tab_rows[0]) hot = (int)e->tab_rows[0];
+  if (hot < 1) hot = 1;
+  const size_t smem = 2 * (size_t)kGatherTile * D * 4 + ((size_t)hot * e->Di + ((e->Dc + 3) & ~3)) * 4 + 64;
+  if (!ldg && smem <= (size_t)e->smem_optin - 1024) {
+    int per_sm = (int)((size_t)(e->smem_optin) / (smem + 1024));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    long long tiles = (npos + kGatherTile - 1) / kGatherTile;
+    long long grid = (long long)e->num_sms * per_sm;
+    if (grid > tiles) grid = tiles;
+    if (!e->gather_attr_set) {
+      CK(cudaFuncSetAttribute(gather_hist_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      e->gather_attr_set = true;
+    }
+    gather_hist_tma_kernel<<<(int)grid, kGatherTile, smem, e->stream>>>(ih, ch, seq_stride, e->T, e->tview[CLSR_TABLE_ITEM],
+                                                                      e->tview[CLSR_TABLE_CATE], e->Di, e->Dc, hot, out, npos);
+  } else {
+    const long long nvec = npos * (D / 4);
+    gather_hist_kernel<4><<<grid1d(e, cdiv(nvec, 4), 256, 8), 256, 0, e->stream>>>(
+        ih, ch, seq_stride, e->T, e->tview[CLSR_TABLE_ITEM], e->tview[CLSR_TABLE_CATE], e->Di, e->Dc, out, npos);
+  }
+  POST("gather_hist");
+  return 0;
 }
 
 // ---- dense variable inventory (mirrors clsr_b200/params.py::dense_spec) ---------------------------
@@ -771,6 +812,17 @@ int dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& a, 
   if (M <= 0) return 0;
   if (tc_eligible(e, name, M, N, K, a, false) && K + (colsum ? 1 : 0) <= 128 && (N <= 240 || b.mode == A_PLAIN))
     return tc_dwgemm(e, name, M, K, N, a, b, dW, lddw, colsum);
+  if (tc_eligible(e, name, M, N, 120, a, false) && a.mode == A_PLAIN && (N <= 240 || b.mode == A_PLAIN)) {
+    // wide models: dW rows are independent -> chunks of <= 120 rows of dW (columns of A), one accumulator each
+    for (int k0 = 0; k0 < K; k0 += 120) {
+      const int kk = K - k0 < 120 ? K - k0 : 120;
+      AOp a2 = a;
+      a2.A = a.A + k0;
+      int rc = tc_dwgemm(e, name, M, kk, N, a2, b, dW + (size_t)k0 * lddw, lddw, k0 == 0 ? colsum : nullptr);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   int ty = cdiv(K, 64), tz = cdiv(N, 64);
   int want = (e->num_sms * 4) / (ty * tz);
   if (want < 1) want = 1;
@@ -1078,12 +1130,7 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
 
   // ---- K1+K3: embedding gathers ----
   float* X = e->B("X");
-  {
-    long long nvec = M * (D / 4);
-    gather_hist_kernel<4><<<grid1d(e, cdiv(nvec, 4), 256, 8), 256, 0, st>>>(
-        c.ih, c.ch, c.seq_stride, T, e->tview[CLSR_TABLE_ITEM], e->tview[CLSR_TABLE_CATE], Di, Dc, X, M);
-    POST("gather_hist");
-  }
+  if ((rc = launch_gather_hist(e, c.ih, c.ch, c.seq_stride, X, M))) return rc;
   float* tgt = e->B("tgt");
   float *ul = e->B("ul"), *us = e->B("us");
   {
@@ -1555,9 +1602,12 @@ int sparse_grads(clsr_engine* e, const StepCtx& c) {
     zero_compact_multi_kernel<<<e->num_sms * 2, 256, 0, st>>>(cm);
     POST("zero_compact");
   }
-  scatter_hist_kernel<<<e->num_sms * 4, 256, (size_t)D * 4, st>>>(dX, ih, ch, seq_stride, T, e->slot[0], e->slot[1],
-                                                                e->cg[0], e->cg[1], Di, Dc, M, e->sumsq);
-  POST("scatter_hist");
+  {
+    const int hot = scatter_hot_rows(e);
+    scatter_hist_kernel<<<e->num_sms * 4, 256, (size_t)(hot * Di + Dc) * 4, st>>>(dX, ih, ch, seq_stride, T, e->slot[0], e->slot[1],
+                                                                                e->cg[0], e->cg[1], Di, Dc, M, e->sumsq, hot);
+    POST("scatter_hist");
+  }
   {
     ScatterRowsMulti sm;
     sm.n = 4;
@@ -2309,10 +2359,8 @@ int clsr_staged_feed_read(clsr_engine* e, int32_t which, void* host_dst, int64_t
 int clsr_gather_history(clsr_engine* e, const int32_t* ih, const int32_t* ch, int64_t positions, float* out) {
   if (!e || !ih || !ch || !out || positions <= 0) return fail(e, CLSR_ERR_ARG, "bad argument");
   if (!e->tab[0] || !e->tab[1]) return fail(e, CLSR_ERR_STATE, "tables not bound");
-  long long nvec = positions * (e->D / 4);
-  gather_hist_kernel<4><<<grid1d(e, cdiv(nvec, 4), 256, 8), 256, 0, e->stream>>>(
-      ih, ch, e->T, e->T, e->tview[0], e->tview[1], e->Di, e->Dc, out, positions);
-  POST("gather_hist");
+  int rc = launch_gather_hist(e, ih, ch, e->T, out, positions);
+  if (rc) return rc;
   return CLSR_OK;
 }
 
@@ -2330,9 +2378,12 @@ int clsr_scatter_history_grad(clsr_engine* e, const int32_t* ih, const int32_t* 
   POST("zero_compact");
   zero_compact_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->cg[1], e->counts + 2, e->Dc);
   POST("zero_compact");
-  scatter_hist_kernel<<<e->num_sms * 4, 256, (size_t)e->D * 4, st>>>(d_hist, ih, ch, e->T, e->T, e->slot[0], e->slot[1], e->cg[0],
-                                                                  e->cg[1], e->Di, e->Dc, positions, e->sumsq);
-  POST("scatter_hist");
+  {
+    const int hot = scatter_hot_rows(e);
+    scatter_hist_kernel<<<e->num_sms * 4, 256, (size_t)(hot * e->Di + e->Dc) * 4, st>>>(
+        d_hist, ih, ch, e->T, e->T, e->slot[0], e->slot[1], e->cg[0], e->cg[1], e->Di, e->Dc, positions, e->sumsq, hot);
+    POST("scatter_hist");
+  }
   for (int i = 0; i < 2; ++i) {
     reset_slots_kernel<<<e->num_sms, 256, 0, st>>>(e->uniq[i], e->counts + 1 + i, e->slot[i]);
     POST("reset_slots");
