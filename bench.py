@@ -146,8 +146,9 @@ def ncu_traffic(name):
             continue
     if t is None:
         return None
-    for key in (name, {"adam_sweep": "adam_sweep (4 tables, one step)", "gather_hist": "gather_hist_kernel<4>",
-                       "scatter_hist": "scatter_hist_kernel"}.get(name)):
+    alias = {"adam_sweep": ("adam_sweep (4 tables, one step)",), "scatter_hist": ("clsr::scatter_hist_kernel", "scatter_hist_kernel"),
+             "gather_hist": ("clsr::gather_hist_tma_kernel", "gather_hist_tma_kernel", "gather_hist_kernel<4>")}
+    for key in (name,) + alias.get(name, ()):
         if key in t:
             return t[key].get("dram_bytes", t[key].get("dram_bytes_per_launch_mean"))
     return None
@@ -483,7 +484,10 @@ def run_b200(a):
         with open(a.profile_out, "w") as f:
             json.dump({"per_kernel": per_kernel, "ms_per_step": ms / a.steps}, f, indent=1)
     if world == 1 and not a.no_cpu_baseline and tabs is not None:
-        out["cpu_baseline"] = cpu_arm(a, w, dense, tabs, steps=8, warmup=2)
+        try:
+            out["cpu_baseline"] = cpu_arm(a, w, dense, tabs, steps=8, warmup=2)
+        except Exception as ex:   # the GPU numbers above must still be printed
+            out["cpu_baseline"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

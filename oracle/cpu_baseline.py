@@ -28,6 +28,7 @@ class CpuTrainer:
         self.m = {}
         self.v = {}
         self.step_no = 0
+        self.opt_seconds = 0.0   # time spent in the table optimizer (sparse Adam / lazy Adam)
 
     def _adam_dense(self, name, g, lr_t):
         c = self.cfg
@@ -54,6 +55,7 @@ class CpuTrainer:
             for k, t in p.items():
                 if t.requires_grad:
                     self._adam_dense(k, O._clip(t.grad, c), lr_t)
+            t_opt = time.perf_counter()
             for tab in O.TABLES:
                 name = O.EMB + tab
                 idx = torch.cat([ix for (tb, ix, rows) in leaves.values() if tb == tab])
@@ -77,6 +79,7 @@ class CpuTrainer:
                     v.mul_(c.beta2)
                     v.index_add_(0, uniq, gs * gs, alpha=1 - c.beta2)
                     var.addcdiv_(m, v.sqrt().add_(c.adam_eps), value=-lr_t)
+            self.opt_seconds += time.perf_counter() - t_opt
             for prefix, (mean, var_b) in out["bn_stats"].items():
                 for suffix, b in (("moving_mean", mean), ("moving_variance", var_b)):
                     mv = self.p[prefix + suffix]

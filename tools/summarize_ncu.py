@@ -49,12 +49,12 @@ def main(d, r):
         tot = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks)
         out["traffic"][name] = {"launches_captured": len(ks), "dram_bytes_per_launch_mean": tot / len(ks),
                                 "dram_bytes_sum": tot, "dur_us_sum": sum(k["dur_us"] for k in ks)}
-    ad = [k for n, ks in agg.items() if n.startswith("adam_sweep_kernel") for k in ks]
+    ad = [k for n, ks in agg.items() if "adam_sweep" in n for k in ks]
     out["traffic"]["adam_sweep (4 tables, one step)"] = {
         "dram_bytes": sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ad), "dur_us": sum(k["dur_us"] for k in ad)}
-    for src, dst in (("gather_hist_kernel<4>", "gather_hist_kernel<4>"), ("scatter_hist_kernel", "scatter_hist_kernel")):
-        if src in out["traffic"]:
-            out["traffic"][dst]["dram_bytes"] = out["traffic"][src]["dram_bytes_per_launch_mean"]
+    for src in list(out["traffic"]):
+        if "gather_hist" in src or "scatter_hist" in src:
+            out["traffic"][src]["dram_bytes"] = out["traffic"][src]["dram_bytes_per_launch_mean"]
     hdr, units, data = export("%s/%s_tc.ncu-rep" % (d, r))
     idx = {h: i for i, h in enumerate(hdr)}
     U = {h: units[i] for i, h in enumerate(hdr)}
@@ -67,7 +67,9 @@ def main(d, r):
                  issue_active_pct=num(row[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
                  regs=num(row[idx["launch__registers_per_thread"]]), grid=num(row[idx["launch__grid_size"]]),
                  smem_dyn_KB=num(row[idx["launch__shared_mem_per_block_dynamic"]]),
-                 lsu_wavefront_pct=num(row[idx["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"]]))
+                 lsu_wavefront_pct=num(row[idx["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"]]),
+                 tensor_pipe_pct=(num(row[idx["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]])
+                                  if "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active" in idx else None))
         k["dram_bytes"] = bps * k["dur_us"] / 1e6
         out["kernels"].append(k)
     tc = [k for k in out["kernels"] if k["set"] == "sections"]
