@@ -213,6 +213,8 @@ struct StageFeed {
   int32_t *o_ih, *o_ch, *o_mask, *o_users, *o_items, *o_cates;
   float *o_tfa, *o_ttn, *o_labels;
   int S, G, T, B;
+  int seq_g;   // rows between consecutive sequences in the [*,T] source arrays (G for a replicated feed, 1 when
+               // the copy engine has already picked every G-th row)
   long long n_items, n_cates, n_users;
   int32_t* err;
 };
@@ -222,7 +224,7 @@ __global__ void stage_device_feed_kernel(StageFeed a) {
   int bad = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
     const long long s = i / a.T;
-    const long long src = s * a.G * a.T + (i - s * a.T);
+    const long long src = s * a.seq_g * a.T + (i - s * a.T);
     int it = __ldg(a.ih + src), ct = __ldg(a.ch + src);
     if ((unsigned long long)(long long)it >= (unsigned long long)a.n_items) { bad |= 8; it = 0; }
     if ((unsigned long long)(long long)ct >= (unsigned long long)a.n_cates) { bad |= 16; ct = 0; }
@@ -436,7 +438,12 @@ __global__ void involved_kernel(const float* __restrict__ tab, const float* __re
 
 struct AdamHyper {
   float lr_t, beta1, beta2, eps, clip;  // clip <= 0: no clipping
+  const float* lr_dev;                  // when set, the step size is read from device memory (a replayed CUDA graph
+                                        // must not bake in a value that changes every step)
 };
+CLSR_DEVINL float adam_lr(const AdamHyper& hp) { return hp.lr_dev ? __ldg(hp.lr_dev) : hp.lr_t; }
+// one-thread kernel: per-step scalars travel in its launch parameters, outside the captured step
+__global__ void set_scalar_kernel(float* dst, float v) { *dst = v; }
 
 // TF's non-lazy sparse Adam: m and v decay and the variable moves on EVERY row;
 // rows present in the batch add their (clipped) compact gradient.  Pure streaming over
@@ -446,6 +453,7 @@ __global__ void __launch_bounds__(256)
 adam_sweep_kernel(float* __restrict__ var, float* __restrict__ m, float* __restrict__ v,
                   const int32_t* __restrict__ slot, const float* __restrict__ g, int dim, long long rows,
                   AdamHyper hp, const double* __restrict__ sumsq) {
+  const float lr_t = adam_lr(hp);
   const int V = dim >> 2;
   float scale = 1.f;
   if (hp.clip > 0.f) {
@@ -484,7 +492,7 @@ adam_sweep_kernel(float* __restrict__ var, float* __restrict__ m, float* __restr
 #define CLSR_ADAM1(c_)                                                      \
   mv[u].c_ = hp.beta1 * mv[u].c_ + (1.f - hp.beta1) * gv.c_;                \
   vv[u].c_ = hp.beta2 * vv[u].c_ + (1.f - hp.beta2) * gv.c_ * gv.c_;        \
-  xv[u].c_ -= hp.lr_t * mv[u].c_ / (sqrtf(vv[u].c_) + hp.eps);
+  xv[u].c_ -= lr_t * mv[u].c_ / (sqrtf(vv[u].c_) + hp.eps);
       CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
 #undef CLSR_ADAM1
       stg_stream(reinterpret_cast<float4*>(m) + i, mv[u]);
@@ -499,6 +507,7 @@ __global__ void adam_lazy_kernel(float* __restrict__ var, float* __restrict__ m,
                                  const int32_t* __restrict__ uniq, const int32_t* __restrict__ counter,
                                  const float* __restrict__ g, int dim, AdamHyper hp,
                                  const double* __restrict__ sumsq) {
+  const float lr_t = adam_lr(hp);
   const int V = dim >> 2;
   float scale = 1.f;
   if (hp.clip > 0.f) {
@@ -519,7 +528,7 @@ __global__ void adam_lazy_kernel(float* __restrict__ var, float* __restrict__ m,
 #define CLSR_ADAM1(c_)                                          \
   mv.c_ = hp.beta1 * mv.c_ + (1.f - hp.beta1) * gv.c_;          \
   vv.c_ = hp.beta2 * vv.c_ + (1.f - hp.beta2) * gv.c_ * gv.c_;  \
-  xv.c_ -= hp.lr_t * mv.c_ / (sqrtf(vv.c_) + hp.eps);
+  xv.c_ -= lr_t * mv.c_ / (sqrtf(vv.c_) + hp.eps);
     CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
     *reinterpret_cast<float4*>(m + off) = mv;
     *reinterpret_cast<float4*>(v + off) = vv;
@@ -657,6 +666,7 @@ struct SweepMulti { SweepSeg s[4]; int n; };
 template <int UN>
 __global__ void __launch_bounds__(256)
 adam_sweep_multi_kernel(const __grid_constant__ SweepMulti a, AdamHyper hp) {
+  const float lr_t = adam_lr(hp);
   for (int k = 0; k < a.n; ++k) {
     const SweepSeg& w = a.s[k];
     const int V = w.dim >> 2;
@@ -693,7 +703,7 @@ adam_sweep_multi_kernel(const __grid_constant__ SweepMulti a, AdamHyper hp) {
 #define CLSR_ADAM1(c_)                                                      \
   mv[u].c_ = hp.beta1 * mv[u].c_ + (1.f - hp.beta1) * gv.c_;                \
   vv[u].c_ = hp.beta2 * vv[u].c_ + (1.f - hp.beta2) * gv.c_ * gv.c_;        \
-  xv[u].c_ -= hp.lr_t * mv[u].c_ / (sqrtf(vv[u].c_) + hp.eps);
+  xv[u].c_ -= lr_t * mv[u].c_ / (sqrtf(vv[u].c_) + hp.eps);
         CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
 #undef CLSR_ADAM1
         stg_stream(reinterpret_cast<float4*>(w.m) + i, mv[u]);
@@ -789,6 +799,7 @@ __global__ void __launch_bounds__(256)
 adam_sweep_shard_kernel(float* __restrict__ var, float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
                         const int32_t* __restrict__ touched, int dim, long long rows, AdamHyper hp,
                         const double* __restrict__ sumsq) {
+  const float lr_t = adam_lr(hp);
   const int V = dim >> 2;
   float scale = 1.f;
   if (hp.clip > 0.f) {
@@ -823,7 +834,7 @@ adam_sweep_shard_kernel(float* __restrict__ var, float* __restrict__ m, float* _
 #define CLSR_ADAM1(c_)                                                      \
   mv[u].c_ = hp.beta1 * mv[u].c_ + (1.f - hp.beta1) * gv.c_;                \
   vv[u].c_ = hp.beta2 * vv[u].c_ + (1.f - hp.beta2) * gv.c_ * gv.c_;        \
-  xv[u].c_ -= hp.lr_t * mv[u].c_ / (sqrtf(vv[u].c_) + hp.eps);
+  xv[u].c_ -= lr_t * mv[u].c_ / (sqrtf(vv[u].c_) + hp.eps);
       CLSR_ADAM1(x) CLSR_ADAM1(y) CLSR_ADAM1(z) CLSR_ADAM1(w)
 #undef CLSR_ADAM1
       stg_stream(reinterpret_cast<float4*>(m) + i, mv[u]);
@@ -838,6 +849,7 @@ adam_sweep_shard_kernel(float* __restrict__ var, float* __restrict__ m, float* _
 __global__ void adam_lazy_shard_kernel(float* __restrict__ var, float* __restrict__ m, float* __restrict__ v,
                                        float* __restrict__ g, const int32_t* __restrict__ touched, int dim,
                                        long long rows, AdamHyper hp, const double* __restrict__ sumsq, int apply) {
+  const float lr_t = adam_lr(hp);
   float scale = 1.f;
   if (hp.clip > 0.f) {
     float nrm = (float)sqrt(*sumsq);
@@ -858,7 +870,7 @@ __global__ void adam_lazy_shard_kernel(float* __restrict__ var, float* __restric
           const float mv = hp.beta1 * m[row + k] + (1.f - hp.beta1) * gv;
           const float vv = hp.beta2 * v[row + k] + (1.f - hp.beta2) * gv * gv;
           m[row + k] = mv; v[row + k] = vv;
-          var[row + k] -= hp.lr_t * mv / (sqrtf(vv) + hp.eps);
+          var[row + k] -= lr_t * mv / (sqrtf(vv) + hp.eps);
         }
       }
     }

@@ -71,6 +71,23 @@ struct clsr_engine {
   std::map<std::string, std::pair<double, long long>> prof_agg;
   long long launches = 0;
   long long adam_step = 0;
+  float* d_lr = nullptr;    // [1] this step's Adam step size (written by set_scalar_kernel before the step body)
+  // Captured training steps (single GPU): one executable graph per (S, B, G, flags) shape.  The first step of a
+  // shape runs eagerly (lazy allocations, attribute calls), the second is captured, later ones are one graph launch.
+  struct StepGraph {
+    int S, B, G;
+    uint32_t flags;
+    int seen;
+    long long launches;
+    cudaGraphExec_t exec;
+  };
+  std::vector<StepGraph> graphs;
+  bool graphs_on = true;
+  long long graph_replays = 0;
+  // The legacy default stream cannot be captured: an engine bound to it records and launches its step graphs on this
+  // (blocking) stream and orders it against the default stream with two events per step.
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
   int num_sms = 148;
   bool gather_attr_set = false;
   int rnn_wglob = 0;   // SIMT recurrences read their weights from global memory (they do not fit shared memory)
@@ -128,6 +145,7 @@ struct clsr_engine {
   float *in_tfa, *in_ttn, *in_labels;
   char* h_stage = nullptr;  // pinned staging
   size_t h_stage_bytes = 0;
+  char* in_raw = nullptr;   // device landing block of feeds copied straight from pinned caller memory (stage_inputs)
   cudaEvent_t h2d_done = nullptr;  // the staging buffer may be rewritten once this has fired
   float* h_out = nullptr;  // pinned [2*Bmax]
   int staged_S = 0, staged_G = 1;   // shape of the batch clsr_build_batch left in the staged-feed block
@@ -628,7 +646,17 @@ int tma_streams(const AOp& a, int K) {
   auto ok = [](const float* p, int ld) { return p && !((uintptr_t)p & 15) && !(ld & 3); };
   if (a.mode == A_PLAIN || a.mode == A_BNRELU) return ok(a.A, a.lda) ? 1 : 0;
   if (a.mode == A_AFFINE2) return (ok(a.A, a.lda) && ok(a.A2, a.lda2)) ? 2 : 0;
+  // concatenation [rows | rows[:, off:] * per-sequence row]: both parts are column ranges of the same plain rows
+  static const bool cat_off = getenv("CLSR_NO_TMA_CATMUL") != nullptr;
+  if (a.mode == A_CATMUL && !cat_off)
+    return (ok(a.A, a.lda) && ok(a.A2, a.lda2) && !(a.W1 & 7) && !(a.off & 3) && K > a.W1) ? 1 : 0;
   return 0;
+}
+// Columns of the first operand stream the tensor map has to cover.
+int tmap_cols(const AOp& a, int K) {
+  if (a.mode != A_CATMUL) return K;
+  const int second = a.off + (K - a.W1);
+  return a.W1 > second ? a.W1 : second;
 }
 
 // One tcgen05 launch: K <= 160 (W resident in shared memory), N <= 256 (one UMMA, one TMEM accumulator).
@@ -659,7 +687,7 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   if (!fits) return fail(e, CLSR_ERR_ARG, "tc_gemm %s: K=%d N=%d does not fit shared memory", name, K, N);
   CUtensorMap tmA, tmA2;
   memset(&tmA2, 0, sizeof tmA2);
-  if (tma >= 1 && !make_tmap(&tmA, a.A, K, M, a.lda)) tma = 0;
+  if (tma >= 1 && !make_tmap(&tmA, a.A, tmap_cols(a, K), M, a.lda)) tma = 0;
   if (tma == 2 && !make_tmap(&tmA2, a.A2, K, M, a.lda2)) tma = 0;
   if (!tma) {
     memset(&tmA, 0, sizeof tmA);
@@ -750,7 +778,21 @@ int gemm(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, co
 // dW on tensor cores; N is cut into column slabs of at most 240.
 int tc_dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& a, const AOp& b, float* dW,
               int lddw, float* colsum) {
-  const int nslab = cdiv(N, 240);
+  // columns of A that are stored (the MMA's remaining lanes alias what follows; CLSR_DW_FULL_A=1 stores all 128: A/B switch)
+  static const bool full_a = getenv("CLSR_DW_FULL_A") != nullptr;
+  const int acols = full_a ? 128 : (colsum ? K + 1 : K);
+  // Column slabs of B: as few as possible (<= 240 columns: one TMEM accumulator), but when B is a plain matrix take
+  // more of them if that is what lets TWO stages with TMA loads fit shared memory -- a single-staged slab loop
+  // serialises load, conversion and MMA (dWx, 480 columns: 3 slabs of 160 instead of 2 of 240).
+  int nslab = cdiv(N, 240);
+  if (b.mode == A_PLAIN) {
+    for (int ns = nslab; ns <= nslab + 2; ++ns) {
+      const int p8 = ((cdiv(N, ns) + 7) / 8) * 8;
+      AOp bs = b;
+      const int tb0 = tma_streams(bs, p8);
+      if (tc::dw_smem_layout(K, acols, p8, round16(p8), 2, tma_streams(a, K), tb0).total <= e->tc_dw_smem_max) { nslab = ns; break; }
+    }
+  }
   const int per = ((cdiv(N, nslab) + 7) / 8) * 8;
   for (int n0 = 0; n0 < N; n0 += per) {
     int nn = N - n0 < per ? N - n0 : per;
@@ -768,18 +810,18 @@ int tc_dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& 
     bool fits = false;
     for (int ci = 0; ci < 6; ++ci) {
       const int* c = cand[ci];
-      L = tc::dw_smem_layout(K, nn, npad, c[0], c[1], c[2]);
+      L = tc::dw_smem_layout(K, acols, nn, npad, c[0], c[1], c[2]);
       if (L.total <= e->tc_dw_smem_max) { nstages = c[0]; ta = c[1]; tb = c[2]; fits = true; break; }
     }
     if (!fits) return fail(e, CLSR_ERR_ARG, "tc_dwgemm %s: N slab %d does not fit", name, nn);
     CUtensorMap tmA, tmA2, tmB, tmB2;
     memset(&tmA, 0, sizeof tmA); memset(&tmA2, 0, sizeof tmA2); memset(&tmB, 0, sizeof tmB); memset(&tmB2, 0, sizeof tmB2);
     bool okm = true;
-    if (ta >= 1) okm = okm && make_tmap(&tmA, a.A, K, M, a.lda);
+    if (ta >= 1) okm = okm && make_tmap(&tmA, a.A, tmap_cols(a, K), M, a.lda);
     if (ta == 2) okm = okm && make_tmap(&tmA2, a.A2, K, M, a.lda2);
-    if (tb >= 1) okm = okm && make_tmap(&tmB, b2.A, nn, M, b2.lda);
+    if (tb >= 1) okm = okm && make_tmap(&tmB, b2.A, tmap_cols(b2, nn), M, b2.lda);
     if (tb == 2) okm = okm && make_tmap(&tmB2, b2.A2, nn, M, b2.lda2);
-    if (!okm) { ta = tb = 0; L = tc::dw_smem_layout(K, nn, npad, nstages, 0, 0); }
+    if (!okm) { ta = tb = 0; L = tc::dw_smem_layout(K, acols, nn, npad, nstages, 0, 0); }
     uint32_t cols = 32;
     while ((int)cols < npad) cols <<= 1;
     int tiles = cdiv(M, tc::kTileM);
@@ -787,7 +829,7 @@ int tc_dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& 
     if (e->dw_grouping && e->dwg.n < tc::kDwGroupMax) {
       // deferred: becomes one problem of the next grouped launch (dw_group_flush)
       tc::DwProblem& P = e->dwg.p[e->dwg.n];
-      P.M = M; P.K = K; P.N = nn; P.npad = npad; P.nstages = nstages; P.tma_a = ta; P.tma_b = tb; P.lddw = lddw;
+      P.M = M; P.K = K; P.acols = acols; P.N = nn; P.npad = npad; P.nstages = nstages; P.tma_a = ta; P.tma_b = tb; P.lddw = lddw;
       P.octa = tc::dw_split(tc::kDwProducers / 8, ((colsum ? K + 1 : K) + 7) / 8, (nn + 7) / 8, tc::piece_cost(a.mode),
                             tc::piece_cost(b2.mode));
       P.tmem_cols = cols; P.a = a; P.b = b2; P.dW = dW + n0; P.colsum = colsum ? colsum + n0 : nullptr;
@@ -800,7 +842,7 @@ int tc_dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& 
     }
     const int octa = tc::dw_split(tc::kDwProducers / 8, ((colsum ? K + 1 : K) + 7) / 8, (nn + 7) / 8, tc::piece_cost(a.mode),
                                   tc::piece_cost(b2.mode));
-    tc::tc_dw_kernel<<<grid, tc::kDwThreads, L.total, e->stream>>>(M, K, nn, npad, nstages, cols, ta, tb, octa, a, b2, dW + n0, lddw,
+    tc::tc_dw_kernel<<<grid, tc::kDwThreads, L.total, e->stream>>>(M, K, acols, nn, npad, nstages, cols, ta, tb, octa, a, b2, dW + n0, lddw,
                                                                  colsum ? colsum + n0 : nullptr, tmA, tmA2, tmB, tmB2);
     POST(name);
   }
@@ -999,7 +1041,7 @@ struct StepCtx {
 };
 
 // Copy (host) or alias (device) the feed arrays.
-int stage_inputs(clsr_engine* e, const clsr_batch* b, StepCtx* c, bool need_labels) {
+int stage_inputs(clsr_engine* e, const clsr_batch* b, StepCtx* c, bool need_labels, bool sync_call) {
   const int T = e->T;
   c->B = b->rows; c->G = b->group; c->S = b->rows / b->group; c->T = T;
   // device layout of the staged block: [ih | ch | mask | tfa | ttn | users | items | cates | labels]
@@ -1029,7 +1071,7 @@ int stage_inputs(clsr_engine* e, const clsr_batch* b, StepCtx* c, bool need_labe
     a.o_tfa = const_cast<float*>(c->tfa); a.o_ttn = const_cast<float*>(c->ttn); a.o_users = const_cast<int32_t*>(c->users);
     a.o_items = const_cast<int32_t*>(c->items); a.o_cates = const_cast<int32_t*>(c->cates);
     a.o_labels = const_cast<float*>(c->labels);
-    a.S = S; a.G = G; a.T = T; a.B = B;
+    a.S = S; a.G = G; a.T = T; a.B = B; a.seq_g = G;
     a.n_items = e->cfg.n_items; a.n_cates = e->cfg.n_cates; a.n_users = e->cfg.n_users;
     a.err = e->d_err;
     CK(cudaMemsetAsync(e->d_err, 0, sizeof(int32_t), e->stream));
@@ -1038,8 +1080,54 @@ int stage_inputs(clsr_engine* e, const clsr_batch* b, StepCtx* c, bool need_labe
     CK(cudaMemcpyAsync(e->h_err, e->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     return 0;
   }
-  // Host feed: pack only what the step reads (one row per sequence) into pinned staging, validate the ids
-  // against the table sizes, then a single async H2D copy.
+  // Host feed in pinned (page-locked / registered) caller memory, synchronous call: the copy engine picks every
+  // G-th row itself (2-D copies, source pitch G*T*4) -- no host-side packing pass over the feed; the ids are
+  // validated on the device by the same kernel that stages device-resident feeds.  Only when the caller waits for
+  // the step (its buffers are then guaranteed to outlive the copies).
+  static const bool no_direct = getenv("CLSR_NO_DIRECT_H2D") != nullptr;
+  if (sync_call && !no_direct && e->in_raw) {
+    auto pinned = [](const void* p) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+      return at.type == cudaMemoryTypeHost;
+    };
+    bool all = pinned(b->item_history) && pinned(b->cate_history) && pinned(b->mask) && pinned(b->time_from_first_action) &&
+               pinned(b->time_to_now) && pinned(b->users) && pinned(b->items) && pinned(b->cates) &&
+               (!need_labels || !b->labels || pinned(b->labels));
+    if (all) {
+      char* r = e->in_raw;
+      const void* seqs[5] = {b->item_history, b->cate_history, b->mask, b->time_from_first_action, b->time_to_now};
+      for (int k = 0; k < 5; ++k)
+        CK(cudaMemcpy2DAsync(r + k * seq_i, (size_t)T * 4, seqs[k], (size_t)G * T * 4, (size_t)T * 4, S, cudaMemcpyHostToDevice,
+                             e->stream));
+      char* rb = r + 5 * seq_i;
+      const size_t bb = (size_t)B * 4;
+      CK(cudaMemcpyAsync(rb, b->users, bb, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(rb + bb, b->items, bb, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(rb + 2 * bb, b->cates, bb, cudaMemcpyHostToDevice, e->stream));
+      const bool lab = need_labels && b->labels;
+      if (lab) CK(cudaMemcpyAsync(rb + 3 * bb, b->labels, bb, cudaMemcpyHostToDevice, e->stream));
+      StageFeed a;
+      a.ih = (const int32_t*)r; a.ch = (const int32_t*)(r + seq_i); a.mask = (const int32_t*)(r + 2 * seq_i);
+      a.tfa = (const float*)(r + 3 * seq_i); a.ttn = (const float*)(r + 4 * seq_i);
+      a.users = (const int32_t*)rb; a.items = (const int32_t*)(rb + bb); a.cates = (const int32_t*)(rb + 2 * bb);
+      a.labels = lab ? (const float*)(rb + 3 * bb) : nullptr;
+      a.o_ih = const_cast<int32_t*>(c->ih); a.o_ch = const_cast<int32_t*>(c->ch); a.o_mask = const_cast<int32_t*>(c->mask);
+      a.o_tfa = const_cast<float*>(c->tfa); a.o_ttn = const_cast<float*>(c->ttn); a.o_users = const_cast<int32_t*>(c->users);
+      a.o_items = const_cast<int32_t*>(c->items); a.o_cates = const_cast<int32_t*>(c->cates);
+      a.o_labels = const_cast<float*>(c->labels);
+      a.S = S; a.G = G; a.T = T; a.B = B; a.seq_g = 1;
+      a.n_items = e->cfg.n_items; a.n_cates = e->cfg.n_cates; a.n_users = e->cfg.n_users;
+      a.err = e->d_err;
+      CK(cudaMemsetAsync(e->d_err, 0, sizeof(int32_t), e->stream));
+      stage_device_feed_kernel<<<grid1d(e, (long long)S * T, 256, 4), 256, 0, e->stream>>>(a);
+      POST("stage_host_feed");
+      CK(cudaMemcpyAsync(e->h_err, e->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      return 0;
+    }
+  }
+  // Host feed in pageable memory (or an asynchronous call): pack only what the step reads (one row per sequence) into
+  // pinned staging, validate the ids against the table sizes, then a single async H2D copy.
   size_t need = 5 * seq_i + (size_t)S * 4 + (size_t)B * 4 * 3;
   if (need > e->h_stage_bytes) return fail(e, CLSR_ERR_ARG, "batch exceeds staging capacity");
   CK(cudaEventSynchronize(e->h2d_done));
@@ -1664,7 +1752,7 @@ int sparse_grads(clsr_engine* e, const StepCtx& c) {
 
 // Sharded mode: zero the touched marks (and, after a gradient-only step, the gradient rows) of the owner's shards.
 int shard_cleanup(clsr_engine* e, bool grads_too) {
-  AdamHyper hz = {0.f, 0.f, 0.f, 1.f, 0.f};
+  AdamHyper hz = {0.f, 0.f, 0.f, 1.f, 0.f, nullptr};
   for (int t = 0; t < 4; ++t) {
     const int tt = t == 3 ? 2 : t;   // the two user tables share one touched array
     if (grads_too) {
@@ -1680,13 +1768,12 @@ int shard_cleanup(clsr_engine* e, bool grads_too) {
 int optimizer_step(clsr_engine* e) {
   cudaStream_t st = e->stream;
   const clsr_config& cf = e->cfg;
-  e->adam_step += 1;
-  double t = (double)e->adam_step;
-  float lr_t = (float)(cf.learning_rate * sqrt(1.0 - pow((double)cf.beta2, t)) / (1.0 - pow((double)cf.beta1, t)));
-  AdamDense hd = {lr_t, cf.beta1, cf.beta2, cf.adam_eps, cf.clip_norm ? cf.max_grad_norm : 0.f};
+  // the step size of this step sits in e->d_lr (step_scalars)
+  const float lr_t = 0.f;
+  AdamDense hd = {lr_t, cf.beta1, cf.beta2, cf.adam_eps, cf.clip_norm ? cf.max_grad_norm : 0.f, e->d_lr};
   dense_adam_kernel<<<(int)e->dense.size(), 1024, 0, st>>>(e->d_vars, e->P, e->Pm, e->Pv, e->Pg, e->d_norms, hd);
   POST("dense_adam");
-  AdamHyper hp = {lr_t, cf.beta1, cf.beta2, cf.adam_eps, cf.clip_norm ? cf.max_grad_norm : 0.f};
+  AdamHyper hp = {lr_t, cf.beta1, cf.beta2, cf.adam_eps, cf.clip_norm ? cf.max_grad_norm : 0.f, e->d_lr};
   const int slot_ix[4] = {0, 1, 2, 2}, cnt_ix[4] = {1, 2, 3, 3};
   for (int tb = 0; tb < 4; ++tb)
     if (!e->tab_m[tb] || !e->tab_v[tb]) return fail(e, CLSR_ERR_STATE, "Adam slots of table %d not bound", tb);
@@ -1755,6 +1842,12 @@ int zero_step_state(clsr_engine* e) {
   }
   MARK("zero_state");
   return 0;
+}
+
+void drop_graphs(clsr_engine* e) {
+  for (auto& g : e->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
 }
 
 }  // namespace
@@ -1891,6 +1984,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
   CKC(dalloc(e, &e->sumsq, 4));
   CKC(dalloc(e, &e->acc, 16));
   CKC(dalloc(e, &e->d_losses, 16));
+  CKC(dalloc(e, &e->d_lr, 4));
   CKC(dalloc(e, &e->d_clip_steps, 1));
   CKCU(cudaMallocHost((void**)&e->h_losses, 16 * sizeof(float)));
   CKCU(cudaMallocHost((void**)&e->h_out, (size_t)2 * Bm * sizeof(float)));
@@ -1906,6 +2000,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
     e->in_ih = (int32_t*)blk;
     e->h_stage_bytes = bytes;
     CKCU(cudaMallocHost((void**)&e->h_stage, bytes));
+    CKC(dalloc(e, &e->in_raw, (long long)((size_t)5 * M * 4 + (size_t)Bm * 4 * 4), false));
     CKCU(cudaEventCreateWithFlags(&e->h2d_done, cudaEventDisableTiming));
     CKC(dalloc(e, &e->d_len, Sm));
   }
@@ -1941,6 +2036,7 @@ void clsr_destroy(clsr_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  drop_graphs(e);
   if (e->comm && e->ncclCommDestroy_) e->ncclCommDestroy_(e->comm);
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   for (void* p : e->peer_opened) cudaIpcCloseMemHandle(p);
@@ -1957,12 +2053,17 @@ void clsr_destroy(clsr_engine* e) {
   }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_memset) cudaEventDestroy(e->ev_memset);
+  if (e->gstream) cudaStreamDestroy(e->gstream);
+  if (e->ev_g0) cudaEventDestroy(e->ev_g0);
+  if (e->ev_g1) cudaEventDestroy(e->ev_g1);
   delete e;
 }
 
 int clsr_set_stream(clsr_engine* e, void* s) {
   if (!e) return CLSR_ERR_ARG;
-  if (e->own_stream && e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  drop_graphs(e);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   e->stream = (cudaStream_t)s;
   e->own_stream = false;
   return CLSR_OK;
@@ -2010,11 +2111,20 @@ int clsr_bind_table(clsr_engine* e, int32_t t, float* values, float* m, float* v
   if (!e || t < 0 || t >= CLSR_NUM_TABLES || !values) return fail(e, CLSR_ERR_ARG, "bad table binding");
   if (((uintptr_t)values | (uintptr_t)m | (uintptr_t)v) & 15) return fail(e, CLSR_ERR_ARG, "table pointers must be 16-byte aligned");
   if (e->sharded) return fail(e, CLSR_ERR_STATE, "tables are row-sharded and engine-owned (clsr_table_local)");
+  if (e->tab[t] != values || e->tab_m[t] != m || e->tab_v[t] != v) drop_graphs(e);   // captured steps hold the old pointers
   e->tab[t] = values; e->tab_m[t] = m; e->tab_v[t] = v;
   memset(&e->tview[t], 0, sizeof(TabView));
   e->tview[t].p[0] = values;
   return CLSR_OK;
 }
+int clsr_set_graphs(clsr_engine* e, int32_t on) {
+  if (!e) return CLSR_ERR_ARG;
+  if (e->stream) CK(cudaStreamSynchronize(e->stream));
+  if (!on) drop_graphs(e);
+  e->graphs_on = on != 0;
+  return CLSR_OK;
+}
+int64_t clsr_graph_replays(const clsr_engine* e) { return e ? e->graph_replays : 0; }
 int clsr_set_adam_step(clsr_engine* e, int64_t s) { if (!e) return CLSR_ERR_ARG; e->adam_step = s; return CLSR_OK; }
 int64_t clsr_get_adam_step(const clsr_engine* e) { return e ? e->adam_step : -1; }
 int clsr_set_debug_sync(clsr_engine* e, int32_t on) { if (!e) return CLSR_ERR_ARG; e->debug_sync = on != 0; return CLSR_OK; }
@@ -2050,13 +2160,25 @@ int clsr_train_step(clsr_engine* e, const clsr_batch* batch, uint32_t flags, cls
   e->launches = 0;
   StepCtx c;
   MARK("(step begin)");
-  if ((rc = stage_inputs(e, batch, &c, true))) return rc;
+  if ((rc = stage_inputs(e, batch, &c, true, out != nullptr))) return rc;
   MARK("h2d_inputs");
   return train_after_stage(e, c, flags, out);
 }
 
-// Everything after the feed is staged (by stage_inputs or by clsr_build_batch).
-static int train_after_stage(clsr_engine* e, const StepCtx& c, uint32_t flags, clsr_losses* out) {
+// The values that change every step and must therefore stay out of a captured graph: Adam's step count.
+static int step_scalars(clsr_engine* e, uint32_t flags) {
+  if (flags & CLSR_STEP_NO_OPTIMIZER) return 0;
+  const clsr_config& cf = e->cfg;
+  e->adam_step += 1;
+  const double t = (double)e->adam_step;
+  const float lr_t = (float)(cf.learning_rate * sqrt(1.0 - pow((double)cf.beta2, t)) / (1.0 - pow((double)cf.beta1, t)));
+  set_scalar_kernel<<<1, 1, 0, e->stream>>>(e->d_lr, lr_t);
+  POST("step_scalars");
+  return 0;
+}
+
+// The step proper: only engine-owned buffers, shape-constant launch parameters -> capturable.
+static int step_body(clsr_engine* e, const StepCtx& c, uint32_t flags) {
   int rc;
   if ((rc = zero_step_state(e))) return rc;
   // sharded tables: peers must have finished the previous step's optimizer (and its touched / gradient clean-up)
@@ -2089,6 +2211,82 @@ static int train_after_stage(clsr_engine* e, const StepCtx& c, uint32_t flags, c
   if (e->sharded && (rc = shard_cleanup(e, (flags & CLSR_STEP_NO_OPTIMIZER) != 0))) return rc;
   if ((rc = reset_slots(e))) return rc;
   CK(cudaMemcpyAsync(e->h_losses, e->d_losses, 9 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  return 0;
+}
+
+// Run the step body eagerly, or (single GPU, no per-kernel events) as one graph launch.
+static int run_step(clsr_engine* e, const StepCtx& c, uint32_t flags) {
+  static const bool env_off = getenv("CLSR_NO_GRAPH") != nullptr;
+  const bool can = e->graphs_on && !env_off && e->world == 1 && !e->profiling && !e->debug_sync;
+  if (!can) return step_body(e, c, flags);
+  clsr_engine::StepGraph* g = nullptr;
+  for (auto& x : e->graphs)
+    if (x.S == c.S && x.B == c.B && x.G == c.G && x.flags == flags) { g = &x; break; }
+  if (!g) {
+    if (e->graphs.size() >= 16) drop_graphs(e);   // a stream of odd shapes: start over rather than grow
+    e->graphs.push_back({c.S, c.B, c.G, flags, 0, 0, nullptr});
+    g = &e->graphs.back();
+  }
+  cudaStream_t user = e->stream, cap = e->stream;
+  if (user == nullptr || user == cudaStreamLegacy) {
+    if (!e->gstream) {
+      bool okc = cudaStreamCreate(&e->gstream) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&e->ev_g0, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&e->ev_g1, cudaEventDisableTiming) == cudaSuccess;
+      if (!okc) { cudaGetLastError(); e->graphs_on = false; return step_body(e, c, flags); }
+    }
+    cap = e->gstream;
+  } else if (user == cudaStreamPerThread) {
+    return step_body(e, c, flags);
+  }
+  auto launch = [&](cudaGraphExec_t x) -> int {
+    if (cap != user) {   // default-stream engine: staged feed / scalars -> graph -> whatever the caller enqueues next
+      CK(cudaEventRecord(e->ev_g0, user));
+      CK(cudaStreamWaitEvent(cap, e->ev_g0, 0));
+    }
+    CK(cudaGraphLaunch(x, cap));
+    if (cap != user) {
+      CK(cudaEventRecord(e->ev_g1, cap));
+      CK(cudaStreamWaitEvent(user, e->ev_g1, 0));
+    }
+    e->graph_replays++;
+    return 0;
+  };
+  if (g->exec) {
+    e->launches += g->launches;
+    return launch(g->exec);
+  }
+  if (g->seen++ == 0) return step_body(e, c, flags);   // first step of this shape: eager
+  // second step of this shape: capture it (relaxed mode: the body may call non-stream APIs such as tensor-map
+  // encoding), then launch the instantiated graph.  Any failure turns graphs off for this engine and runs eagerly.
+  const long long l0 = e->launches;
+  cudaGraph_t graph = nullptr;
+  bool ok = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+  int rc = 0;
+  if (ok) {
+    e->stream = cap;
+    rc = step_body(e, c, flags);
+    e->stream = user;
+    ok = cudaStreamEndCapture(cap, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
+  }
+  if (ok) ok = cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {
+    cudaGetLastError();
+    g->exec = nullptr;
+    e->graphs_on = false;
+    e->launches = l0;
+    return step_body(e, c, flags);
+  }
+  g->launches = e->launches - l0;
+  return launch(g->exec);
+}
+
+// Everything after the feed is staged (by stage_inputs or by clsr_build_batch).
+static int train_after_stage(clsr_engine* e, const StepCtx& c, uint32_t flags, clsr_losses* out) {
+  int rc;
+  if ((rc = step_scalars(e, flags))) return rc;
+  if ((rc = run_step(e, c, flags))) return rc;
   if (out) {
     CK(cudaStreamSynchronize(e->stream));
     if ((rc = check_feed_flags(e))) return rc;
@@ -2100,12 +2298,12 @@ static int train_after_stage(clsr_engine* e, const StepCtx& c, uint32_t flags, c
 }
 
 // Inference forward on the staged feed; leaves sigmoid(logit) in the "pred" buffer and alpha in "alpha".
-static int predict_forward(clsr_engine* e, const clsr_batch* batch, StepCtx* c) {
+static int predict_forward(clsr_engine* e, const clsr_batch* batch, StepCtx* c, bool sync_call) {
   int rc;
   CK(cudaSetDevice(e->cfg.device));
   if ((rc = check_batch(e, batch, false))) return rc;
   e->launches = 0;
-  if ((rc = stage_inputs(e, batch, c, false))) return rc;
+  if ((rc = stage_inputs(e, batch, c, false, sync_call))) return rc;
   CK(cudaMemsetAsync(e->counts, 0, 8 * sizeof(int32_t), e->stream));
   // sharded tables: a collective call -- peers must have finished updating the rows this rank is about to read
   if (e->sharded && (rc = peer_reduce(e, nullptr, 0, nullptr, 0, nullptr, 0))) return rc;
@@ -2120,7 +2318,7 @@ int clsr_predict(clsr_engine* e, const clsr_batch* batch, float* pred, float* al
   if (!pred) return fail(e, CLSR_ERR_ARG, "null pred buffer");
   int rc;
   StepCtx c;
-  if ((rc = predict_forward(e, batch, &c))) return rc;
+  if ((rc = predict_forward(e, batch, &c, true))) return rc;
   const int B = c.B;
   CK(cudaMemcpyAsync(e->h_out, e->B("pred"), (size_t)B * 4, cudaMemcpyDeviceToHost, e->stream));
   if (alpha) CK(cudaMemcpyAsync(e->h_out + e->Bmax, e->B("alpha"), (size_t)B * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -2136,7 +2334,7 @@ int clsr_predict_device(clsr_engine* e, const clsr_batch* batch, float* dev_pred
   if (!dev_pred) return fail(e, CLSR_ERR_ARG, "null pred buffer");
   int rc;
   StepCtx c;
-  if ((rc = predict_forward(e, batch, &c))) return rc;
+  if ((rc = predict_forward(e, batch, &c, false))) return rc;
   CK(cudaMemcpyAsync(dev_pred, e->B("pred"), (size_t)c.B * 4, cudaMemcpyDeviceToDevice, e->stream));
   if (dev_alpha) CK(cudaMemcpyAsync(dev_alpha, e->B("alpha"), (size_t)c.B * 4, cudaMemcpyDeviceToDevice, e->stream));
   return CLSR_OK;

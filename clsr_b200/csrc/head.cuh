@@ -429,6 +429,7 @@ __global__ void dense_l2_norm_kernel(const DenseVar* __restrict__ vars, const fl
 
 struct AdamDense {
   float lr_t, beta1, beta2, eps, clip;
+  const float* lr_dev;   // see AdamHyper
 };
 
 __global__ void dense_adam_kernel(const DenseVar* __restrict__ vars, float* __restrict__ w,
@@ -436,6 +437,7 @@ __global__ void dense_adam_kernel(const DenseVar* __restrict__ vars, float* __re
                                   const float* __restrict__ g, const float* __restrict__ norms, AdamDense hp) {
   const DenseVar v = vars[blockIdx.x];
   if (!v.trainable) return;
+  const float lr_t = hp.lr_dev ? __ldg(hp.lr_dev) : hp.lr_t;
   float scale = 1.f;
   if (hp.clip > 0.f) scale = hp.clip / fmaxf(sqrtf(norms[blockIdx.x]), hp.clip);
   for (int i = threadIdx.x; i < v.n; i += blockDim.x) {
@@ -444,7 +446,7 @@ __global__ void dense_adam_kernel(const DenseVar* __restrict__ vars, float* __re
     float mv = hp.beta1 * m[o] + (1.f - hp.beta1) * gv;
     float vv = hp.beta2 * v2[o] + (1.f - hp.beta2) * gv * gv;
     m[o] = mv; v2[o] = vv;
-    w[o] -= hp.lr_t * mv / (sqrtf(vv) + hp.eps);
+    w[o] -= lr_t * mv / (sqrtf(vv) + hp.eps);
   }
 }
 

@@ -396,9 +396,11 @@ CLSR_DEVINL void produce_fast(const AOp& a, const float* sv, int svld, int m0, i
 // rows: A_PLAIN, A_BNRELU, A_AFFINE2 with the second stream in raw2).  Same plane ownership as
 // produce_fast.  The eight threads of an octet read their block's 256 raw bytes, synchronise among
 // themselves, then overwrite the block with its hi / lo core matrices.
+// A_CATMUL: the loader delivers columns [0, W1) of the rows and, a second time, columns [off, off + K - W1) into the
+// planes of the second part; those are multiplied here by the row of the small per-sequence operand (L1 / L2 resident).
 template <int MODE>
-CLSR_DEVINL void convert_tile(const float* sv, int svld, int m0, int M, int nfull, int ptid, int nprod, uint32_t base,
-                              uint32_t raw2) {
+CLSR_DEVINL void convert_tile(const AOp& a, const float* sv, int svld, int m0, int M, int nfull, int ptid, int nprod,
+                              uint32_t base, uint32_t raw2) {
   const int noct = nprod >> 3;
   const int per = noct / nfull;
   const int o = ptid >> 3, rl = ptid & 7;
@@ -421,6 +423,7 @@ CLSR_DEVINL void convert_tile(const float* sv, int svld, int m0, int M, int nful
   const uint32_t step = (uint32_t)per * 256;
   uint32_t off = (uint32_t)(cc * kPlaneBytes + ro0 * 256);
   constexpr int UN = 2;
+  const bool second = MODE == A_CATMUL && k0 >= a.W1;   // thread-constant: one plane per octet
 #pragma unroll 1
   for (int ro = ro0; ro < 16; ro += per * UN, off += step * UN) {
     float4 a0[UN], a1[UN], b0[UN], b1[UN];
@@ -430,6 +433,16 @@ CLSR_DEVINL void convert_tile(const float* sv, int svld, int m0, int M, int nful
       const uint32_t o2 = off + (ro + u * per < 16 ? u * step : 0) + rl * 32;
       a0[u] = lds4(base + o2); a1[u] = lds4(base + o2 + 16);
       if (MODE == A_AFFINE2) { b0[u] = lds4(raw2 + o2); b1[u] = lds4(raw2 + o2 + 16); }
+      if (MODE == A_CATMUL) {
+        if (second) {
+          int m = m0 + (ro + (ro + u * per < 16 ? u * per : 0)) * 8 + rl;
+          m = m < M ? m : M - 1;
+          const float4* hp = reinterpret_cast<const float4*>(a.A2 + (size_t)(m / a.T) * a.lda2 + (k0 - a.W1));
+          b0[u] = __ldg(hp); b1[u] = __ldg(hp + 1);
+        } else {
+          b0[u] = make_float4(1.f, 1.f, 1.f, 1.f); b1[u] = b0[u];
+        }
+      }
     }
     __syncwarp(omask);
 #pragma unroll
@@ -443,6 +456,10 @@ CLSR_DEVINL void convert_tile(const float* sv, int svld, int m0, int M, int nful
       } else if (MODE == A_BNRELU) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = fmaxf(0.f, fmaf(v[i], c0[i], c1[i]));
+      } else if (MODE == A_CATMUL) {
+        const float h[8] = {b0[u].x, b0[u].y, b0[u].z, b0[u].w, b1[u].x, b1[u].y, b1[u].z, b1[u].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = second ? v[i] * h[i] : v[i];   // (same expression as the register path)
       } else {
         const float h[8] = {b0[u].x, b0[u].y, b0[u].z, b0[u].w, b1[u].x, b1[u].y, b1[u].z, b1[u].w};
 #pragma unroll
@@ -492,9 +509,10 @@ CLSR_DEVINL void produce_tile(const AOp& a, Fast f, int tma, const float* sv, in
   const int kall = one_col >= K ? one_col + 1 : K;
   const int nall = (kall + 7) >> 3;
   if (nfull > 0 && tma) {
-    if (a.mode == A_PLAIN) convert_tile<A_PLAIN>(sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
-    else if (a.mode == A_BNRELU) convert_tile<A_BNRELU>(sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
-    else convert_tile<A_AFFINE2>(sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
+    if (a.mode == A_PLAIN) convert_tile<A_PLAIN>(a, sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
+    else if (a.mode == A_BNRELU) convert_tile<A_BNRELU>(a, sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
+    else if (a.mode == A_CATMUL) convert_tile<A_CATMUL>(a, sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
+    else convert_tile<A_AFFINE2>(a, sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
   } else if (nfull > 0) switch (a.mode) {
     case A_PLAIN: produce_fast_v<A_PLAIN>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, base); break;
     case A_BNRELU: produce_fast_v<A_BNRELU>(a, f.v256, sv, svld, m0, M, nfull, ptid, nprod, base); break;
@@ -507,10 +525,13 @@ CLSR_DEVINL void produce_tile(const AOp& a, Fast f, int tma, const float* sv, in
 }
 
 // Loader warp: TMA loads of the raw planes of one tile (tma = number of streams), all arriving on `bar`.
-CLSR_DEVINL void tma_issue_tile(int tma, const CUtensorMap* t1, const CUtensorMap* t2, int nplanes, int m0, uint32_t base,
-                                uint32_t raw2, uint64_t* bar, int lane) {
+// (A_CATMUL: the planes of the second part re-load columns [off, ...) of the same rows)
+CLSR_DEVINL void tma_issue_tile(const AOp& a, int tma, const CUtensorMap* t1, const CUtensorMap* t2, int nplanes, int m0,
+                                uint32_t base, uint32_t raw2, uint64_t* bar, int lane) {
+  const int w1 = a.mode == A_CATMUL ? a.W1 : (1 << 30);
   for (int p = lane; p < nplanes; p += 32) {
-    tma_load_plane(base + p * kPlaneBytes, t1, p * 8, m0, bar);
+    const int col = p * 8 < w1 ? p * 8 : a.off + p * 8 - w1;
+    tma_load_plane(base + p * kPlaneBytes, t1, col, m0, bar);
     if (tma == 2) tma_load_plane(raw2 + p * kPlaneBytes, t2, p * 8, m0, bar);
   }
 }
@@ -719,7 +740,7 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
       const int nplanes = K >> 3;
       if (lane == 0) mbar_expect_tx(&rawfull[s], (uint32_t)(nplanes * kPlaneBytes * tma));
       __syncwarp();
-      tma_issue_tile(tma, &tmA, &tmA2, nplanes, tile * kTileM, smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes),
+      tma_issue_tile(a, tma, &tmA, &tmA2, nplanes, tile * kTileM, smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes),
                      smem_u32(smem + L.raw2 + s * L.raw2_bytes), &rawfull[s], lane);
     }
   } else if (warp == kMmaWarp) {
@@ -1015,16 +1036,23 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
 struct DwSmem {
   int a_bytes, b_bytes, a2_bytes, b2_bytes, stage_bytes, bars, total;
 };
-// Stage = [A planes (16) | B planes (npad / 8) | raw second stream of A | raw second stream of B].
-__host__ __device__ inline DwSmem dw_smem_layout(int K, int N, int npad, int nstages, int tma_a, int tma_b) {
+// Stage = [A planes (ceil(acols / 8)) | B planes (npad / 8) | raw second stream of A | raw second stream of B].
+// The MMA always reads 16 A planes (its 128 lanes); only the first ceil(acols / 8) of them carry operand columns
+// (acols = K, + 1 for the constant-one column).  The lanes past them produce accumulator rows nobody reads, and
+// accumulator rows are independent, so those planes are not stored: the descriptor simply runs on into whatever
+// follows the A planes in shared memory (B planes, raw buffers, the next stage).  That is what lets two stages of
+// the wide problems (dWx, dWt, dKm, dWs0t) fit; `total` keeps the 64 KB window of the last stage inside the allocation.
+__host__ __device__ inline DwSmem dw_smem_layout(int K, int acols, int N, int npad, int nstages, int tma_a, int tma_b) {
   DwSmem s;
-  s.a_bytes = 16 * kPlaneBytes;            // 16 planes = the 128 MMA lanes
+  s.a_bytes = ((acols + 7) >> 3) * kPlaneBytes;
   s.b_bytes = (npad / 8) * kPlaneBytes;
   s.a2_bytes = tma_a == 2 ? (K >> 3) * kPlaneBytes : 0;
   s.b2_bytes = tma_b == 2 ? (N >> 3) * kPlaneBytes : 0;
   s.stage_bytes = s.a_bytes + s.b_bytes + s.a2_bytes + s.b2_bytes;
   s.bars = nstages * s.stage_bytes;
   s.total = s.bars + 128;
+  const int window = (nstages - 1) * s.stage_bytes + 16 * kPlaneBytes;
+  if (s.total < window) s.total = window;
   return s;
 }
 
@@ -1061,11 +1089,11 @@ constexpr int kDwThreads = 448;
 
 // Body of the weight-gradient kernel for one problem; `cta` of `nctas` CTAs share the problem's row slabs.
 // (The tensor maps are passed by address: they must stay in the kernel's parameter space.)
-CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, int N, int npad, int nstages,
+CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, int acols, int N, int npad, int nstages,
                          uint32_t tmem_cols, int tma_a, int tma_b, int octa, const AOp& a, const AOp& b,
                          float* __restrict__ dW, int lddw, float* __restrict__ colsum, const CUtensorMap* tmA,
                          const CUtensorMap* tmA2, const CUtensorMap* tmB, const CUtensorMap* tmB2, int cta, int nctas) {
-  const DwSmem L = dw_smem_layout(K, N, npad, nstages, tma_a, tma_b);
+  const DwSmem L = dw_smem_layout(K, acols, N, npad, nstages, tma_a, tma_b);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full = bars;         // [2]
   uint64_t* empty = bars + 2;    // [2]
@@ -1138,8 +1166,8 @@ CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, in
       if (lane == 0)
         mbar_expect_tx(&rawfull[s], (uint32_t)(((K >> 3) * tma_a + (N >> 3) * tma_b) * kPlaneBytes));
       __syncwarp();
-      if (tma_a) tma_issue_tile(tma_a, tmA, tmA2, K >> 3, tile * kTileM, a_base, a_raw2, &rawfull[s], lane);
-      if (tma_b) tma_issue_tile(tma_b, tmB, tmB2, N >> 3, tile * kTileM, b_base, b_raw2, &rawfull[s], lane);
+      if (tma_a) tma_issue_tile(a, tma_a, tmA, tmA2, K >> 3, tile * kTileM, a_base, a_raw2, &rawfull[s], lane);
+      if (tma_b) tma_issue_tile(b, tma_b, tmB, tmB2, N >> 3, tile * kTileM, b_base, b_raw2, &rawfull[s], lane);
     }
   } else {
     // MMA issue: D[128 x npad] += A^T-slab . B-slab, both operands MN-major
@@ -1197,23 +1225,23 @@ CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, in
 }
 
 __global__ void __launch_bounds__(kDwThreads, 1)
-tc_dw_kernel(int M, int K, int N, int npad, int nstages, uint32_t tmem_cols, int tma_a, int tma_b, int octa, AOp a, AOp b,
+tc_dw_kernel(int M, int K, int acols, int N, int npad, int nstages, uint32_t tmem_cols, int tma_a, int tma_b, int octa, AOp a, AOp b,
              float* __restrict__ dW, int lddw, float* __restrict__ colsum, const __grid_constant__ CUtensorMap tmA,
              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmB2) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(16) float sva[3 * 128];
   __shared__ __align__(16) float svb[3 * 256];
-  dw_body(smem, sva, svb, M, K, N, npad, nstages, tmem_cols, tma_a, tma_b, octa, a, b, dW, lddw, colsum, &tmA, &tmA2, &tmB,
+  dw_body(smem, sva, svb, M, K, acols, N, npad, nstages, tmem_cols, tma_a, tma_b, octa, a, b, dW, lddw, colsum, &tmA, &tmA2, &tmB,
           &tmB2, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // Several independent weight-gradient problems in ONE launch: the launches over M = S*T rows process only ~11
 // slabs per CTA each, so pipeline fill, TMEM allocation and the final atomics dominate them; here the grid is
 // partitioned between the problems in proportion to their work and every CTA runs dw_body on its share.
-constexpr int kDwGroupMax = 8;
+constexpr int kDwGroupMax = 12;
 struct DwProblem {
-  int M, K, N, npad, nstages, tma_a, tma_b, octa, lddw, cta0, ncta;
+  int M, K, acols, N, npad, nstages, tma_a, tma_b, octa, lddw, cta0, ncta;
   uint32_t tmem_cols;
   AOp a, b;
   float* dW;
@@ -1233,7 +1261,7 @@ tc_dw_group_kernel(const __grid_constant__ DwGroup g) {
   int i = 0;
   while (i + 1 < g.n && (int)blockIdx.x >= g.p[i].cta0 + g.p[i].ncta) ++i;
   const DwProblem& P = g.p[i];
-  dw_body(smem, sva, svb, P.M, P.K, P.N, P.npad, P.nstages, P.tmem_cols, P.tma_a, P.tma_b, P.octa, P.a, P.b, P.dW, P.lddw,
+  dw_body(smem, sva, svb, P.M, P.K, P.acols, P.N, P.npad, P.nstages, P.tmem_cols, P.tma_a, P.tma_b, P.octa, P.a, P.b, P.dW, P.lddw,
           P.colsum, &P.tmA, &P.tmA2, &P.tmB, &P.tmB2, (int)blockIdx.x - P.cta0, P.ncta);
 }
 

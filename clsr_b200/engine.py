@@ -56,7 +56,7 @@ EXPORTS = [
     "clsr_dense_total", "clsr_dense_read", "clsr_dense_write", "clsr_bind_table", "clsr_set_adam_step",
     "clsr_get_adam_step", "clsr_train_step", "clsr_predict", "clsr_synchronize", "clsr_gather_history",
     "clsr_scatter_history_grad", "clsr_sparse_grad_view", "clsr_nccl_unique_id", "clsr_comm_init",
-    "clsr_debug_buffer", "clsr_debug_read", "clsr_set_debug_sync", "clsr_kernel_launches",
+    "clsr_debug_buffer", "clsr_debug_read", "clsr_set_debug_sync", "clsr_kernel_launches", "clsr_set_graphs", "clsr_graph_replays",
     "clsr_set_profiling", "clsr_profile_collect", "clsr_profile_entry", "clsr_debug_gemm", "clsr_debug_dwgemm",
     "clsr_shard_create", "clsr_shard_destroy", "clsr_shard_last_error", "clsr_shard_local_rows",
     "clsr_shard_local_values", "clsr_shard_local_grad", "clsr_shard_export", "clsr_shard_attach",
@@ -108,6 +108,8 @@ def load_library(path=None):
         "clsr_debug_buffer": (C.c_int, [P, C.c_char_p, C.POINTER(P), C.POINTER(I64)]),
         "clsr_debug_read": (C.c_int, [P, P, P, I64]),
         "clsr_set_debug_sync": (C.c_int, [P, I32]),
+        "clsr_set_graphs": (C.c_int, [P, I32]),
+        "clsr_graph_replays": (I64, [P]),
         "clsr_kernel_launches": (I64, [P]),
         "clsr_debug_gemm": (C.c_int, [P, I32, I32, I32, P, I32, P, I32, P, P, I32, I32]),
         "clsr_debug_dwgemm": (C.c_int, [P, I32, I32, I32, P, I32, P, I32, P, I32, P, I32]),
@@ -551,6 +553,13 @@ class Engine:
 
     def kernel_launches(self):
         return int(self.lib.clsr_kernel_launches(self.h))
+
+    def set_graphs(self, on=True):
+        """Replay single-GPU training steps as CUDA graphs (default on)."""
+        self._check(self.lib.clsr_set_graphs(self.h, 1 if on else 0))
+
+    def graph_replays(self):
+        return int(self.lib.clsr_graph_replays(self.h))
 
     def set_debug_sync(self, on=True):
         self._check(self.lib.clsr_set_debug_sync(self.h, 1 if on else 0))

@@ -193,6 +193,12 @@ int clsr_debug_buffer(clsr_engine* e, const char* name, const float** dev_ptr, i
 int clsr_debug_read(clsr_engine* e, const void* dev_src, void* host_dst, int64_t bytes);
 int clsr_set_debug_sync(clsr_engine* e, int32_t on);  /* sync + check after every kernel */
 int64_t clsr_kernel_launches(const clsr_engine* e);   /* kernels launched by the last step */
+/* Single-GPU training steps are replayed as one CUDA graph per batch shape (first step of a shape eager, second
+ * captured, later ones one cudaGraphLaunch; per-step scalars such as Adam's step size live in device memory).
+ * clsr_set_graphs(e, 0) turns that off (every step launches its kernels one by one), clsr_graph_replays counts the
+ * steps that ran as a graph launch so far. */
+int clsr_set_graphs(clsr_engine* e, int32_t on);
+int64_t clsr_graph_replays(const clsr_engine* e);
 /* Standalone linear layer C[M,N] = A[M,K].W[K,N] + bias on device pointers; mode 0 = fp32 SIMT kernel,
  * 1 = tcgen05 split-bf16 kernel.  Used by the kernel-level parity tests. */
 int clsr_debug_gemm(clsr_engine* e, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* W,

@@ -442,3 +442,40 @@ def test_device_batches_match_reference_golden(cuda_lib):
     hp, _ = eng.predict({k: (ef[k] if k != "labels" else ef[k].reshape(-1, 1)) for k in ef}, group=1)
     assert np.allclose(p.cpu().numpy(), hp, rtol=1e-6, atol=1e-7)
     assert np.array_equal(u.cpu().numpy(), ef["users"]) and np.array_equal(y.cpu().numpy(), ef["labels"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math_mode", [0, 1])
+def test_graph_replayed_steps_match_eager_steps(cuda_lib, math_mode):
+    """Single-GPU training steps run as one CUDA graph launch from the third step of a batch shape on
+    (clsr_set_graphs / clsr_graph_replays).  Six optimizer steps over two batch shapes, host feeds and
+    device-resident feeds: same losses and same variables as an engine that launches every kernel itself
+    (differences are the atomics' summation order only).  Adam's step size must advance inside replays."""
+    G, S = 5, 32
+    feed, prm = PU.small_problem(S=S, G=G, seed=11)
+    feeds = [PU.small_problem(S=S if i % 3 else S - 8, G=G, seed=20 + i)[0] for i in range(8)]
+    engs = []
+    for graphs in (True, False):
+        e = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, G=G, math_mode=math_mode)
+        e.set_graphs(graphs)
+        engs.append(e)
+    losses = [[], []]
+    for i, f in enumerate(feeds):
+        for j, e in enumerate(engs):
+            if i % 2:
+                from clsr_b200.engine import normalize_feed
+                d = e.to_device(normalize_feed(f))
+                e.train_step(d, group=G, on_device=True, wait=False)
+                losses[j].append(e.train_step(d, group=G, on_device=True))   # same batch again: waits, returns losses
+            else:
+                losses[j].append(e.train_step(f, group=G))
+    assert engs[0].graph_replays() >= 5 and engs[1].graph_replays() == 0
+    assert engs[0].kernel_launches() == engs[1].kernel_launches()
+    for a, b in zip(*losses):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 2e-5 * max(abs(b[k]), 1e-3), (k, a[k], b[k])
+    pa, pb = engs[0].get_params(), engs[1].get_params()
+    for k in pb:
+        moved = np.abs(pb[k] - prm[k].reshape(pb[k].shape)).max() if k in prm else 1.0
+        # 13 Adam steps: Adam normalises the atomics' rounding noise of near-zero gradients to +-lr per step
+        assert np.abs(pa[k] - pb[k]).max() <= 0.08 * moved + 1e-7, k

@@ -29,8 +29,15 @@ int main() {
     tc::Smem L = tc::smem_layout(kpad, npad, c[1], c[2], c[3], c[4], c[5]);
     printf("gemm %d %d %d %d\n", c[0], c[1], L.total, L.a_stage_bytes);
   }
-  tc::DwSmem D = tc::dw_smem_layout(80, 40, 48, 2, 1, 2);
+  tc::DwSmem D = tc::dw_smem_layout(80, 80, 40, 48, 2, 1, 2);
   printf("dw %d %d %d %d\n", D.a_bytes, D.b_bytes, D.b2_bytes, D.total);
+  // the widest weight gradients double-buffer once the unused MMA lanes are not stored: dWx slab (K=40 + ones
+  // column, 160 plain columns), dWt (80 x 120), dKm (40 x 160), dWs0t (40 x 80, two-stream B)
+  const int w[][5] = {{40, 41, 160, 1, 1}, {80, 80, 120, 1, 1}, {40, 40, 160, 1, 1}, {40, 40, 80, 0, 2}};
+  for (auto& c : w) {
+    tc::DwSmem E = tc::dw_smem_layout(c[0], c[1], c[2], (c[2] + 15) / 16 * 16, 2, c[3], c[4]);
+    printf("dw2 %d %d %d %d\n", c[0], c[2], E.total, (2 - 1) * E.stage_bytes + 16 * 4096);
+  }
   return 0;
 }
 '''
@@ -68,4 +75,9 @@ def test_operand_stage_is_one_plane_per_eight_columns(host_out):
         assert total <= 227 * 1024, (K, N, total)
     dw = [ln for ln in host_out if ln[0] == "dw"][0]
     a, b, b2, total = map(int, dw[1:])
-    assert a == 16 * 4096 and b == 6 * 4096 and b2 == 5 * 4096 and total <= 227 * 1024
+    assert a == 10 * 4096 and b == 6 * 4096 and b2 == 5 * 4096 and total <= 227 * 1024
+    for ln in host_out:
+        if ln[0] == "dw2":
+            k, n, tot, window = map(int, ln[1:])
+            # two stages fit, and the 16-plane window the MMA reads from the last stage stays inside the allocation
+            assert tot <= 227 * 1024 - 4608 - 256 and window <= tot, ln
