@@ -555,7 +555,9 @@ def run_reference(a):
 
 if __name__ == "__main__":
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
+    # keep stdout to the one JSON line: NCCL prints its version banner (and warnings) to stdout unless told otherwise
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_%h_%p.log")
     args = parse()
     if args.impl == "reference":
         run_reference(args)

@@ -891,6 +891,9 @@ struct PeerComm {
   double* data[kMaxWorld];                // rank r's buffer: [2][world][kPeerSlots]
   unsigned long long* flag[kMaxWorld];    // rank r's flags:  [2][world]
   int rank, world;
+  unsigned long long* seq_ctr;            // this rank's exchange counter, in device memory: every rank issues the
+                                          // same sequence of exchanges, so the counters agree without the host
+                                          // passing a number per launch (which a replayed CUDA graph would freeze)
 };
 CLSR_DEVINL void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -910,8 +913,14 @@ CLSR_DEVINL void st_volatile_f64(double* p, double v) {
 }
 // All threads of ONE CTA call this; vals: n doubles in shared memory, replaced by their sum over ranks.
 CLSR_DEVINL void peer_allreduce_block(const PeerComm& pc, unsigned long long seq, double* vals, int n) {
-  const int ph = (int)(seq & 1ull);
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (pc.seq_ctr) {
+    __shared__ unsigned long long s_seq;
+    if (tid == 0) { s_seq = *pc.seq_ctr + 1ull; *pc.seq_ctr = s_seq; }
+    __syncthreads();
+    seq = s_seq;
+  }
+  const int ph = (int)(seq & 1ull);
   for (int r = 0; r < pc.world; ++r) {
     double* dst = pc.data[r] + ((size_t)ph * pc.world + pc.rank) * kPeerSlots;
     for (int i = tid; i < n; i += nt) st_volatile_f64(dst + i, vals[i]);

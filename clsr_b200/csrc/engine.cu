@@ -2217,7 +2217,9 @@ static int step_body(clsr_engine* e, const StepCtx& c, uint32_t flags) {
 // Run the step body eagerly, or (single GPU, no per-kernel events) as one graph launch.
 static int run_step(clsr_engine* e, const StepCtx& c, uint32_t flags) {
   static const bool env_off = getenv("CLSR_NO_GRAPH") != nullptr;
-  const bool can = e->graphs_on && !env_off && e->world == 1 && !e->profiling && !e->debug_sync;
+  // (data parallel: only with row-sharded tables -- its exchanges are peer-memory kernels with device-side sequence
+  //  numbers plus one NCCL all-reduce, all capturable; every rank replays or launches the same kernel sequence)
+  const bool can = e->graphs_on && !env_off && (e->world == 1 || e->sharded) && !e->profiling && !e->debug_sync;
   if (!can) return step_body(e, c, flags);
   clsr_engine::StepGraph* g = nullptr;
   for (auto& x : e->graphs)
@@ -2761,8 +2763,13 @@ int clsr_peer_setup_finish(clsr_engine* e, const void* all_blobs) {
   CK(cudaSetDevice(e->cfg.device));
   int shift = 0;
   while ((1 << shift) < e->world) ++shift;
+  drop_graphs(e);
   memset(&e->pc, 0, sizeof e->pc);
   e->pc.rank = e->rank; e->pc.world = e->world;
+  {
+    int rc0 = dalloc(e, &e->pc.seq_ctr, 2);   // zeroed: exchange counter (see PeerComm)
+    if (rc0) return rc0;
+  }
   for (int t = 0; t < CLSR_NUM_TABLES; ++t) {
     memset(&e->gview[t], 0, sizeof(GradView));
     if (e->sharded) { memset(&e->tview[t], 0, sizeof(TabView)); e->tview[t].shift = shift; e->tview[t].mask = e->world - 1; }
@@ -2830,6 +2837,7 @@ int clsr_nccl_unique_id(void* out128) {
 // directions, the contrastive row count, dense gradients + loss partial sums, and an all-gather of the
 // sparse-gradient inputs.  Every rank must feed the same number of rows per step.
 int clsr_comm_init(clsr_engine* e, int32_t rank, int32_t world, const void* id128) {
+  if (e) drop_graphs(e);
   if (!e || !id128 || world < 1 || rank < 0 || rank >= world) return fail(e, CLSR_ERR_ARG, "bad argument");
   if (world == 1) return CLSR_OK;
   if (e->comm) return fail(e, CLSR_ERR_STATE, "communicator already initialised");

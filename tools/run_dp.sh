@@ -6,7 +6,7 @@ tail -2 ${OUT%.json}.err | cut -c1-300
 python - <<PY
 import json
 try:
-    d = json.load(open("$OUT"))
+    d = json.loads([l for l in open("$OUT").read().splitlines() if l.startswith("{")][-1])
     print("$OUT", "value", round(d["value"]), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]), "launches", d["launches_per_step"])
     print("  windows", d["timing"]["window_ms"])
     print("  top", d["top_kernels"][:10])
