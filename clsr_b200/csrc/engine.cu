@@ -22,6 +22,7 @@
 #include "embed.cuh"
 #include "gemm.cuh"
 #include "head.cuh"
+#include "head_mlp.cuh"
 #include "rnn.cuh"
 #include "rnn_tc.cuh"
 #include "tc_gemm.cuh"
@@ -71,6 +72,10 @@ struct clsr_engine {
   std::map<std::string, std::pair<double, long long>> prof_agg;
   long long launches = 0;
   long long adam_step = 0;
+  // fused _fcn_net kernels (head_mlp.cuh): grid-barrier counter, rows per CTA the shared-memory layouts are sized for
+  unsigned long long* coop_bar = nullptr;
+  int coop_rpc = 0;
+  bool coop_alpha = false, coop_logit = false;
   float* d_lr = nullptr;    // [1] this step's Adam step size (written by set_scalar_kernel before the step body)
   // Captured training steps (single GPU): one executable graph per (S, B, G, flags) shape.  The first step of a
   // shape runs eagerly (lazy allocations, attribute calls), the second is captured, later ones are one graph launch.
@@ -984,9 +989,58 @@ int bn_bwd(clsr_engine* e, BnLayer& b, double count) {
 }
 
 // Forward of a row-wise _fcn_net (alpha gate, logit): in [rows, m.in] -> h0, h1, out[rows].
+// Fill the argument block of the fused _fcn_net kernels.
+void coop_args(clsr_engine* e, Mlp& m, const float* in, int rows, float* h0, float* h1, CoopMlp* a) {
+  memset(a, 0, sizeof *a);
+  a->rows = rows; a->K = m.in; a->n0 = m.n0; a->n1 = m.n1; a->ld_in = m.in;
+  a->in = in; a->w0 = e->P + m.w0; a->b0 = e->P + m.b0; a->w1 = e->P + m.w1; a->b1 = e->P + m.b1;
+  a->wo = e->P + m.wo; a->bo = e->P + m.bo;
+  a->h0 = h0; a->h1 = h1;
+  a->dw0 = e->Pg + m.w0; a->dw1 = e->Pg + m.w1;
+  a->dwo = e->Pg + m.wo; a->dbo = e->Pg + m.bo;
+  BnLayer* bl[2] = {&m.bn0, &m.bn1};
+  CoopBn* cb[2] = {&a->bn0, &a->bn1};
+  for (int i = 0; i < 2; ++i) {
+    BnLayer& b = *bl[i];
+    *cb[i] = CoopBn{e->P + b.gamma, e->P + b.beta, e->P + b.mmean, e->P + b.mvar, b.scale, b.shift, b.mean, b.rstd,
+                    b.al, b.be, b.ga, e->Pg + b.gamma, e->Pg + b.beta, b.stat_f, b.stat_b};
+  }
+  a->count = (double)rows * e->world;
+  a->eps = e->cfg.bn_eps; a->momentum = e->cfg.bn_momentum;
+  a->add_scale = e->rank == 0 ? 1.f : 0.f;
+  a->bar = e->coop_bar;
+  a->world = (e->world > 1 && e->peer_ready) ? e->world : 1;
+  a->pc = e->pc;
+}
+bool coop_usable(const clsr_engine* e, const Mlp& m, int rows) {
+  const bool on = (&m == &e->mlp_alpha) ? e->coop_alpha : ((&m == &e->mlp_logit) ? e->coop_logit : false);
+  // data parallel without the peer-memory exchange (plain NCCL mode before clsr_peer_setup_*): layer-by-layer path
+  return on && rows <= (long long)e->coop_rpc * e->num_sms && (e->world == 1 || e->peer_ready);
+}
+template <typename Kern>
+int coop_launch(clsr_engine* e, Kern kern, const CoopMlp& a, size_t smem, const char* name) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(e->num_sms); cfg.blockDim = dim3(kCoopThreads); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;    // all CTAs co-resident: the kernels synchronise through a grid barrier
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, a, e->coop_rpc));
+  POST(name);
+  return 0;
+}
+
 int mlp_fwd(clsr_engine* e, Mlp& m, const float* in, int rows, float* h0, float* h1, float* out, int train,
             int update) {
   int rc;
+  if (train && coop_usable(e, m, rows)) {
+    CoopMlp a;
+    coop_args(e, m, in, rows, h0, h1, &a);
+    a.out = out; a.update_moving = update;
+    const CoopFwdSmem L = coop_fwd_smem(m.in, m.n0, m.n1, e->coop_rpc);
+    return coop_launch(e, mlp_fwd_coop_kernel, a, (size_t)L.total * 4, "mlp_fwd_fused");
+  }
   EpiOp ep = e_store(h0, m.n0, e->P + m.b0);
   ep.stat = m.bn0.stat_f;
   if ((rc = gemm(e, "mlp_l0", rows, m.n0, m.in, a_plain(in, m.in), e->P + m.w0, m.n0, ep, train != 0))) return rc;
@@ -1006,6 +1060,13 @@ int mlp_fwd(clsr_engine* e, Mlp& m, const float* in, int rows, float* h0, float*
 int mlp_bwd(clsr_engine* e, Mlp& m, const float* in, int rows, const float* h0, const float* h1,
             const float* dout, float* dy1, float* dy0, const float* w0T, const float* w1T, float* din) {
   int rc;
+  if (coop_usable(e, m, rows)) {
+    CoopMlp a;
+    coop_args(e, m, in, rows, const_cast<float*>(h0), const_cast<float*>(h1), &a);
+    a.dout = dout; a.din = din; a.w0T = w0T; a.w1T = w1T;
+    const CoopBwdSmem L = coop_bwd_smem(m.in, m.n0, m.n1, e->coop_rpc);
+    return coop_launch(e, mlp_bwd_coop_kernel, a, (size_t)L.total * 4, "mlp_bwd_fused");
+  }
   {
     int nx = ((m.n1 + 31) / 32) * 32;
     dim3 blk(nx, 256 / nx > 0 ? 256 / nx : 1);
@@ -1985,6 +2046,32 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
   CKC(dalloc(e, &e->acc, 16));
   CKC(dalloc(e, &e->d_losses, 16));
   CKC(dalloc(e, &e->d_lr, 4));
+  {
+    // fused _fcn_net kernels: usable when both layouts of a network fit the opt-in shared memory
+    CKC(dalloc(e, &e->coop_bar, 2));
+    e->coop_rpc = cdiv(e->Bmax, e->num_sms);
+    cudaFuncAttributes ff, fb;
+    CKCU(cudaFuncGetAttributes(&ff, mlp_fwd_coop_kernel));
+    CKCU(cudaFuncGetAttributes(&fb, mlp_bwd_coop_kernel));
+    int coop_ok = 0;
+    CKCU(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, e->cfg.device));
+    const bool off = getenv("CLSR_NO_COOP_HEAD") != nullptr;
+    size_t need_f = 0, need_b = 0;
+    Mlp* ms[2] = {&e->mlp_alpha, &e->mlp_logit};
+    bool* flag[2] = {&e->coop_alpha, &e->coop_logit};
+    for (int i = 0; i < 2; ++i) {
+      const Mlp& m = *ms[i];
+      const bool shape = m.n0 % 4 == 0 && m.n1 % 4 == 0 && m.n0 <= kCoopMaxN && m.n1 <= kCoopMaxN && m.n0 >= 4 && m.n1 >= 4 &&
+                         (m.in + 3) / 4 <= kCoopThreads && 2 * m.n0 <= kPeerSlots;
+      const size_t sf = (size_t)coop_fwd_smem(m.in, m.n0, m.n1, e->coop_rpc).total * 4;
+      const size_t sb = (size_t)coop_bwd_smem(m.in, m.n0, m.n1, e->coop_rpc).total * 4;
+      const bool fits = sf + ff.sharedSizeBytes + 512 <= (size_t)e->smem_optin && sb + fb.sharedSizeBytes + 512 <= (size_t)e->smem_optin;
+      *flag[i] = !off && coop_ok && shape && fits;
+      if (*flag[i]) { need_f = sf > need_f ? sf : need_f; need_b = sb > need_b ? sb : need_b; }
+    }
+    if (need_f) CKCU(cudaFuncSetAttribute(mlp_fwd_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_f));
+    if (need_b) CKCU(cudaFuncSetAttribute(mlp_bwd_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_b));
+  }
   CKC(dalloc(e, &e->d_clip_steps, 1));
   CKCU(cudaMallocHost((void**)&e->h_losses, 16 * sizeof(float)));
   CKCU(cudaMallocHost((void**)&e->h_out, (size_t)2 * Bm * sizeof(float)));
