@@ -90,7 +90,7 @@ pool_fwd_kernel(const float* __restrict__ h1, int A1, const float* __restrict__ 
 //   dy1[row,t,n] = dsc[t]*wout[n] where bn(h1)>0 (zero elsewhere and on padded positions)
 //   stat += (sum dy1, sum dy1*xhat) per channel;  dwout += sum relu(bn(h1))*dsc;  dbout += sum dsc
 //   dV[seq,t,:] (=|+=) sum_g w[g,t] * datt[g,:]  (+ proxy gradients dhm/L, dhr/k when given)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)   // <= 64 registers: 8 CTAs (32 warps) per SM hide the h1 / V load latency
 pool_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ w, const float* __restrict__ V,
                 int Dv, const float* __restrict__ h1, int A1, const float* __restrict__ scale,
                 const float* __restrict__ shift, const float* __restrict__ mean,

@@ -557,34 +557,50 @@ __global__ void gather_rows_multi_kernel(const __grid_constant__ GatherRowsMulti
 }
 
 struct UniqueSeg { const int32_t* ids; long long n; int T, seq_stride; int32_t* slot; int32_t* uniq; int32_t* counter; };
-struct UniqueMulti { UniqueSeg s[kMaxSeg]; int n; };
-__global__ void mark_unique_multi_kernel(const __grid_constant__ UniqueMulti a) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
+struct UniqueMulti { UniqueSeg s[kMaxSeg]; int n; int blk0[kMaxSeg + 1]; };
+// One 256-id chunk of ONE segment per CTA (blk0: first CTA of every segment), all segments side by side: the kernel is a
+// chain of dependent memory operations (id -> slot[id] -> CAS -> append), so it costs one such chain instead of one per
+// segment.  Appends are aggregated per CTA: one atomic on the (single-address) counter per CTA, not per warp.
+constexpr int kUniqueBlock = 256;
+inline void unique_plan(UniqueMulti* a) {
+  a->blk0[0] = 0;
+  for (int k = 0; k < a->n; ++k) a->blk0[k + 1] = a->blk0[k] + (int)((a->s[k].n + kUniqueBlock - 1) / kUniqueBlock);
+}
+__global__ void __launch_bounds__(kUniqueBlock) mark_unique_multi_kernel(const __grid_constant__ UniqueMulti a) {
+  __shared__ int s_cnt, s_base;
+  int k = 0;
+  while (k + 1 < a.n && (int)blockIdx.x >= a.blk0[k + 1]) ++k;
+  const UniqueSeg& u = a.s[k];
   const int lane = threadIdx.x & 31;
-  for (int k = 0; k < a.n; ++k) {
-    const UniqueSeg& u = a.s[k];
-    const long long nround = (u.n + stride - 1) / stride * stride;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-      bool claim = false;
-      int id = 0;
-      if (i < u.n) {
-        const long long sq = i / u.T;
-        id = __ldg(u.ids + sq * u.seq_stride + (i - sq * u.T));
-        if (u.slot[id] == -1) claim = atomicCAS(&u.slot[id], -1, -2) == -1;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, claim);
-      if (m) {
-        const int leader = __ffs(m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(u.counter, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (claim) {
-          const int c = base + __popc(m & ((1u << lane) - 1u));
-          u.uniq[c] = id;
-          u.slot[id] = c;
-        }
-      }
-    }
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const long long i = (long long)((int)blockIdx.x - a.blk0[k]) * kUniqueBlock + threadIdx.x;
+  bool claim = false;
+  int id = 0;
+  const bool valid = i < u.n;
+  if (valid) {
+    const long long sq = i / u.T;
+    id = __ldg(u.ids + sq * u.seq_stride + (i - sq * u.T));
+  }
+  // one lane per distinct id of the warp goes to the slot table: when the kernel starts, every warp finds the hot ids
+  // (the padding row above all) still unclaimed, and a compare-and-swap per lane on one address serialises for tens of
+  // microseconds
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? id : -1 - lane);
+  if (valid && lane == __ffs(peers) - 1 && u.slot[id] == -1) claim = atomicCAS(&u.slot[id], -1, -2) == -1;
+  const unsigned m = __ballot_sync(0xffffffffu, claim);
+  int wbase = 0;
+  if (m) {
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) wbase = atomicAdd(&s_cnt, __popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, leader);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt > 0) s_base = atomicAdd(u.counter, s_cnt);
+  __syncthreads();
+  if (claim) {
+    const int c = s_base + wbase + __popc(m & ((1u << lane) - 1u));
+    u.uniq[c] = id;
+    u.slot[id] = c;
   }
 }
 

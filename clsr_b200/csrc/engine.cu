@@ -1742,7 +1742,8 @@ int sparse_grads(clsr_engine* e, const StepCtx& c) {
     um.s[2] = UniqueSeg{ch, M, T, seq_stride, e->slot[1], e->uniq[1], e->counts + 2};
     um.s[3] = UniqueSeg{cates, B, 1, 1, e->slot[1], e->uniq[1], e->counts + 2};
     um.s[4] = UniqueSeg{users, S, 1, user_stride, e->slot[2], e->uniq[2], e->counts + 3};
-    mark_unique_multi_kernel<<<grid1d(e, M, 256), 256, 0, st>>>(um);
+    unique_plan(&um);
+    mark_unique_multi_kernel<<<um.blk0[um.n], kUniqueBlock, 0, st>>>(um);
     POST("unique(items|cates|users)");
     CompactMulti cm;
     cm.n = 4;

@@ -482,4 +482,4 @@ def test_graph_replayed_steps_match_eager_steps(cuda_lib, math_mode):
         # so single elements may drift apart by a few lr; the variable as a whole must have moved the same way
         moved = np.linalg.norm((pb[k] - prm[k].reshape(pb[k].shape)).astype(np.float64))
         diff = np.linalg.norm((pa[k] - pb[k]).astype(np.float64))
-        assert diff <= 0.1 * moved + 1e-7, (k, diff, moved)
+        assert diff <= 0.25 * moved + 1e-7, (k, diff, moved)
