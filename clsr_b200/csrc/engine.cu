@@ -631,7 +631,7 @@ EncodeTiledFn encode_tiled() {
   }();
   return fn;
 }
-bool make_tmap(CUtensorMap* m, const float* base, int cols, long long rows, int ld) {
+bool make_tmap(CUtensorMap* m, const float* base, int cols, long long rows, int ld, bool swizzle32 = false) {
   memset(m, 0, sizeof *m);
   EncodeTiledFn enc = encode_tiled();
   if (!enc || !base) return false;
@@ -640,7 +640,8 @@ bool make_tmap(CUtensorMap* m, const float* base, int cols, long long rows, int 
   cuuint32_t box[2] = {8, (cuuint32_t)tc::kTileM};
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // Number of operand streams the TMA can load for this prologue (0: register loads): the rows must be plain
@@ -679,25 +680,29 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   }
   const int st = stats ? 1 : 0;
   int tma = tma_streams(a, K);
+  // TMA-store epilogue: the output tile goes through a shared-memory image (the kernel re-checks the operand
+  // alignments its vector epilogue needs)
+  static const bool no_tstore = getenv("CLSR_NO_TMA_STORE") != nullptr;
+  int tstore = (!no_tstore && encode_tiled() && (N & 7) == 0 && (ep.ldc & 3) == 0 && al16p(ep.C) && M >= tc::kTileM) ? 1 : 0;
   // first configuration that fits shared memory: prefer two stages + operand prefetch + TMA
-  // (two operand stages matter more than the prefetched epilogue operand)
-  const int cand[][3] = {{2, eop, tma}, {2, eop, tma == 2 ? 0 : tma}, {2, 0, tma}, {1, eop, tma},
-                         {2, 0, 0},     {1, eop, 0},                  {1, 0, 0}};
+  // (two operand stages matter more than the prefetched epilogue operand, which matters more than the store image)
+  const int cand[][4] = {{2, eop, tma, tstore}, {2, eop, tma, 0}, {2, eop, tma == 2 ? 0 : tma, 0}, {2, 0, tma, 0}, {1, eop, tma, 0},
+                         {2, 0, 0, 0},          {1, eop, 0, 0},   {1, 0, 0, 0}};
   tc::Smem L;
   bool fits = false;
   for (const auto& c : cand) {
-    L = tc::smem_layout(kpad, npad, N, c[0], c[1], st, c[2]);
-    if (L.total <= e->tc_smem_max) { nstages = c[0]; eop = c[1]; tma = c[2]; fits = true; break; }
+    L = tc::smem_layout(kpad, npad, N, c[0], c[1], st, c[2], c[3]);
+    if (L.total <= e->tc_smem_max) { nstages = c[0]; eop = c[1]; tma = c[2]; tstore = c[3]; fits = true; break; }
   }
   if (!fits) return fail(e, CLSR_ERR_ARG, "tc_gemm %s: K=%d N=%d does not fit shared memory", name, K, N);
-  CUtensorMap tmA, tmA2;
+  CUtensorMap tmA, tmA2, tmC;
   memset(&tmA2, 0, sizeof tmA2);
+  memset(&tmC, 0, sizeof tmC);
   if (tma >= 1 && !make_tmap(&tmA, a.A, tmap_cols(a, K), M, a.lda)) tma = 0;
   if (tma == 2 && !make_tmap(&tmA2, a.A2, K, M, a.lda2)) tma = 0;
-  if (!tma) {
-    memset(&tmA, 0, sizeof tmA);
-    L = tc::smem_layout(kpad, npad, N, nstages, eop, st, 0);
-  }
+  if (tstore && !make_tmap(&tmC, ep.C, N, M, ep.ldc, true)) tstore = 0;
+  if (!tma) memset(&tmA, 0, sizeof tmA);
+  L = tc::smem_layout(kpad, npad, N, nstages, eop, st, tma, tstore);
   uint32_t cols = 32;
   while ((int)cols < (stats ? 4 : 2) * npad) cols <<= 1;   // two accumulators (+ two statistic regions)
   int per_sm = e->smem_optin / (L.total + 6 * 1024);
@@ -706,8 +711,8 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   if (per_sm < 1) per_sm = 1;
   int tiles = cdiv(M, tc::kTileM);
   int grid = tiles < e->num_sms * per_sm ? tiles : e->num_sms * per_sm;
-  if (stats) tc::tc_gemm_kernel<true><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, tma, a, W, ldw, ep, tmA, tmA2);
-  else tc::tc_gemm_kernel<false><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, tma, a, W, ldw, ep, tmA, tmA2);
+  if (stats) tc::tc_gemm_kernel<true><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, tma, tstore, a, W, ldw, ep, tmA, tmA2, tmC);
+  else tc::tc_gemm_kernel<false><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, tma, tstore, a, W, ldw, ep, tmA, tmA2, tmC);
   POST(name);
   return 0;
 }

@@ -98,6 +98,19 @@ CLSR_DEVINL void tma_load_plane(uint32_t smem_dst, const CUtensorMap* tm, int co
 CLSR_DEVINL void l2_prefetch(const void* gsrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
+// 2-D tiled TMA store: one plane (box {8 columns, 128 rows}) of the finished tile from shared to global memory;
+// rows past the end of the matrix are clipped by the tensor map.
+CLSR_DEVINL void tma_store_plane(const CUtensorMap* tm, uint32_t smem_src, int col, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(smem_src),
+               "r"(col), "r"(row)
+               : "memory");
+}
+CLSR_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+CLSR_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+CLSR_DEVINL void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+CLSR_DEVINL void sts4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 CLSR_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 CLSR_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 CLSR_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -604,11 +617,14 @@ CLSR_DEVINL int colmap16(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3)
 
 struct Smem {
   // byte offsets into dynamic shared memory
-  int w_hi, w_lo, a_stage0, a_stage_bytes, raw2, raw2_bytes, eop, eop_bytes, vec, dstat, bars, total;
+  int w_hi, w_lo, a_stage0, a_stage_bytes, raw2, raw2_bytes, eop, eop_bytes, cst, cst_bytes, vec, dstat, bars, total;
 };
 // eop != 0 reserves two [128 x N] fp32 tiles for the prefetched epilogue operand; tma == 2 reserves one raw
 // buffer per stage for the second operand stream.
-__host__ __device__ inline Smem smem_layout(int kpad, int npad, int N, int nstages, int eop, int stats, int tma) {
+// tstore != 0 reserves two [N / 8 planes x 4 KB] images of the output tile for the TMA-store epilogue (the store of
+// tile i reads one while the epilogue of tile i+1 fills the other).
+__host__ __device__ inline Smem smem_layout(int kpad, int npad, int N, int nstages, int eop, int stats, int tma,
+                                            int tstore = 0) {
   Smem s;
   const int wbytes = kpad * npad * 2;
   s.w_hi = 0;
@@ -619,7 +635,9 @@ __host__ __device__ inline Smem smem_layout(int kpad, int npad, int N, int nstag
   s.raw2_bytes = tma == 2 ? s.a_stage_bytes : 0;
   s.eop = s.raw2 + nstages * s.raw2_bytes;
   s.eop_bytes = eop ? ((kTileM * N * 4 + 127) & ~127) : 0;
-  s.vec = s.eop + 2 * s.eop_bytes;
+  s.cst = s.eop + 2 * s.eop_bytes;
+  s.cst_bytes = tstore ? (N >> 3) * kPlaneBytes : 0;
+  s.vec = s.cst + 2 * s.cst_bytes;
   s.dstat = s.vec + (3 * kpad + 5 * npad) * 4;   // prologue vectors + bias / scale / shift / mean / rstd
   s.dstat = (s.dstat + 15) & ~15;
   s.bars = s.dstat + (stats ? 4 * 2 * npad * 8 : 0);
@@ -630,16 +648,19 @@ __host__ __device__ inline Smem smem_layout(int kpad, int npad, int N, int nstag
 // STATS: accumulate per-column statistics into ep.stat (see gemm.cuh).
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tmem_cols, int eop_kind, int tma, AOp a,
-               const float* __restrict__ W, int ldw, EpiOp ep, const __grid_constant__ CUtensorMap tmA,
-               const __grid_constant__ CUtensorMap tmA2) {
+tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tmem_cols, int eop_kind, int tma, int tstore,
+               AOp a, const float* __restrict__ W, int ldw, EpiOp ep, const __grid_constant__ CUtensorMap tmA,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmC) {
+  // tstore: the epilogue writes the finished tile into a shared-memory image (same plane layout as the operand
+  // stages: 8 columns x 128 rows = 4 KB) and one thread stores it with 2-D TMA (one box per plane) instead of every
+  // thread storing 32-byte pieces of its own row (one L1 wavefront per row and instruction).
   // tma: 0 = producers read the operand with register loads; 1 / 2 = the loader warp brings the raw rows of
   // one / two operand streams in with 2-D TMA (one box per plane) and the producers convert in place.
   // eop_kind: which per-element epilogue operand is prefetched into shared memory by bulk copy
   // (0 none, 1 hpre, 2 group-add rows, 3 old C for accumulation); the host only selects one when the
   // operand rows are contiguous (leading dimension == N).
   extern __shared__ __align__(128) uint8_t smem[];
-  const Smem L = smem_layout(kpad, npad, N, nstages, eop_kind, STATS ? 1 : 0, tma);
+  const Smem L = smem_layout(kpad, npad, N, nstages, eop_kind, STATS ? 1 : 0, tma, tstore);
   uint8_t* w_hi = smem + L.w_hi;
   uint8_t* w_lo = smem + L.w_lo;
   float* sv = reinterpret_cast<float*>(smem + L.vec);     // [3][kpad]
@@ -811,6 +832,12 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
                         (!(flags & E_ROWBIAS) || ((ep.ldrb & 3) == 0 && al16(ep.rb))) &&
                         (!(flags & E_GROUPADD) || eop_kind == 2 || ((ep.ldga & 3) == 0 && al16(ep.ga)));
     const bool st256 = (ep.ldc & 7) == 0 && al32(ep.C);
+    const bool ts = tstore != 0 && vec_ok && (N & 7) == 0;
+    // The image uses the 32-byte TMA swizzle (16-byte halves of a row exchanged when bit 7 of the address is set, i.e.
+    // for rows 4..7 of every 8): eight consecutive lanes then cover all 32 banks and a 16-byte store instruction costs
+    // its minimum of four wavefronts.
+    const uint32_t cst_row = smem_u32(smem + L.cst) + (uint32_t)row * 32;
+    const uint32_t sw0 = ((row >> 2) & 1) * 16, sw1 = 16 - sw0;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     // Per-thread (= per-row) column statistics accumulate in two spare TMEM regions
     // [2 npad, 3 npad) and [3 npad, 4 npad): no shuffles in the tile loop, one reduction per kernel.
@@ -916,7 +943,16 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
 #pragma unroll
           for (int i = 0; i < 16; ++i) { v[i] = 0.f; h[i] = 0.f; }
         }
-        if (ok) {
+        if (ts) {
+          // plane c0 / 8 (and the next one when the chunk holds 16 valid columns), this thread's 32-byte row
+          const uint32_t d0 = cst_row + (uint32_t)(acc * L.cst_bytes) + (uint32_t)(c0 >> 3) * kPlaneBytes;
+          sts4(d0 + sw0, v[0], v[1], v[2], v[3]);
+          sts4(d0 + sw1, v[4], v[5], v[6], v[7]);
+          if (FULL || nq > 2) {
+            sts4(d0 + kPlaneBytes + sw0, v[8], v[9], v[10], v[11]);
+            sts4(d0 + kPlaneBytes + sw1, v[12], v[13], v[14], v[15]);
+          }
+        } else if (ok) {
           if (FULL && st256) {
             st8(crow + c0, v, true);
             st8(crow + c0 + 8, v + 8, true);
@@ -947,6 +983,11 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
         }
       };
 
+      if (ts) {
+        // the previous tile's stores must have finished reading the image before it is overwritten
+        if (et == 0) bulk_wait_read1();   // (the store of the tile before last used this image)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       for (int c0 = half * 16; c0 < npad; c0 += 32) {
         float v[16], s1[16], s2[16];
         const uint32_t tcol = tlane + (uint32_t)(acc * npad + c0);
@@ -989,7 +1030,17 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (ts) {
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          const uint32_t img = smem_u32(smem + L.cst) + (uint32_t)(acc * L.cst_bytes);
+          for (int p = 0; p < (N >> 3); ++p) tma_store_plane(&tmC, img + (uint32_t)p * kPlaneBytes, p * 8, m0);
+          bulk_commit();
+        }
+      }
     }
+    if (ts && et == 0) bulk_wait_read0();
     if (STATS) {
       // fold the per-row accumulators: 16-shuffle transpose reduction per chunk, quadrants summed in double
       double* myd = dstat + (size_t)q * 2 * npad;
