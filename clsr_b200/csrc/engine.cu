@@ -667,7 +667,10 @@ int tmap_cols(const AOp& a, int K) {
 
 // One tcgen05 launch: K <= 160 (W resident in shared memory), N <= 256 (one UMMA, one TMEM accumulator).
 int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, const float* W, int ldw,
-                const EpiOp& ep, bool stats) {
+                const EpiOp& ep, bool stats, int kchunks = 1, bool probe = false) {
+  // kchunks > 1: K is the width of one chunk, the contraction runs over kchunks * K columns of the (plain) operand in
+  // ONE launch (accumulator resident in TMEM across the chunks); probe: only report whether that configuration fits
+  // with two operand stages.
   const int kpad = round16(K), npad = round16(N);
   int nstages = 2;
   // per-element epilogue operand prefetched by bulk copy: needs contiguous, 16-byte aligned rows
@@ -691,18 +694,19 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   tc::Smem L;
   bool fits = false;
   for (const auto& c : cand) {
-    L = tc::smem_layout(kpad, npad, N, c[0], c[1], st, c[2], c[3]);
+    L = tc::smem_layout(kpad, npad, N, c[0], c[1], st, c[2], c[3], kchunks);
     if (L.total <= e->tc_smem_max) { nstages = c[0]; eop = c[1]; tma = c[2]; tstore = c[3]; fits = true; break; }
   }
+  if (probe) return (fits && nstages == 2) ? 0 : 1;
   if (!fits) return fail(e, CLSR_ERR_ARG, "tc_gemm %s: K=%d N=%d does not fit shared memory", name, K, N);
   CUtensorMap tmA, tmA2, tmC;
   memset(&tmA2, 0, sizeof tmA2);
   memset(&tmC, 0, sizeof tmC);
-  if (tma >= 1 && !make_tmap(&tmA, a.A, tmap_cols(a, K), M, a.lda)) tma = 0;
+  if (tma >= 1 && !make_tmap(&tmA, a.A, kchunks > 1 ? kchunks * K : tmap_cols(a, K), M, a.lda)) tma = 0;
   if (tma == 2 && !make_tmap(&tmA2, a.A2, K, M, a.lda2)) tma = 0;
   if (tstore && !make_tmap(&tmC, ep.C, N, M, ep.ldc, true)) tstore = 0;
   if (!tma) memset(&tmA, 0, sizeof tmA);
-  L = tc::smem_layout(kpad, npad, N, nstages, eop, st, tma, tstore);
+  L = tc::smem_layout(kpad, npad, N, nstages, eop, st, tma, tstore, kchunks);
   uint32_t cols = 32;
   while ((int)cols < (stats ? 4 : 2) * npad) cols <<= 1;   // two accumulators (+ two statistic regions)
   int per_sm = e->smem_optin / (L.total + 6 * 1024);
@@ -711,8 +715,8 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   if (per_sm < 1) per_sm = 1;
   int tiles = cdiv(M, tc::kTileM);
   int grid = tiles < e->num_sms * per_sm ? tiles : e->num_sms * per_sm;
-  if (stats) tc::tc_gemm_kernel<true><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, tma, tstore, a, W, ldw, ep, tmA, tmA2, tmC);
-  else tc::tc_gemm_kernel<false><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, tma, tstore, a, W, ldw, ep, tmA, tmA2, tmC);
+  if (stats) tc::tc_gemm_kernel<true><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, tma, tstore, kchunks, a, W, ldw, ep, tmA, tmA2, tmC);
+  else tc::tc_gemm_kernel<false><<<grid, tc::kThreads, L.total, e->stream>>>(M, N, K, kpad, npad, nstages, cols, eop, tma, tstore, kchunks, a, W, ldw, ep, tmA, tmA2, tmC);
   POST(name);
   return 0;
 }
@@ -737,6 +741,15 @@ bool tc_eligible(clsr_engine* e, const char* name, int M, int N, int K, const AO
 int tc_gemm(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, const float* W, int ldw,
             const EpiOp& ep, bool stats) {
   int rc;
+  static const bool no_kloop = getenv("CLSR_NO_KLOOP") != nullptr;
+  if (!no_kloop && K > 160 && N <= 256 && a.mode == A_PLAIN && tma_streams(a, 8) == 1) {
+    // deep contraction of a plain operand (dX: K = 480): one launch that walks K in chunks, if W and two stages fit
+    for (int kc = cdiv(K, 160); kc <= 16; ++kc) {
+      if (K % kc || (K / kc) % 8) continue;
+      if (tc_gemm_one(e, name, M, N, K / kc, a, W, ldw, ep, stats, kc, true) == 0)
+        return tc_gemm_one(e, name, M, N, K / kc, a, W, ldw, ep, stats, kc);
+    }
+  }
   for (int n0 = 0; n0 < N; n0 += 240) {          // column slabs (one UMMA is at most 256 wide)
     int nn = N - n0 < 240 ? N - n0 : 240;
     if (N <= 256) nn = N;

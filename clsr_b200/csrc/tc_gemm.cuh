@@ -540,12 +540,12 @@ CLSR_DEVINL void produce_tile(const AOp& a, Fast f, int tma, const float* sv, in
 // Loader warp: TMA loads of the raw planes of one tile (tma = number of streams), all arriving on `bar`.
 // (A_CATMUL: the planes of the second part re-load columns [off, ...) of the same rows)
 CLSR_DEVINL void tma_issue_tile(const AOp& a, int tma, const CUtensorMap* t1, const CUtensorMap* t2, int nplanes, int m0,
-                                uint32_t base, uint32_t raw2, uint64_t* bar, int lane) {
+                                uint32_t base, uint32_t raw2, uint64_t* bar, int lane, int col0 = 0) {
   const int w1 = a.mode == A_CATMUL ? a.W1 : (1 << 30);
   for (int p = lane; p < nplanes; p += 32) {
     const int col = p * 8 < w1 ? p * 8 : a.off + p * 8 - w1;
-    tma_load_plane(base + p * kPlaneBytes, t1, col, m0, bar);
-    if (tma == 2) tma_load_plane(raw2 + p * kPlaneBytes, t2, p * 8, m0, bar);
+    tma_load_plane(base + p * kPlaneBytes, t1, col0 + col, m0, bar);
+    if (tma == 2) tma_load_plane(raw2 + p * kPlaneBytes, t2, col0 + p * 8, m0, bar);
   }
 }
 
@@ -623,10 +623,11 @@ struct Smem {
 // buffer per stage for the second operand stream.
 // tstore != 0 reserves two [N / 8 planes x 4 KB] images of the output tile for the TMA-store epilogue (the store of
 // tile i reads one while the epilogue of tile i+1 fills the other).
+// kchunks > 1: the contraction runs over kchunks chunks of K columns each (all of W resident, one operand stage per chunk).
 __host__ __device__ inline Smem smem_layout(int kpad, int npad, int N, int nstages, int eop, int stats, int tma,
-                                            int tstore = 0) {
+                                            int tstore = 0, int kchunks = 1) {
   Smem s;
-  const int wbytes = kpad * npad * 2;
+  const int wbytes = kchunks * kpad * npad * 2;
   s.w_hi = 0;
   s.w_lo = wbytes;
   s.a_stage0 = 2 * wbytes;
@@ -649,8 +650,11 @@ __host__ __device__ inline Smem smem_layout(int kpad, int npad, int N, int nstag
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tmem_cols, int eop_kind, int tma, int tstore,
-               AOp a, const float* __restrict__ W, int ldw, EpiOp ep, const __grid_constant__ CUtensorMap tmA,
+               int kchunks, AOp a, const float* __restrict__ W, int ldw, EpiOp ep, const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmC) {
+  // kchunks > 1 (plain operands only): C = sum over kchunks chunks of K columns of A, rows [kc*K, (kc+1)*K) of W; every
+  // chunk is one operand stage, the accumulator stays in TMEM across the chunks of a tile (one launch instead of
+  // kchunks launches that re-read and re-write C).
   // tstore: the epilogue writes the finished tile into a shared-memory image (same plane layout as the operand
   // stages: 8 columns x 128 rows = 4 KB) and one thread stores it with 2-D TMA (one box per plane) instead of every
   // thread storing 32-byte pieces of its own row (one L1 wavefront per row and instruction).
@@ -660,7 +664,7 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
   // (0 none, 1 hpre, 2 group-add rows, 3 old C for accumulation); the host only selects one when the
   // operand rows are contiguous (leading dimension == N).
   extern __shared__ __align__(128) uint8_t smem[];
-  const Smem L = smem_layout(kpad, npad, N, nstages, eop_kind, STATS ? 1 : 0, tma, tstore);
+  const Smem L = smem_layout(kpad, npad, N, nstages, eop_kind, STATS ? 1 : 0, tma, tstore, kchunks);
   uint8_t* w_hi = smem + L.w_hi;
   uint8_t* w_lo = smem + L.w_lo;
   float* sv = reinterpret_cast<float*>(smem + L.vec);     // [3][kpad]
@@ -685,15 +689,16 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
   const Fast fa = fast_eligible(a);
 
   // ---- one-time setup: W split into canonical hi/lo tiles, vectors, barriers, TMEM ----
-  for (int idx = tid; idx < (kpad >> 3) * npad; idx += kThreads) {
-    int c = idx / npad, n = idx - c * npad;  // plane c holds k = 8c..8c+7 for every n
+  for (int idx = tid; idx < kchunks * (kpad >> 3) * npad; idx += kThreads) {
+    const int ct = idx / npad, n = idx - ct * npad;   // plane ct = (chunk, plane of the chunk) holds 8 consecutive k for every n
+    const int kc = ct / (kpad >> 3), c = ct - kc * (kpad >> 3);
     float x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       int k = c * 8 + i;
-      x[i] = (k < K && n < N) ? W[(size_t)k * ldw + n] : 0.f;
+      x[i] = (k < K && n < N) ? W[(size_t)(kc * K + k) * ldw + n] : 0.f;
     }
-    const uint32_t off = (uint32_t)(c * npad * 16 + n * 16);
+    const uint32_t off = (uint32_t)(ct * npad * 16 + n * 16);
     split_store8_w(x, smem_u32(w_hi) + off, smem_u32(w_lo) + off);
   }
   // operand stages start as zeros: planes past ceil(K/8) are never written again
@@ -733,37 +738,41 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
   if (warp < kLoadWarp) {
     // =============================== producers / converters ===============================
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int s = it % nstages;
-      const uint32_t ph = (it / nstages) & 1;
-      if (tma) mbar_wait(&rawfull[s], ph);      // implies empty[s]: the loader waited for it
-      else {
-        mbar_wait(&empty[s], ph ^ 1);
-        // register-load path: warp 0 prefetches the rows of a later tile into L2 (paced by the pipeline)
-        if (CLSR_TC_PREFETCH && warp == 0)
-          prefetch_operand(a, (tile + CLSR_TC_PREFETCH * (int)gridDim.x) * kTileM, M, K, lane);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int kc = 0; kc < kchunks; ++kc, ++it) {
+        const int s = it % nstages;
+        const uint32_t ph = (it / nstages) & 1;
+        AOp ak = a;
+        ak.A = a.A + kc * K;   // (kchunks > 1: plain operand)
+        if (tma) mbar_wait(&rawfull[s], ph);      // implies empty[s]: the loader waited for it
+        else {
+          mbar_wait(&empty[s], ph ^ 1);
+          // register-load path: warp 0 prefetches the rows of a later tile into L2 (paced by the pipeline)
+          if (CLSR_TC_PREFETCH && warp == 0)
+            prefetch_operand(ak, (tile + CLSR_TC_PREFETCH * (int)gridDim.x) * kTileM, M, K, lane);
+        }
+        const uint32_t a_base = smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes);
+        const uint32_t a_raw2 = smem_u32(smem + L.raw2 + s * L.raw2_bytes);
+        produce_tile(ak, fa, tma, sv, kpad, tile * kTileM, M, K, -1, tid, kProducers, a_base, a_raw2);
+        fence_proxy_async();
+        mbar_arrive(&full[s]);
       }
-      const uint32_t a_base = smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes);
-      const uint32_t a_raw2 = smem_u32(smem + L.raw2 + s * L.raw2_bytes);
-      produce_tile(a, fa, tma, sv, kpad, tile * kTileM, M, K, -1, tid, kProducers, a_base, a_raw2);
-      fence_proxy_async();
-      mbar_arrive(&full[s]);
-    }
   } else if (warp == kLoadWarp) {
     // =============================== operand loader ===============================
     // (idle on the register-load path: a role that nothing waits for must not wait on the ring barriers,
     //  it could fall two phases behind and alias the parity)
     int it = 0;
-    for (int tile = blockIdx.x; tma && tile < ntiles; tile += gridDim.x, ++it) {
-      const int s = it % nstages;
-      const uint32_t ph = (it / nstages) & 1;
-      mbar_wait(&empty[s], ph ^ 1);
-      const int nplanes = K >> 3;
-      if (lane == 0) mbar_expect_tx(&rawfull[s], (uint32_t)(nplanes * kPlaneBytes * tma));
-      __syncwarp();
-      tma_issue_tile(a, tma, &tmA, &tmA2, nplanes, tile * kTileM, smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes),
-                     smem_u32(smem + L.raw2 + s * L.raw2_bytes), &rawfull[s], lane);
-    }
+    for (int tile = blockIdx.x; tma && tile < ntiles; tile += gridDim.x)
+      for (int kc = 0; kc < kchunks; ++kc, ++it) {
+        const int s = it % nstages;
+        const uint32_t ph = (it / nstages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int nplanes = K >> 3;
+        if (lane == 0) mbar_expect_tx(&rawfull[s], (uint32_t)(nplanes * kPlaneBytes * tma));
+        __syncwarp();
+        tma_issue_tile(a, tma, &tmA, &tmA2, nplanes, tile * kTileM, smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes),
+                       smem_u32(smem + L.raw2 + s * L.raw2_bytes), &rawfull[s], lane, kc * K);
+      }
   } else if (warp == kMmaWarp) {
     // ====================== MMA issue + epilogue-operand prefetch ======================
     const uint32_t idesc = make_idesc(npad);
@@ -771,10 +780,8 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
     const uint32_t lbo_a = kPlaneBytes, sbo_a = 256, lbo_b = (uint32_t)npad * 16, sbo_b = 128;
     const uint64_t bdesc_hi = make_desc(smem_u32(w_hi), lbo_b, sbo_b);
     const uint64_t bdesc_lo = make_desc(smem_u32(w_lo), lbo_b, sbo_b);
-    int it = 0;
+    int it = 0, its = 0;   // tiles, operand stages (tiles x chunks) processed by this CTA
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int s = it % nstages;
-      const uint32_t ph = (it / nstages) & 1;
       const int acc = it & 1;
       const uint32_t pa = (it >> 1) & 1;
       mbar_wait(&tempty[acc], pa ^ 1);   // the epilogue of tile it-2 has released accumulator and operand tile
@@ -798,24 +805,28 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
           bulk_g2s(dst, src, (uint32_t)rows * N * 4, &efull[acc]);
         }
       }
-      mbar_wait(&full[s], ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_base = smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes);
-        const uint64_t adesc_hi = make_desc(a_base, lbo_a, sbo_a);
-        const uint64_t adesc_lo = make_desc(a_base + 128, lbo_a, sbo_a);
-        const uint32_t d = tmem_base + (uint32_t)(acc * npad);
-        for (int kb = 0; kb < nkb; ++kb) {
-          // advance both operands by one 16-wide K block = two planes
-          const uint64_t ka = (uint64_t)((2 * lbo_a * kb) >> 4), kbo = (uint64_t)((2 * lbo_b * kb) >> 4);
-          umma_bf16(d, adesc_hi + ka, bdesc_hi + kbo, idesc, kb > 0 ? 1u : 0u);
-          umma_bf16(d, adesc_lo + ka, bdesc_hi + kbo, idesc, 1u);
-          umma_bf16(d, adesc_hi + ka, bdesc_lo + kbo, idesc, 1u);
+      for (int kc = 0; kc < kchunks; ++kc, ++its) {
+        const int s = its % nstages;
+        const uint32_t ph = (its / nstages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = smem_u32(smem + L.a_stage0 + s * L.a_stage_bytes);
+          const uint64_t adesc_hi = make_desc(a_base, lbo_a, sbo_a);
+          const uint64_t adesc_lo = make_desc(a_base + 128, lbo_a, sbo_a);
+          const uint32_t d = tmem_base + (uint32_t)(acc * npad);
+          for (int kb = 0; kb < nkb; ++kb) {
+            // advance both operands by one 16-wide K block = two planes (W: past the blocks of the earlier chunks)
+            const uint64_t ka = (uint64_t)((2 * lbo_a * kb) >> 4), kbo = (uint64_t)((2 * lbo_b * (kc * nkb + kb)) >> 4);
+            umma_bf16(d, adesc_hi + ka, bdesc_hi + kbo, idesc, (kc > 0 || kb > 0) ? 1u : 0u);
+            umma_bf16(d, adesc_lo + ka, bdesc_hi + kbo, idesc, 1u);
+            umma_bf16(d, adesc_hi + ka, bdesc_lo + kbo, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+          if (kc == kchunks - 1) umma_commit(&tfull[acc]);
         }
-        umma_commit(&empty[s]);
-        umma_commit(&tfull[acc]);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // =============================== epilogue ===============================
