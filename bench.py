@@ -168,8 +168,9 @@ def kernel_models(S, B, T, w, d=DIMS, shards=1):
         "gather_hist": (M * (8 + 2 * D * f4), None),                     # T*8 + 2*T*D*e per sequence
         "scatter_hist": (M * (8 + 2 * D * f4), None),                    # read d_hist + ids, RMW-add one row slice
         "adam_sweep": (rows_state, None),
-        "px": (M * (D + NX) * f4, 2 * M * NX * D),
-        "px_time": (M * (2 * H + 2 * 3 * H) * f4, 2 * M * 3 * H * 2 * H),
+        # hoisted input projections: columns [0, NX-3H) = x.Wx; the last 3H columns = [x | time features].[Wx ; Wt] in one product
+        "px": (M * (2 * D + NX - 3 * H) * f4, 2 * M * (NX - 3 * H) * D),
+        "px_time": (M * (D + 2 * H + 3 * H) * f4, 2 * M * 3 * H * (D + 2 * H)),
         "al": (M * (D + U) * f4, 2 * M * D * U),
         "h0l": (M * (U + A0) * f4, 2 * M * 2 * U * A0),
         "h1l": (M * (A0 + A1) * f4, 2 * M * A0 * A1),
@@ -185,7 +186,7 @@ def kernel_models(S, B, T, w, d=DIMS, shards=1):
         "pool_bwd_short": (MB * 2 * A1 * f4 + M * 2 * D * f4, None),
         "pool_fwd_short": (MB * A1 * f4 + M * D * f4, None),
         "h0_reduce_short": (MB * 2 * A0 * f4, None),
-        "dX": (M * (NX + D) * f4, 2 * M * NX * D),
+        "dX": (M * (NX + D) * f4, 2 * M * NX * D),                       # one launch, K walked in chunks inside the kernel
         "dW_bptt_group": (M * (NX + D + 2 * H + 2 * U + 3 * H) * f4,
                           2 * M * (D * NX + 2 * H * 3 * H + U * 3 * U + H * 3 * H + H * 4 * H)),
         # recurrences: read the hoisted projections once, write the stored gate / state tensors once

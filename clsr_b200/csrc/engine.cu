@@ -510,7 +510,9 @@ int build_weight_maps(clsr_engine* e) {
   }
   // ---- recurrences: input halves of every kernel side by side in Wx_all [D, NX] ----
   {
-    long long wx = wd_add(e, "Wx_all", (long long)D * NX), bx = wd_add(e, "bx_all", NX);
+    // Wx_all [D + 2H, NX]: rows D.. hold [0 | Wt] under the last 3H columns, so that PX[:, oO:] = [X | TNL] . Wx_all[:, oO:]
+    // is ONE product (the rows above are zero-initialised and never written)
+    long long wx = wd_add(e, "Wx_all", (long long)(D + 2 * H) * NX), bx = wd_add(e, "bx_all", NX);
     long long wxT = wd_add(e, "Wx_allT", (long long)D * NX);
     long long wt = wd_add(e, "Wt", 2LL * H * 3 * H), wtT = wd_add(e, "WtT", 2LL * H * 3 * H);
     const std::string gs[2] = {st + "short_term_intention/gru_cell/", sc + "causal2/causal2/gru_cell/"};
@@ -562,6 +564,13 @@ int build_weight_maps(clsr_engine* e) {
     prep.push_back(mk(wt + (long long)H * 3 * H, 3 * H, o2, H, H, H));
     prep.push_back(mk(wt + H, 3 * H, t1, H, H, H));
     prep.push_back(mk(wt + (long long)H * 3 * H + 2 * H, 3 * H, t2, H, H, H));
+    {
+      const long long wxe = wx + (long long)D * NX + e->oO;   // same four blocks, row pitch NX
+      prep.push_back(mk(wxe, NX, o1, H, H, H));
+      prep.push_back(mk(wxe + (long long)H * NX, NX, o2, H, H, H));
+      prep.push_back(mk(wxe + H, NX, t1, H, H, H));
+      prep.push_back(mk(wxe + (long long)H * NX + 2 * H, NX, t2, H, H, H));
+    }
     prep.push_back(mk(wtT, 2 * H, o1, H, H, H, 1.f, -1, 0, 0.f, 1));
     prep.push_back(mk(wtT + H, 2 * H, o2, H, H, H, 1.f, -1, 0, 0.f, 1));
     prep.push_back(mk(wtT + (long long)H * 2 * H, 2 * H, t1, H, H, H, 1.f, -1, 0, 0.f, 1));
@@ -653,6 +662,9 @@ int tma_streams(const AOp& a, int K) {
   if (a.mode == A_PLAIN || a.mode == A_BNRELU) return ok(a.A, a.lda) ? 1 : 0;
   if (a.mode == A_AFFINE2) return (ok(a.A, a.lda) && ok(a.A2, a.lda2)) ? 2 : 0;
   // concatenation [rows | rows[:, off:] * per-sequence row]: both parts are column ranges of the same plain rows
+  // [A | A2], two plain matrices side by side (A_CAT2ROW with G == 1): one stream, two tensor maps
+  if (a.mode == A_CAT2ROW)
+    return (a.G == 1 && ok(a.A, a.lda) && ok(a.A2, a.lda2) && !(a.W1 & 7) && K > a.W1) ? 1 : 0;
   static const bool cat_off = getenv("CLSR_NO_TMA_CATMUL") != nullptr;
   if (a.mode == A_CATMUL && !cat_off)
     return (ok(a.A, a.lda) && ok(a.A2, a.lda2) && !(a.W1 & 7) && !(a.off & 3) && K > a.W1) ? 1 : 0;
@@ -660,6 +672,7 @@ int tma_streams(const AOp& a, int K) {
 }
 // Columns of the first operand stream the tensor map has to cover.
 int tmap_cols(const AOp& a, int K) {
+  if (a.mode == A_CAT2ROW) return a.W1;
   if (a.mode != A_CATMUL) return K;
   const int second = a.off + (K - a.W1);
   return a.W1 > second ? a.W1 : second;
@@ -704,6 +717,7 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   memset(&tmC, 0, sizeof tmC);
   if (tma >= 1 && !make_tmap(&tmA, a.A, kchunks > 1 ? kchunks * K : tmap_cols(a, K), M, a.lda)) tma = 0;
   if (tma == 2 && !make_tmap(&tmA2, a.A2, K, M, a.lda2)) tma = 0;
+  if (tma == 1 && a.mode == A_CAT2ROW && !make_tmap(&tmA2, a.A2, K - a.W1, M, a.lda2)) tma = 0;
   if (tstore && !make_tmap(&tmC, ep.C, N, M, ep.ldc, true)) tstore = 0;
   if (!tma) memset(&tmA, 0, sizeof tmA);
   L = tc::smem_layout(kpad, npad, N, nstages, eop, st, tma, tstore, kchunks);
@@ -1321,10 +1335,19 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
     time_feat_kernel<<<grid1d(e, M * 2 * H, 256), 256, 0, st>>>(c.ttn, c.tfa, c.seq_stride, T, e->P + e->p_tw1, e->P + e->p_tb1,
                                                                e->P + e->p_tw2, e->P + e->p_tb2, H, TNL, M);
   POST("time_feat");
-  if ((rc = gemm(e, "px", (int)M, NX, D, a_plain(X, D), W("Wx_all"), NX, e_store(PX, NX, W("bx_all")), false))) return rc;
-  if ((rc = gemm(e, "px_time", (int)M, 3 * H, 2 * H, a_plain(TNL, 2 * H), W("Wt"), 3 * H,
-                 e_store(PX + e->oO, NX, nullptr, E_ACCUM), false)))
-    return rc;
+  static const bool px_split = getenv("CLSR_PX_SPLIT") != nullptr;   // A/B: separate time product accumulated onto PX
+  if (!px_split && e->oO + 3 * H == NX && (D & 7) == 0 && (H & 3) == 0 && D + 2 * H <= 160) {
+    // columns [0, oO): x . Wx;  columns [oO, NX) (o gate, two time gates): [x | time features] . [Wx ; Wt] in one product
+    if ((rc = gemm(e, "px", (int)M, e->oO, D, a_plain(X, D), W("Wx_all"), NX, e_store(PX, NX, W("bx_all")), false))) return rc;
+    if ((rc = gemm(e, "px_time", (int)M, 3 * H, D + 2 * H, a_cat2row(X, D, D, TNL, 2 * H, 1), W("Wx_all") + e->oO, NX,
+                   e_store(PX + e->oO, NX, W("bx_all") + e->oO), false)))
+      return rc;
+  } else {
+    if ((rc = gemm(e, "px", (int)M, NX, D, a_plain(X, D), W("Wx_all"), NX, e_store(PX, NX, W("bx_all")), false))) return rc;
+    if ((rc = gemm(e, "px_time", (int)M, 3 * H, 2 * H, a_plain(TNL, 2 * H), W("Wt"), 3 * H,
+                   e_store(PX + e->oO, NX, nullptr, E_ACCUM), false)))
+      return rc;
+  }
 
   // ---- recurrences: three independent kernels, one per stream ----
   const int nblk = cdiv(S, RNN_NSEQ);

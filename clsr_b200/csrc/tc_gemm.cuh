@@ -522,7 +522,7 @@ CLSR_DEVINL void produce_tile(const AOp& a, Fast f, int tma, const float* sv, in
   const int kall = one_col >= K ? one_col + 1 : K;
   const int nall = (kall + 7) >> 3;
   if (nfull > 0 && tma) {
-    if (a.mode == A_PLAIN) convert_tile<A_PLAIN>(a, sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
+    if (a.mode == A_PLAIN || a.mode == A_CAT2ROW) convert_tile<A_PLAIN>(a, sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
     else if (a.mode == A_BNRELU) convert_tile<A_BNRELU>(a, sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
     else if (a.mode == A_CATMUL) convert_tile<A_CATMUL>(a, sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
     else convert_tile<A_AFFINE2>(a, sv, svld, m0, M, nfull, ptid, nprod, base, raw2);
@@ -541,6 +541,13 @@ CLSR_DEVINL void produce_tile(const AOp& a, Fast f, int tma, const float* sv, in
 // (A_CATMUL: the planes of the second part re-load columns [off, ...) of the same rows)
 CLSR_DEVINL void tma_issue_tile(const AOp& a, int tma, const CUtensorMap* t1, const CUtensorMap* t2, int nplanes, int m0,
                                 uint32_t base, uint32_t raw2, uint64_t* bar, int lane, int col0 = 0) {
+  if (a.mode == A_CAT2ROW) {   // [A | A2] (G == 1): the planes of the second part come from the second matrix
+    for (int p = lane; p < nplanes; p += 32) {
+      if (p * 8 < a.W1) tma_load_plane(base + p * kPlaneBytes, t1, p * 8, m0, bar);
+      else tma_load_plane(base + p * kPlaneBytes, t2, p * 8 - a.W1, m0, bar);
+    }
+    return;
+  }
   const int w1 = a.mode == A_CATMUL ? a.W1 : (1 << 30);
   for (int p = lane; p < nplanes; p += 32) {
     const int col = p * 8 < w1 ? p * 8 : a.off + p * 8 - w1;
