@@ -413,7 +413,7 @@ def run_b200(a):
         if not k:
             return None
         nbytes, flops = models.get(name, (None, None))
-        t_ms = step_ms(name) if name == "adam_sweep" else k["ms"]
+        t_ms = step_ms(name)   # the byte / flop models are per step: all launches recorded under this name together
         r = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
              "kernel": name, "peak_source": peak_src, "ms": t_ms}
         if nbytes is not None:
