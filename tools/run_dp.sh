@@ -1,7 +1,7 @@
 #!/bin/bash
 # One multi-GPU bench line: tools/run_dp.sh N out.json [bench.py flags...]
 N=$1; OUT=$2; shift 2
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus $N "$@" > $OUT 2> ${OUT%.json}.err
+timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus $N "$@" > $OUT 2> ${OUT%.json}.err
 tail -2 ${OUT%.json}.err | cut -c1-300
 python - <<PY
 import json
