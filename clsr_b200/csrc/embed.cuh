@@ -537,6 +537,25 @@ __global__ void adam_lazy_kernel(float* __restrict__ var, float* __restrict__ m,
 }
 #undef CLSR_ADAM1
 
+// Zero up to kZeroSegs buffers in one launch (byte counts are multiples of 4; 16-byte stores where the segment allows).
+constexpr int kZeroSegs = 24;
+struct ZeroMulti { void* p[kZeroSegs]; long long bytes[kZeroSegs]; int n; };
+__global__ void zero_multi_kernel(const __grid_constant__ ZeroMulti a) {
+  for (int k = 0; k < a.n; ++k) {
+    char* p = static_cast<char*>(a.p[k]);
+    const long long nb = a.bytes[k];
+    if (((reinterpret_cast<uintptr_t>(p) | (uintptr_t)nb) & 15) == 0) {
+      uint4* q = reinterpret_cast<uint4*>(p);
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nb / 16; i += (long long)gridDim.x * blockDim.x)
+        q[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      uint32_t* q = reinterpret_cast<uint32_t*>(p);
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nb / 4; i += (long long)gridDim.x * blockDim.x)
+        q[i] = 0u;
+    }
+  }
+}
+
 // ---- several small per-table launches folded into one (the step is a long chain of short kernels: every launch
 // saved is a few microseconds of tail + ramp) ---------------------------------------------------------------------
 constexpr int kMaxSeg = 5;

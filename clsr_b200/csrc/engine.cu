@@ -1931,17 +1931,28 @@ int reset_slots(clsr_engine* e) {
 }
 
 int zero_step_state(clsr_engine* e) {
-  CK(cudaMemsetAsync(e->counts, 0, 8 * sizeof(int32_t), e->stream));
-  CK(cudaMemsetAsync(e->sumsq, 0, 4 * sizeof(double), e->stream));
-  CK(cudaMemsetAsync(e->acc, 0, 16 * sizeof(double), e->stream));
-  CK(cudaMemsetAsync(e->Pg, 0, (size_t)(e->Ptot + e->Wtot) * 4, e->stream));   // Pg | dWd: one block
+  // counters, loss / norm accumulators, the dense-gradient block (Pg | dWd) and the 16 BatchNorm sum vectors: one launch
+  // instead of 20 memset nodes
+  ZeroMulti z;
+  z.n = 0;
+  auto add = [&](void* p, size_t bytes) { z.p[z.n] = p; z.bytes[z.n] = (long long)bytes; z.n++; };
+  add(e->counts, 8 * sizeof(int32_t));
+  add(e->sumsq, 4 * sizeof(double));
+  add(e->acc, 16 * sizeof(double));
+  add(e->Pg, (size_t)(e->Ptot + e->Wtot) * 4);
   Mlp* ms[4] = {&e->mlp_long, &e->mlp_short, &e->mlp_alpha, &e->mlp_logit};
   for (Mlp* m : ms) {
     BnLayer* bl[2] = {&m->bn0, &m->bn1};
     for (BnLayer* b : bl) {
-      CK(cudaMemsetAsync(b->stat_f, 0, 2 * b->N * sizeof(double), e->stream));
-      CK(cudaMemsetAsync(b->stat_b, 0, 2 * b->N * sizeof(double), e->stream));
+      add(b->stat_f, 2 * b->N * sizeof(double));
+      add(b->stat_b, 2 * b->N * sizeof(double));
     }
+  }
+  zero_multi_kernel<<<e->num_sms, 256, 0, e->stream>>>(z);
+  e->launches++;
+  {
+    cudaError_t c = cudaGetLastError();
+    if (c != cudaSuccess) return fail(e, CLSR_ERR_CUDA, "zero_multi_kernel failed: %s", cudaGetErrorString(c));
   }
   MARK("zero_state");
   return 0;
