@@ -640,6 +640,18 @@ EncodeTiledFn encode_tiled() {
   }();
   return fn;
 }
+// L2 promotion of the TMA requests (a box row is only 32 bytes: the promotion size decides how much of the surrounding
+// line(s) one request brings into L2).  CLSR_TMA_L2 = 0 | 64 | 128 | 256 overrides the default for A/B runs.
+CUtensorMapL2promotion l2_promotion() {
+  static const CUtensorMapL2promotion v = [] {
+    const char* s = getenv("CLSR_TMA_L2");
+    const int b = s ? atoi(s) : 128;
+    return b >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                    : (b >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                : (b >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE));
+  }();
+  return v;
+}
 bool make_tmap(CUtensorMap* m, const float* base, int cols, long long rows, int ld, bool swizzle32 = false) {
   memset(m, 0, sizeof *m);
   EncodeTiledFn enc = encode_tiled();
@@ -650,7 +662,7 @@ bool make_tmap(CUtensorMap* m, const float* base, int cols, long long rows, int 
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
-             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             l2_promotion(),
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // Number of operand streams the TMA can load for this prologue (0: register loads): the rows must be plain
