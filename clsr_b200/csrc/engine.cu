@@ -107,6 +107,11 @@ struct clsr_engine {
   int dwg_smem = 0;
 
   int T, Di, Dc, D, U, H, Q, A0, A1, L0, L1, CA, NX;
+  // graph variants (clsr.py:159-274): which optional blocks exist
+  bool has_gru1 = true;    // short_term_intention GRU (interest_evolve)
+  bool has_gru2 = true;    // causal2 GRU (predict_long_short and not manual_alpha)
+  bool has_alpha = true;   // fcn_alpha MLP (not manual_alpha)
+  int Hf = 0;              // width of the causal2 final state at the front of concat_all (H or 0)
   int oG1, oC1, oG2, oC2, oL, oO, oTN, oTL;
   int Bmax, Smax;
 
@@ -417,6 +422,7 @@ void build_inventory(clsr_engine* e) {
   const std::string gs[2] = {st + "short_term_intention/gru_cell/", sc + "causal2/causal2/gru_cell/"};
   const int gu[2] = {U, H};
   for (int i = 0; i < 2; ++i) {
+    if (!(i == 0 ? e->has_gru1 : e->has_gru2)) continue;   // the reference graph does not create these variables then
     add_dense(e, gs[i] + "gates/kernel", D + gu[i], 2 * gu[i], 1);
     add_dense(e, gs[i] + "gates/bias", 1, 2 * gu[i], 1);
     add_dense(e, gs[i] + "candidate/kernel", D + gu[i], gu[i], 1);
@@ -432,7 +438,8 @@ void build_inventory(clsr_engine* e) {
   add_dense(e, tl + "_time_kernel_w2", D, H, 1);
   const char* v2[] = {"_time_kernel_t1", "_time_kernel_t2", "_o_kernel_t1", "_o_kernel_t2"};
   for (const char* n : v2) add_dense(e, tl + n, H, H, 1);
-  add_fcn(e, sc + "fcn_alpha/nn_part/", e->CA, e->A0, e->A1, &e->mlp_alpha);
+  if (e->has_alpha) add_fcn(e, sc + "fcn_alpha/nn_part/", e->CA, e->A0, e->A1, &e->mlp_alpha);
+  else { memset(&e->mlp_alpha, 0, sizeof e->mlp_alpha); }
   add_fcn(e, "sequential/logit_fcn/nn_part/", H + D, e->L0, e->L1, &e->mlp_logit);
   e->p_wattl = poff(e, lt + "attention_mat");
   e->p_watts = poff(e, st + "attention_fcn/attention_mat");
@@ -520,6 +527,7 @@ int build_weight_maps(clsr_engine* e) {
     const int og[2] = {e->oG1, e->oG2}, oc[2] = {e->oC1, e->oC2};
     const char* ng[2][4] = {{"Wgh1", "Wch1", "Wgh1T", "Wch1T"}, {"Wgh2", "Wch2", "Wgh2T", "Wch2T"}};
     for (int i = 0; i < 2; ++i) {
+      if (!(i == 0 ? e->has_gru1 : e->has_gru2)) continue;   // its PX columns stay zero and are never read
       int u = gu[i];
       long long gk = poff(e, gs[i] + "gates/kernel"), gb = poff(e, gs[i] + "gates/bias");
       long long ck = poff(e, gs[i] + "candidate/kernel"), cb = poff(e, gs[i] + "candidate/bias");
@@ -591,8 +599,10 @@ int build_weight_maps(clsr_engine* e) {
   {
     long long a0T = wd_add(e, "Wa0T", (long long)CA * A0), a1T = wd_add(e, "Wa1T", (long long)A0 * A1);
     long long g0T = wd_add(e, "Wg0T", (long long)(H + D) * L0), g1T = wd_add(e, "Wg1T", (long long)L0 * L1);
-    prep.push_back(mk(a0T, CA, e->mlp_alpha.w0, A0, CA, A0, 1.f, -1, 0, 0.f, 1));
-    prep.push_back(mk(a1T, A0, e->mlp_alpha.w1, A1, A0, A1, 1.f, -1, 0, 0.f, 1));
+    if (e->has_alpha) {
+      prep.push_back(mk(a0T, CA, e->mlp_alpha.w0, A0, CA, A0, 1.f, -1, 0, 0.f, 1));
+      prep.push_back(mk(a1T, A0, e->mlp_alpha.w1, A1, A0, A1, 1.f, -1, 0, 0.f, 1));
+    }
     prep.push_back(mk(g0T, H + D, e->mlp_logit.w0, L0, H + D, L0, 1.f, -1, 0, 0.f, 1));
     prep.push_back(mk(g1T, L0, e->mlp_logit.w1, L1, L0, L1, 1.f, -1, 0, 0.f, 1));
   }
@@ -1365,14 +1375,20 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
   const int nblk = cdiv(S, RNN_NSEQ);
   {
     if ((rc = fork_aux(e))) return rc;
+    // interest_evolve = False: short_term_intention is the user's short embedding itself (clsr.py:169-170)
+    if (!e->has_gru1) CK(cudaMemcpyAsync(e->B("sti"), us, (size_t)S * U * 4, cudaMemcpyDeviceToDevice, e->aux[0]));
     if (rnn_tc_ok(e)) {
       // mma.sync kernels: weights in registers, states thread-local (rnn_tc.cuh)
-      rtc::gru_fwd_tc_kernel<40><<<nblk, 160, 0, e->aux[0]>>>(PX, NX, e->oG1, e->oC1, us, W("Wgh1"), W("Wch1"), e->d_len, S, T,
-                                                            e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"));
-      e->launches++;
-      rtc::gru_fwd_tc_kernel<40><<<nblk, 160, 0, e->aux[1]>>>(PX, NX, e->oG2, e->oC2, nullptr, W("Wgh2"), W("Wch2"), e->d_len, S,
-                                                            T, e->B("g2"), e->B("c2"), e->B("hp2"), e->B("rh2"), e->B("fs"));
-      e->launches++;
+      if (e->has_gru1) {
+        rtc::gru_fwd_tc_kernel<40><<<nblk, 160, 0, e->aux[0]>>>(PX, NX, e->oG1, e->oC1, us, W("Wgh1"), W("Wch1"), e->d_len, S, T,
+                                                              e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"));
+        e->launches++;
+      }
+      if (e->has_gru2) {
+        rtc::gru_fwd_tc_kernel<40><<<nblk, 160, 0, e->aux[1]>>>(PX, NX, e->oG2, e->oC2, nullptr, W("Wgh2"), W("Wch2"), e->d_len, S,
+                                                              T, e->B("g2"), e->B("c2"), e->B("hp2"), e->B("rh2"), e->B("fs"));
+        e->launches++;
+      }
       rtc::lstm_fwd_tc_kernel<40><<<nblk, 160, 0, st>>>(PX, NX, e->oL, e->oTN, e->oTL, W("Km"), e->d_len, S, T, e->B("G4"),
                                                       e->B("cp"), e->B("mp"), e->B("R"));
       e->launches++;
@@ -1380,13 +1396,17 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
     // shared memory: resident recurrent weights + state tiles, or (wide states) the state tiles only
     const int wg = e->rnn_wglob;
     size_t smg = (size_t)((wg ? 0 : U * 2 * U + U * U) + 3 * U * RNN_LD) * 4;
-    gru_fwd_kernel<<<nblk, RNN_THREADS, smg, e->aux[0]>>>(PX, NX, e->oG1, e->oC1, us, W("Wgh1"), W("Wch1"), e->d_len, S, T, U,
-                                                       e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"), wg);
-    e->launches++;
+    if (e->has_gru1) {
+      gru_fwd_kernel<<<nblk, RNN_THREADS, smg, e->aux[0]>>>(PX, NX, e->oG1, e->oC1, us, W("Wgh1"), W("Wch1"), e->d_len, S, T, U,
+                                                         e->B("g1"), e->B("c1"), e->B("hp1"), e->B("rh1"), e->B("sti"), wg);
+      e->launches++;
+    }
     size_t smg2 = (size_t)((wg ? 0 : H * 2 * H + H * H) + 3 * H * RNN_LD) * 4;
-    gru_fwd_kernel<<<nblk, RNN_THREADS, smg2, e->aux[1]>>>(PX, NX, e->oG2, e->oC2, nullptr, W("Wgh2"), W("Wch2"), e->d_len, S, T, H,
-                                                        e->B("g2"), e->B("c2"), e->B("hp2"), e->B("rh2"), e->B("fs"), wg);
-    e->launches++;
+    if (e->has_gru2) {
+      gru_fwd_kernel<<<nblk, RNN_THREADS, smg2, e->aux[1]>>>(PX, NX, e->oG2, e->oC2, nullptr, W("Wgh2"), W("Wch2"), e->d_len, S, T, H,
+                                                          e->B("g2"), e->B("c2"), e->B("hp2"), e->B("rh2"), e->B("fs"), wg);
+      e->launches++;
+    }
     size_t sml = (size_t)((wg ? 0 : H * 4 * H) + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
     lstm_fwd_kernel<<<nblk, RNN_THREADS, sml, st>>>(PX, NX, e->oL, e->oTN, e->oTL, W("Km"), e->d_len, S, T, H,
                                                     e->B("G4"), e->B("cp"), e->B("mp"), e->B("R"), wg);
@@ -1449,10 +1469,13 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
 
   // ---- alpha gate, fusion, prediction MLP ----
   float *ca = e->B("ca"), *mo = e->B("mo");
-  concat_alpha_kernel<<<grid1d(e, (long long)B * e->CA, 256), 256, 0, st>>>(
-      e->B("fs"), tgt, e->B("afl"), e->B("afs"), c.ttn, c.seq_stride, T, H, D, G, B, ca);
-  POST("concat_alpha");
-  if ((rc = mlp_fwd(e, e->mlp_alpha, ca, B, e->B("ha0"), e->B("ha1"), e->B("alogit"), train, update_bn))) return rc;
+  if (e->has_alpha) {
+    concat_alpha_kernel<<<grid1d(e, (long long)B * e->CA, 256), 256, 0, st>>>(
+        e->B("fs"), tgt, e->B("afl"), e->B("afs"), c.ttn, c.seq_stride, T, H, D, G, B, ca, e->Hf);
+    POST("concat_alpha");
+    if ((rc = mlp_fwd(e, e->mlp_alpha, ca, B, e->B("ha0"), e->B("ha1"), e->B("alogit"), train, update_bn))) return rc;
+  }
+  // (manual_alpha: the "alogit" buffer holds logit(manual_alpha_value) in every row since clsr_create)
   head_mid_kernel<<<grid1d(e, (long long)B * (H + D), 256), 256, 0, st>>>(e->B("alogit"), e->B("afl"), e->B("afs"), tgt, H,
                                                                         D, G, B, e->B("alpha"), mo);
   POST("head_mid");
@@ -1516,8 +1539,9 @@ int backward(clsr_engine* e, const StepCtx& c) {
   head_mid_bwd_kernel<<<grid1d(e, (long long)B * 32, 256), 256, 0, st>>>(e->B("dmo"), H + D, e->B("afl"), e->B("afs"),
                                                                        e->B("alpha"), H, G, B, e->B("dalogit"));
   POST("head_mid_bwd");
-  if ((rc = mlp_bwd(e, e->mlp_alpha, e->B("ca"), B, e->B("ha0"), e->B("ha1"), e->B("dalogit"), e->B("dha1"), e->B("dha0"),
-                    W("Wa0T"), W("Wa1T"), e->B("dca"))))
+  // (manual_alpha: no alpha MLP; "dca" is zero since clsr_create and nothing writes it)
+  if (e->has_alpha && (rc = mlp_bwd(e, e->mlp_alpha, e->B("ca"), B, e->B("ha0"), e->B("ha1"), e->B("dalogit"), e->B("dha1"),
+                                    e->B("dha0"), W("Wa0T"), W("Wa1T"), e->B("dca"))))
     return rc;
   const float* bpr_gs = nullptr;
   if (e->cfg.contrastive_kind == 1) {
@@ -1530,7 +1554,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
   head_final_bwd_kernel<<<grid1d(e, (long long)S * D, 128), 128, 0, st>>>(
       e->B("dmo"), e->B("dca"), e->B("alpha"), e->B("afl"), e->B("afs"), e->B("hm"), e->B("hr"), e->d_len, e->counts,
       e->cfg.contrastive_len_threshold, e->cfg.triplet_margin, e->cfg.contrastive_weight, bpr_gs, H, D, G, S, e->B("dfs"),
-      e->B("dtgt"), e->B("dafl"), e->B("dafs"), e->B("dhm"), e->B("dhr"), e->acc);
+      e->B("dtgt"), e->B("dafl"), e->B("dafs"), e->B("dhm"), e->B("dhr"), e->acc, e->Hf);
   POST("head_final_bwd");
 
   // ---- short-term attention ----
@@ -1617,16 +1641,22 @@ int backward(clsr_engine* e, const StepCtx& c) {
   {
     // the three BPTT kernels write disjoint column ranges of dPX: run them side by side
     if ((rc = fork_aux(e))) return rc;
+    // interest_evolve = False: the gradient of short_term_intention IS the gradient of the short user rows
+    if (!e->has_gru1) CK(cudaMemcpyAsync(e->B("dus"), e->B("dsti"), (size_t)S * U * 4, cudaMemcpyDeviceToDevice, e->aux[0]));
     if (rnn_tc_ok(e)) {
       rtc::lstm_bwd_tc_kernel<40><<<nblk, 160, 0, st>>>(PX, NX, e->oL, e->oTN, e->oTL, e->B("G4"), e->B("cp"), W("KmT"), dR,
                                                       e->d_len, S, T, dPX);
       e->launches++;
-      rtc::gru_bwd_tc_kernel<40><<<nblk, 160, 0, e->aux[0]>>>(e->B("g1"), e->B("c1"), e->B("hp1"), W("Wgh1T"), W("Wch1T"),
-                                                            e->B("dsti"), e->d_len, S, T, dPX, NX, e->oG1, e->oC1, e->B("dus"));
-      e->launches++;
-      rtc::gru_bwd_tc_kernel<40><<<nblk, 160, 0, e->aux[1]>>>(e->B("g2"), e->B("c2"), e->B("hp2"), W("Wgh2T"), W("Wch2T"),
-                                                            e->B("dfs"), e->d_len, S, T, dPX, NX, e->oG2, e->oC2, nullptr);
-      e->launches++;
+      if (e->has_gru1) {
+        rtc::gru_bwd_tc_kernel<40><<<nblk, 160, 0, e->aux[0]>>>(e->B("g1"), e->B("c1"), e->B("hp1"), W("Wgh1T"), W("Wch1T"),
+                                                              e->B("dsti"), e->d_len, S, T, dPX, NX, e->oG1, e->oC1, e->B("dus"));
+        e->launches++;
+      }
+      if (e->has_gru2) {
+        rtc::gru_bwd_tc_kernel<40><<<nblk, 160, 0, e->aux[1]>>>(e->B("g2"), e->B("c2"), e->B("hp2"), W("Wgh2T"), W("Wch2T"),
+                                                              e->B("dfs"), e->d_len, S, T, dPX, NX, e->oG2, e->oC2, nullptr);
+        e->launches++;
+      }
     } else {
     const int wg = e->rnn_wglob;
     size_t sml = (size_t)((wg ? 0 : H * 4 * H) + 2 * H * RNN_LD + 4 * H * RNN_LD) * 4;
@@ -1634,13 +1664,17 @@ int backward(clsr_engine* e, const StepCtx& c) {
                                                     e->d_len, S, T, H, dPX, wg);
     e->launches++;
     size_t smg = (size_t)((wg ? 0 : 2 * U * U + U * U) + 5 * U * RNN_LD) * 4;
-    gru_bwd_kernel<<<nblk, RNN_THREADS, smg, e->aux[0]>>>(e->B("g1"), e->B("c1"), e->B("hp1"), W("Wgh1T"), W("Wch1T"), e->B("dsti"),
-                                                       e->d_len, S, T, U, dPX, NX, e->oG1, e->oC1, e->B("dus"), wg);
-    e->launches++;
+    if (e->has_gru1) {
+      gru_bwd_kernel<<<nblk, RNN_THREADS, smg, e->aux[0]>>>(e->B("g1"), e->B("c1"), e->B("hp1"), W("Wgh1T"), W("Wch1T"), e->B("dsti"),
+                                                         e->d_len, S, T, U, dPX, NX, e->oG1, e->oC1, e->B("dus"), wg);
+      e->launches++;
+    }
     size_t smg2 = (size_t)((wg ? 0 : 2 * H * H + H * H) + 5 * H * RNN_LD) * 4;
-    gru_bwd_kernel<<<nblk, RNN_THREADS, smg2, e->aux[1]>>>(e->B("g2"), e->B("c2"), e->B("hp2"), W("Wgh2T"), W("Wch2T"), e->B("dfs"),
-                                                        e->d_len, S, T, H, dPX, NX, e->oG2, e->oC2, nullptr, wg);
-    e->launches++;
+    if (e->has_gru2) {
+      gru_bwd_kernel<<<nblk, RNN_THREADS, smg2, e->aux[1]>>>(e->B("g2"), e->B("c2"), e->B("hp2"), W("Wgh2T"), W("Wch2T"), e->B("dfs"),
+                                                          e->d_len, S, T, H, dPX, NX, e->oG2, e->oC2, nullptr, wg);
+      e->launches++;
+    }
     }
     if ((rc = join_aux(e, "rnn_bwd(time4lstm|gru_sti|gru_causal2)"))) return rc;
   }
@@ -1668,10 +1702,14 @@ int backward(clsr_engine* e, const StepCtx& c) {
     }
     POST("time_feat_bwd");
   }
-  if ((rc = dwgemm(e, "dWgh1", (int)M, U, 2 * U, a_plain(e->B("hp1"), U), a_plain(dPX + e->oG1, NX), dW("Wgh1"), 2 * U, nullptr))) return rc;
-  if ((rc = dwgemm(e, "dWch1", (int)M, U, U, a_plain(e->B("rh1"), U), a_plain(dPX + e->oC1, NX), dW("Wch1"), U, nullptr))) return rc;
-  if ((rc = dwgemm(e, "dWgh2", (int)M, H, 2 * H, a_plain(e->B("hp2"), H), a_plain(dPX + e->oG2, NX), dW("Wgh2"), 2 * H, nullptr))) return rc;
-  if ((rc = dwgemm(e, "dWch2", (int)M, H, H, a_plain(e->B("rh2"), H), a_plain(dPX + e->oC2, NX), dW("Wch2"), H, nullptr))) return rc;
+  if (e->has_gru1) {
+    if ((rc = dwgemm(e, "dWgh1", (int)M, U, 2 * U, a_plain(e->B("hp1"), U), a_plain(dPX + e->oG1, NX), dW("Wgh1"), 2 * U, nullptr))) return rc;
+    if ((rc = dwgemm(e, "dWch1", (int)M, U, U, a_plain(e->B("rh1"), U), a_plain(dPX + e->oC1, NX), dW("Wch1"), U, nullptr))) return rc;
+  }
+  if (e->has_gru2) {
+    if ((rc = dwgemm(e, "dWgh2", (int)M, H, 2 * H, a_plain(e->B("hp2"), H), a_plain(dPX + e->oG2, NX), dW("Wgh2"), 2 * H, nullptr))) return rc;
+    if ((rc = dwgemm(e, "dWch2", (int)M, H, H, a_plain(e->B("rh2"), H), a_plain(dPX + e->oC2, NX), dW("Wch2"), H, nullptr))) return rc;
+  }
   if ((rc = dwgemm(e, "dKm", (int)M, H, 4 * H, a_plain(e->B("mp"), H), a_plain(dPX + e->oL, NX), dW("Km"), 4 * H, nullptr))) return rc;
   if ((rc = dw_group_flush(e, "dW_bptt_group"))) return rc;
 
@@ -2030,7 +2068,11 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
 
   e->T = cfg->seq_len; e->Di = cfg->item_dim; e->Dc = cfg->cate_dim; e->D = e->Di + e->Dc; e->U = cfg->user_dim;
   e->H = cfg->hidden; e->Q = e->U + e->D; e->A0 = cfg->att0; e->A1 = cfg->att1; e->L0 = cfg->fc0; e->L1 = cfg->fc1;
-  e->CA = 2 * e->H + 2 * e->D + 1;
+  e->has_gru1 = !cfg->no_interest_evolve;
+  e->has_alpha = !cfg->manual_alpha;
+  e->has_gru2 = e->has_alpha && !cfg->no_predict_long_short;
+  e->Hf = e->has_gru2 ? e->H : 0;
+  e->CA = e->Hf + 2 * e->D + e->H + 1;
   const int U = e->U, H = e->H, D = e->D, T = e->T;
   e->oG1 = 0; e->oC1 = 2 * U; e->oG2 = 3 * U; e->oC2 = 3 * U + 2 * H; e->oL = 3 * U + 3 * H;
   e->oO = e->oL + 3 * H; e->oTN = e->oL + 4 * H; e->oTL = e->oL + 5 * H; e->NX = e->oL + 6 * H;
@@ -2128,6 +2170,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
       const Mlp& m = *ms[i];
       const bool shape = m.n0 % 4 == 0 && m.n1 % 4 == 0 && m.n0 <= kCoopMaxN && m.n1 <= kCoopMaxN && m.n0 >= 4 && m.n1 >= 4 &&
                          (m.in + 3) / 4 <= kCoopThreads && 2 * m.n0 <= kPeerSlots;
+      if (!shape) { *flag[i] = false; continue; }   // (also the absent alpha MLP of manual_alpha: all sizes zero)
       const size_t sf = (size_t)coop_fwd_smem(m.in, m.n0, m.n1, e->coop_rpc).total * 4;
       const size_t sb = (size_t)coop_bwd_smem(m.in, m.n0, m.n1, e->coop_rpc).total * 4;
       const bool fits = sf + ff.sharedSizeBytes + 512 <= (size_t)e->smem_optin && sb + fb.sharedSizeBytes + 512 <= (size_t)e->smem_optin;
@@ -2179,6 +2222,14 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
       {"bpr_gs", Bm * 4},
   };
   for (auto& s : specs) CKC(fbuf(e, s.n, s.sz));
+  if (cfg->manual_alpha) {
+    // alpha is the constant manual_alpha_value (clsr.py:272-274): the fusion kernels read sigmoid("alogit"), so the buffer
+    // is filled once with its logit (+-inf at the ends: sigmoid gives exactly 0 / 1)
+    const double a = (double)cfg->manual_alpha_value;
+    const float lg = a <= 0.0 ? -INFINITY : (a >= 1.0 ? INFINITY : (float)log(a / (1.0 - a)));
+    std::vector<float> h((size_t)Bm, lg);
+    CKCU(cudaMemcpy(e->B("alogit"), h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   CKCU(cudaDeviceSynchronize());
   *out = e;
   return CLSR_OK;

@@ -201,18 +201,19 @@ __global__ void rowdot_bwd_kernel(const float* __restrict__ dout, const float* _
 __global__ void concat_alpha_kernel(const float* __restrict__ fs, const float* __restrict__ tgt,
                                     const float* __restrict__ afl, const float* __restrict__ afs,
                                     const float* __restrict__ ttn, int seq_stride, int T, int H, int D, int G,
-                                    int B, float* __restrict__ ca) {
-  const int CA = 2 * H + 2 * D + 1;
+                                    int B, float* __restrict__ ca, int Hf) {
+  // Hf: width of the causal2 final state in front (H, or 0 with predict_long_short = False: fs is then not read)
+  const int CA = Hf + 2 * D + H + 1;
   long long n = (long long)B * CA;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i / CA), k = (int)(i - (long long)b * CA);
     int s = b / G;
     float v;
-    if (k < H) v = fs[(size_t)s * H + k];
-    else if (k < H + D) v = tgt[(size_t)b * D + (k - H)];
-    else if (k < H + 2 * D) v = afl[(size_t)s * D + (k - H - D)];
-    else if (k < 2 * H + 2 * D) v = afs[(size_t)b * H + (k - H - 2 * D)];
+    if (k < Hf) v = fs[(size_t)s * H + k];
+    else if (k < Hf + D) v = tgt[(size_t)b * D + (k - Hf)];
+    else if (k < Hf + 2 * D) v = afl[(size_t)s * D + (k - Hf - D)];
+    else if (k < Hf + 2 * D + H) v = afs[(size_t)b * H + (k - Hf - 2 * D)];
     else v = ttn[(size_t)s * seq_stride + (T - 1)];
     ca[i] = v;
   }
@@ -337,8 +338,8 @@ __global__ void head_final_bwd_kernel(const float* __restrict__ dmo, const float
                                       float* __restrict__ dfs,
                                       float* __restrict__ dtgt, float* __restrict__ dafl,
                                       float* __restrict__ dafs, float* __restrict__ dhm,
-                                      float* __restrict__ dhr, double* __restrict__ acc) {
-  const int CA = 2 * H + 2 * D + 1, W = H + D;
+                                      float* __restrict__ dhr, double* __restrict__ acc, int Hf) {
+  const int CA = Hf + 2 * D + H + 1, W = H + D;   // Hf: see concat_alpha_kernel
   const float den = (float)G * (float)counts[0];
   float l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S * D; i += gridDim.x * blockDim.x) {
@@ -352,10 +353,10 @@ __global__ void head_final_bwd_kernel(const float* __restrict__ dmo, const float
       const float a = alpha[b];
       const float due = dmo[b * W + d];
       const float sh = afs[b * H + d];
-      sfs += dca[b * CA + d];
-      dtgt[b * D + d] = dmo[b * W + H + d] + dca[b * CA + H + d];
-      float dl = dca[b * CA + H + D + d] + due * a;
-      float ds = dca[b * CA + H + 2 * D + d] + due * (1.f - a);
+      if (Hf) sfs += dca[b * CA + d];
+      dtgt[b * D + d] = dmo[b * W + H + d] + dca[b * CA + Hf + d];
+      float dl = dca[b * CA + Hf + D + d] + due * a;
+      float ds = dca[b * CA + Hf + 2 * D + d] + due * (1.f - a);
       if (bpr_gs) {  // BPR: gradients through the four inner products, derivative = sigmoid(x_i)
         const float g1 = c * bpr_gs[b * 4 + 0], g2 = c * bpr_gs[b * 4 + 1], g3 = c * bpr_gs[b * 4 + 2],
                     g4 = c * bpr_gs[b * 4 + 3];

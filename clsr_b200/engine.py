@@ -32,6 +32,8 @@ class Config(C.Structure):
         ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float), ("clip_norm", C.c_int32),
         ("max_grad_norm", C.c_float), ("bn_momentum", C.c_float), ("bn_eps", C.c_float),
         ("math_mode", C.c_int32), ("max_seqs", C.c_int32),
+        ("no_interest_evolve", C.c_int32), ("no_predict_long_short", C.c_int32), ("manual_alpha", C.c_int32),
+        ("manual_alpha_value", C.c_float),
     ]
 
 
@@ -212,7 +214,8 @@ class Engine:
                  embed_l2=1e-6, layer_l2=1e-6, contrastive_loss="triplet", triplet_margin=1.0,
                  contrastive_weight=0.1, discrepancy_weight=0.01, contrastive_len_threshold=5,
                  contrastive_recent_k=3, optimizer="adam", learning_rate=1e-3, clip_norm=True,
-                 max_grad_norm=2.0, device=0, math_mode=0, training=True, alloc_tables=True, max_seqs=0):
+                 max_grad_norm=2.0, device=0, math_mode=0, training=True, alloc_tables=True, max_seqs=0,
+                 interest_evolve=True, predict_long_short=True, manual_alpha=False, manual_alpha_value=0.5):
         import torch
         if not torch.cuda.is_available():
             raise EngineError("clsr_b200 needs a CUDA device (no CPU fallback)")
@@ -231,7 +234,9 @@ class Engine:
             contrastive_len_threshold=contrastive_len_threshold, contrastive_recent_k=contrastive_recent_k,
             optimizer=0 if optimizer == "adam" else 1, learning_rate=learning_rate, beta1=0.9, beta2=0.999,
             adam_eps=1e-8, clip_norm=1 if clip_norm else 0, max_grad_norm=max_grad_norm, bn_momentum=0.95,
-            bn_eps=1e-4, math_mode=math_mode, max_seqs=int(max_seqs or 0))
+            bn_eps=1e-4, math_mode=math_mode, max_seqs=int(max_seqs or 0),
+            no_interest_evolve=0 if interest_evolve else 1, no_predict_long_short=0 if predict_long_short else 1,
+            manual_alpha=1 if manual_alpha else 0, manual_alpha_value=float(manual_alpha_value))
         self.device = torch.device("cuda", device)
         self.h = C.c_void_p()
         rc = self.lib.clsr_create(C.byref(self.cfg), C.byref(self.h))

@@ -35,8 +35,11 @@ def _fcn(spec, scope, in_dim, sizes):
     spec.append((scope + "b_nn_output", (1,), "zeros", True))
 
 
-def dense_spec(D, U, H, att_sizes, layer_sizes):
-    """Ordered [(name, shape, init, trainable)] for every non-table variable."""
+def dense_spec(D, U, H, att_sizes, layer_sizes, interest_evolve=True, predict_long_short=True, manual_alpha=False):
+    """Ordered [(name, shape, init, trainable)] for every non-table variable.  The three flags are the graph
+    variants of _build_seq_graph (clsr.py:159-274): without interest_evolve the short_term_intention GRU does not
+    exist, with manual_alpha neither the causal2 GRU nor the alpha MLP, without predict_long_short the causal2 GRU
+    is absent and the alpha MLP's input loses its final state."""
     assert H == D, "the CLSR graph only type-checks when hidden_size == item_dim + cate_dim"
     s = []
     lt = SC + "long_term/attention_fcn/"
@@ -46,7 +49,11 @@ def dense_spec(D, U, H, att_sizes, layer_sizes):
     Q = U + D
     s.append((st + "attention_fcn/attention_mat", (H, Q), "tnormal", True))
     _fcn(s, st + "attention_fcn/att_fcn/nn_part/", 4 * Q, att_sizes)
-    for scope, units in ((st + "short_term_intention/gru_cell/", U), (SC + "causal2/causal2/gru_cell/", H)):
+    has_gru2 = predict_long_short and not manual_alpha
+    for scope, units, present in ((st + "short_term_intention/gru_cell/", U, interest_evolve),
+                                  (SC + "causal2/causal2/gru_cell/", H, has_gru2)):
+        if not present:
+            continue
         s.append((scope + "gates/kernel", (D + units, 2 * units), "glorot", True))
         s.append((scope + "gates/bias", (2 * units,), "ones", True))
         s.append((scope + "candidate/kernel", (D + units, units), "glorot", True))
@@ -61,7 +68,8 @@ def dense_spec(D, U, H, att_sizes, layer_sizes):
         s.append((tl + n, (D, H), "glorot", True))
     for n in ("_time_kernel_t1", "_time_kernel_t2", "_o_kernel_t1", "_o_kernel_t2"):
         s.append((tl + n, (H, H), "glorot", True))
-    _fcn(s, SC + "fcn_alpha/nn_part/", 2 * H + 2 * D + 1, att_sizes)
+    if not manual_alpha:
+        _fcn(s, SC + "fcn_alpha/nn_part/", (H if has_gru2 else 0) + 2 * D + H + 1, att_sizes)
     _fcn(s, LOGIT, H + D, layer_sizes)
     return s
 
@@ -97,11 +105,11 @@ def init_array(rng, shape, kind, init_value=0.01):
 
 
 def init_params(n_items, n_cates, n_users, Di=32, Dc=8, U=40, H=40, att_sizes=(80, 40),
-                layer_sizes=(100, 64), seed=None, init_value=0.01, tables=True):
-    """Fresh parameters as an ordered {name: float32 array}."""
+                layer_sizes=(100, 64), seed=None, init_value=0.01, tables=True, **variant):
+    """Fresh parameters as an ordered {name: float32 array} (variant: the dense_spec flags)."""
     rng = np.random.default_rng(seed)
     out = OrderedDict()
-    for name, shape, kind, _ in dense_spec(Di + Dc, U, H, list(att_sizes), list(layer_sizes)):
+    for name, shape, kind, _ in dense_spec(Di + Dc, U, H, list(att_sizes), list(layer_sizes), **variant):
         out[name] = init_array(rng, shape, kind, init_value)
     if tables:
         for name, shape in table_spec(n_items, n_cates, n_users, Di, Dc, U):

@@ -59,6 +59,11 @@ typedef struct clsr_config {
   float bn_momentum, bn_eps; /* 0.95 / 1e-4 (base_model.py:676-677) */
   int32_t math_mode;         /* 0 = fp32 SIMT everywhere, 1 = bf16 tcgen05 for the large GEMMs */
   int32_t max_seqs;          /* capacity in sequences (rows / group); 0 = max_rows (ungrouped batches of max_rows fit) */
+  /* Graph variants of _build_seq_graph (clsr.py:159-274); all zero = the CLSR configuration the reference ships. */
+  int32_t no_interest_evolve;    /* hparams.interest_evolve = False: short_term_intention = user_short_embedding (no GRU) */
+  int32_t no_predict_long_short; /* hparams.predict_long_short = False: no causal2 GRU, alpha MLP input without its final state */
+  int32_t manual_alpha;          /* hparams.manual_alpha = True: alpha = manual_alpha_value, no causal2 GRU, no alpha MLP */
+  float manual_alpha_value;
 } clsr_config;
 
 /* One feed_dict (sequential_iterator.py:718-731), as plain arrays.  `group` declares that

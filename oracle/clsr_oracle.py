@@ -67,6 +67,11 @@ class OracleConfig:
     beta1: float = 0.9
     beta2: float = 0.999
     adam_eps: float = 1e-8
+    # graph variants (clsr.py:159-274)
+    interest_evolve: bool = True
+    predict_long_short: bool = True
+    manual_alpha: bool = False
+    manual_alpha_value: float = 0.5
 
 
 def _t(x, dtype):
@@ -272,7 +277,10 @@ def forward(params, batch, cfg, train, dtype=torch.float64, leaves=None):
     hist_mean = (hist * real_mask.unsqueeze(-1)).sum(1) / real_mask.sum(1, keepdim=True)
 
     # short term (clsr.py:159-222)
-    sti = _gru(hist, length, us, p, SC + "short_term/short_term_intention/gru_cell/")
+    if cfg.interest_evolve:   # clsr.py:160-170
+        sti = _gru(hist, length, us, p, SC + "short_term/short_term_intention/gru_cell/")
+    else:
+        sti = us
     position = torch.flip(torch.cumsum(torch.flip(real_mask, [1]), 1), [1])
     recent = ((position >= 1) & (position <= cfg.contrastive_recent_k)).to(dtype)
     hist_recent = (hist * recent.unsqueeze(-1)).sum(1) / recent.sum(1, keepdim=True)
@@ -283,12 +291,20 @@ def forward(params, batch, cfg, train, dtype=torch.float64, leaves=None):
     afs = att_short.sum(1)
 
     # alpha (clsr.py:225-275)
-    fs = _gru(hist, length, torch.zeros(hist.shape[0], H, dtype=dtype), p, SC + "causal2/causal2/gru_cell/")
-    concat_all = torch.cat([fs, target, afl, afs, ttn[:, -1:]], 1)
-    alpha_logit = _fcn_net(concat_all, p, SC + "fcn_alpha/nn_part/", cfg.att_fcn_layer_sizes, train, cfg,
-                           stats, inter, "alpha")
-    alpha = torch.sigmoid(alpha_logit)
-    user_embed = afl * alpha + afs * (1.0 - alpha)
+    fs = None
+    if not cfg.manual_alpha:
+        if cfg.predict_long_short:
+            fs = _gru(hist, length, torch.zeros(hist.shape[0], H, dtype=dtype), p, SC + "causal2/causal2/gru_cell/")
+            concat_all = torch.cat([fs, target, afl, afs, ttn[:, -1:]], 1)
+        else:
+            concat_all = torch.cat([target, afl, afs, ttn[:, -1:]], 1)
+        alpha_logit = _fcn_net(concat_all, p, SC + "fcn_alpha/nn_part/", cfg.att_fcn_layer_sizes, train, cfg,
+                               stats, inter, "alpha")
+        alpha = torch.sigmoid(alpha_logit)
+        user_embed = afl * alpha + afs * (1.0 - alpha)
+    else:   # clsr.py:272-274
+        alpha = torch.full((hist.shape[0], 1), cfg.manual_alpha_value, dtype=dtype)
+        user_embed = afl * cfg.manual_alpha_value + afs * (1.0 - cfg.manual_alpha_value)
     model_output = torch.cat([user_embed, target], 1)
     logit = _fcn_net(model_output, p, "sequential/logit_fcn/nn_part/", cfg.layer_sizes, train, cfg, stats,
                      inter, "logit")

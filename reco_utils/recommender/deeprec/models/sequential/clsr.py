@@ -26,9 +26,6 @@ class CLSRModel(SequentialBaseModel):
         hp = self.hparams
         unsupported = []
         if hp.sequential_model != "time4lstm": unsupported.append("sequential_model=%s" % hp.sequential_model)
-        if not hp.interest_evolve: unsupported.append("interest_evolve=False")
-        if not hp.predict_long_short: unsupported.append("predict_long_short=False")
-        if hp.manual_alpha: unsupported.append("manual_alpha=True")
         if hp.loss != "softmax": unsupported.append("loss=%s" % hp.loss)
         if hp.enable_BN is not True: unsupported.append("enable_BN=%s" % hp.enable_BN)
         if list(hp.activation) != ["relu", "relu"]: unsupported.append("activation=%s" % hp.activation)
@@ -73,13 +70,21 @@ class CLSRModel(SequentialBaseModel):
             contrastive_len_threshold=hp.contrastive_length_threshold,
             contrastive_recent_k=hp.contrastive_recent_k, optimizer=hp.optimizer,
             learning_rate=hp.learning_rate, clip_norm=bool(hp.is_clip_norm), max_grad_norm=float(hp.max_grad_norm),
-            math_mode=self.math_mode)
+            math_mode=self.math_mode, **self._variant())
         if hp.init_method != "tnormal":
             raise NotImplementedError("init_method=%s (only tnormal) on the B200 CLSR path" % hp.init_method)
         self.engine.set_params(P.init_params(
             self.item_vocab_length, self.cate_vocab_length, self.user_vocab_length, hp.item_embedding_dim,
             hp.cate_embedding_dim, hp.user_embedding_dim, hp.hidden_size, hp.att_fcn_layer_sizes, hp.layer_sizes,
-            seed=self.seed, init_value=hp.init_value))
+            seed=self.seed, init_value=hp.init_value,
+            **{k: v for k, v in self._variant().items() if k != "manual_alpha_value"}))
+
+    def _variant(self):
+        """Graph variants of the reference's _build_seq_graph (clsr.py:159-274) selected by hparams."""
+        hp = self.hparams
+        return dict(interest_evolve=bool(hp.interest_evolve), predict_long_short=bool(hp.predict_long_short),
+                    manual_alpha=bool(hp.manual_alpha),
+                    manual_alpha_value=float(hp.manual_alpha_value if "manual_alpha_value" in hp else 0.5))
 
     # ---- variables <-> checkpoints ---------------------------------------------------------------
     def _export_variables(self):

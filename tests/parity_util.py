@@ -10,8 +10,10 @@ RETAIN = ["logit", "afl", "afs", "hist_mean", "hist_recent", "sti", "fs", "rnn_o
 
 
 def small_problem(S=24, G=5, T=50, seed=3, n_items=3000, n_cates=40, n_users=200, init_scale=8.0,
-                  edge_lengths=True, dims=None):
-    """dims: (item_dim, cate_dim, user_dim = hidden) for the wide configurations (BASELINE configs 4-5)."""
+                  edge_lengths=True, dims=None, variant=None):
+    """dims: (item_dim, cate_dim, user_dim = hidden) for the wide configurations (BASELINE configs 4-5);
+    variant: graph flags (interest_evolve / predict_long_short / manual_alpha) deciding which variables exist."""
+    vkw = {k: v for k, v in (variant or {}).items() if k != "manual_alpha_value"}
     src = synth.SyntheticSource(n_items=n_items, n_cates=n_cates, n_users=n_users, T=T, seed=seed)
     feed = src.batch(S, G - 1) if G > 1 else src.batch(S, 0)
     if G == 1:
@@ -19,9 +21,9 @@ def small_problem(S=24, G=5, T=50, seed=3, n_items=3000, n_cates=40, n_users=200
         lab[::5] = 1.0
         feed["labels"] = lab
     if dims:
-        prm = P.init_params(n_items, n_cates, n_users, Di=dims[0], Dc=dims[1], U=dims[2], H=dims[2], seed=seed)
+        prm = P.init_params(n_items, n_cates, n_users, Di=dims[0], Dc=dims[1], U=dims[2], H=dims[2], seed=seed, **vkw)
     else:
-        prm = P.init_params(n_items, n_cates, n_users, seed=seed)
+        prm = P.init_params(n_items, n_cates, n_users, seed=seed, **vkw)
     return feed, scale_params(prm, seed, init_scale)
 
 

@@ -483,3 +483,91 @@ def test_graph_replayed_steps_match_eager_steps(cuda_lib, math_mode):
         moved = np.linalg.norm((pb[k] - prm[k].reshape(pb[k].shape)).astype(np.float64))
         diff = np.linalg.norm((pa[k] - pb[k]).astype(np.float64))
         assert diff <= 0.25 * moved + 1e-7, (k, diff, moved)
+
+
+VARIANTS = [dict(interest_evolve=False), dict(predict_long_short=False), dict(manual_alpha=True, manual_alpha_value=0.3),
+            dict(interest_evolve=False, manual_alpha=True, manual_alpha_value=1.0)]
+
+
+@pytest.mark.parametrize("math_mode", [0, 1])
+@pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: "-".join("%s=%s" % kv for kv in v.items()))
+def test_graph_variants_match_oracle(cuda_lib, variant, math_mode):
+    """hparams.interest_evolve / predict_long_short / manual_alpha select sub-graphs of _build_seq_graph
+    (clsr.py:159-274): the variable inventory, logits, alpha, losses and every gradient follow the oracle's
+    restatement of the same branches."""
+    import torch
+    from oracle import clsr_oracle as O
+    from clsr_b200.engine import STEP_NO_OPTIMIZER, STEP_NO_BN_UPDATE, TABLE_VARS
+    G, S = 5, 48
+    feed, prm = PU.small_problem(S=S, G=G, seed=9, variant=variant)
+    feed = PU.set_lengths(feed, [1, 50, 3, 5, 6, 2], G)
+    B = S * G
+    eng = PU.make_engine(prm, NI, NC, NU, max_rows=B, G=G, math_mode=math_mode, **variant)
+    assert set(eng.get_dense(0)) == {k for k in prm if "/embedding/" not in k}
+    gone = [k for k in prm if ("short_term_intention" in k and not variant.get("interest_evolve", True)) or
+            ("causal2" in k and (variant.get("manual_alpha") or not variant.get("predict_long_short", True))) or
+            ("fcn_alpha" in k and variant.get("manual_alpha"))]
+    assert not gone, gone
+    losses = eng.train_step(feed, group=G, flags=STEP_NO_OPTIMIZER | STEP_NO_BN_UPDATE)
+    cfg = PU.oracle_config(G, **variant)
+    out, L, dense, slices, _ = O.compute_gradients(prm, feed, cfg, torch.float64)
+    ftol, btol = (2e-4, 2e-2) if math_mode else (FWD_TOL, BWD_TOL)
+    assert PU.relerr(eng.debug("logit", (B,)), out["logit"].detach().numpy().reshape(-1)) < ftol
+    a_ref = out["alpha"].detach().numpy().reshape(-1)
+    assert PU.relerr(eng.debug("alpha", (B,)), np.broadcast_to(a_ref, (B,)) if a_ref.size == 1 else a_ref) < ftol
+    for k in ("loss", "data_loss", "regular_loss", "contrastive_loss", "discrepancy_loss"):
+        assert abs(losses[k] - float(L[k])) <= ftol * max(abs(float(L[k])), 1e-6), (k, losses[k], float(L[k]))
+    dg = eng.get_dense(3)
+    bad = {}
+    for name, gref in dense.items():
+        if name.endswith("b_nn_output"):
+            continue
+        err = PU.relerr_l2(dg[name], gref.numpy().reshape(-1))
+        if not err < btol:
+            bad[name] = err
+    for t, name in TABLE_VARS.items():
+        ids, rows = eng.sparse_grad(t)
+        idx, val = slices[name.split("/")[-1]]
+        ref = np.zeros(prm[name].shape, np.float64)
+        np.add.at(ref, idx.numpy(), val.numpy())
+        got = np.zeros(prm[name].shape, np.float64)
+        got[ids] = rows
+        err = PU.relerr_l2(got, ref)
+        if not err < btol:
+            bad[name] = err
+    assert not bad, bad
+
+
+def test_graph_variant_trains(cuda_lib):
+    """Two optimizer steps of the smallest variant (no short_term_intention GRU, no causal2 GRU): losses follow the oracle."""
+    import torch
+    from oracle import clsr_oracle as O
+    variant = dict(interest_evolve=False, predict_long_short=False)
+    G, S = 5, 20
+    feed, prm = PU.small_problem(S=S, G=G, seed=13, variant=variant)
+    feeds = [feed, PU.small_problem(S=S, G=G, seed=14, variant=variant)[0]]
+    eng = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, G=G, **variant)
+    cfg = PU.oracle_config(G, **variant)
+    ref, slots = {k: v.copy() for k, v in prm.items()}, {}
+    for i, f in enumerate(feeds):
+        got = eng.train_step(f, group=G)
+        want, _ = O.train_step(ref, slots, f, cfg, i + 1, torch.float64)
+        for k in want:
+            assert abs(got[k] - want[k]) <= 2e-4 * max(abs(want[k]), 1e-3), (i, k, got[k], want[k])
+
+
+def test_contrastive_loss_without_long_sequences_is_nan_like_the_reference(cuda_lib):
+    """No sequence longer than contrastive_length_threshold: the reference divides the four triplet sums by
+    tf.reduce_sum(mask) = 0 (clsr.py:58-71) and trains on NaN; the engine reproduces that instead of hiding it."""
+    import torch
+    from oracle import clsr_oracle as O
+    from clsr_b200.engine import STEP_NO_OPTIMIZER, STEP_NO_BN_UPDATE
+    G, S = 5, 8
+    feed, prm = PU.small_problem(S=S, G=G, seed=4)
+    feed = PU.set_lengths(feed, [1, 2, 3, 4, 5, 5, 2, 1], G)
+    eng = PU.make_engine(prm, NI, NC, NU, max_rows=S * G, G=G)
+    got = eng.train_step(feed, group=G, flags=STEP_NO_OPTIMIZER | STEP_NO_BN_UPDATE)
+    out = O.forward({k: torch.as_tensor(v, dtype=torch.float64) for k, v in prm.items()}, feed, PU.oracle_config(G), True)
+    want = O.losses(out, {k: torch.as_tensor(v, dtype=torch.float64) for k, v in prm.items()}, feed, PU.oracle_config(G))
+    assert np.isnan(float(want["contrastive_loss"])) and np.isnan(got["contrastive_loss"]) and np.isnan(got["loss"])
+    assert abs(got["data_loss"] - float(want["data_loss"])) <= 1e-4 * abs(float(want["data_loss"]))
