@@ -835,75 +835,100 @@ int gemm(clsr_engine* e, const char* name, int M, int N, int K, const AOp& a, co
 }
 
 // dW on tensor cores; N is cut into column slabs of at most 240.
+// One weight-gradient problem: `la` (Kl columns) on the MMA's lanes, `cb` (Nc columns, + a constant-one column when
+// ones_b) on its N side.  transposed = 0: dW[Kl, Nc] (+ colsum row from a ones column on the lane side);
+// transposed = 1: the operands were exchanged by the caller and the accumulator is dW^T (tc_gemm.cuh, dw_body).
+int tc_dw_emit(clsr_engine* e, const char* name, int M, int Kl, int acols, int Nc, int transposed, const AOp& la, const AOp& cb,
+               float* dW, int lddw, float* colsum) {
+  const int ncols = Nc + ((transposed && colsum) ? 1 : 0);   // columns of the N-side stage (with the ones column)
+  const int npad = round16(ncols);
+  int nstages = 2;
+  int ta = tma_streams(la, Kl), tb = tma_streams(cb, Nc);
+  // first configuration that fits: two stages beat TMA with one stage (measured on dWs0t: 0.25 vs 0.28 ms)
+  const int cand[][3] = {{2, ta, tb}, {2, ta == 2 ? 0 : ta, tb}, {2, ta == 2 ? 0 : ta, tb == 2 ? 0 : tb}, {1, ta, tb}, {2, 0, 0}, {1, 0, 0}};
+  tc::DwSmem L;
+  bool fits = false;
+  for (int ci = 0; ci < 6; ++ci) {
+    const int* c = cand[ci];
+    L = tc::dw_smem_layout(Kl, acols, Nc, npad, c[0], c[1], c[2]);
+    if (L.total <= e->tc_dw_smem_max) { nstages = c[0]; ta = c[1]; tb = c[2]; fits = true; break; }
+  }
+  if (!fits) return fail(e, CLSR_ERR_ARG, "tc_dwgemm %s: %d x %d does not fit", name, Kl, Nc);
+  CUtensorMap tmA, tmA2, tmB, tmB2;
+  memset(&tmA, 0, sizeof tmA); memset(&tmA2, 0, sizeof tmA2); memset(&tmB, 0, sizeof tmB); memset(&tmB2, 0, sizeof tmB2);
+  bool okm = true;
+  if (ta >= 1) okm = okm && make_tmap(&tmA, la.A, tmap_cols(la, Kl), M, la.lda);
+  if (ta == 2) okm = okm && make_tmap(&tmA2, la.A2, Kl, M, la.lda2);
+  if (tb >= 1) okm = okm && make_tmap(&tmB, cb.A, tmap_cols(cb, Nc), M, cb.lda);
+  if (tb == 2) okm = okm && make_tmap(&tmB2, cb.A2, Nc, M, cb.lda2);
+  if (!okm) { ta = tb = 0; L = tc::dw_smem_layout(Kl, acols, Nc, npad, nstages, 0, 0); }
+  uint32_t cols = 32;
+  while ((int)cols < npad) cols <<= 1;
+  const int tiles = cdiv(M, tc::kTileM);
+  const int grid = tiles < e->num_sms ? tiles : e->num_sms;
+  const int planes_a = (acols + 7) / 8, planes_b = (ncols + 7) / 8;
+  const int octa = tc::dw_split(tc::kDwProducers / 8, planes_a, planes_b, tc::piece_cost(la.mode), tc::piece_cost(cb.mode));
+  if (e->dw_grouping && e->dwg.n < tc::kDwGroupMax) {
+    // deferred: becomes one problem of the next grouped launch (dw_group_flush)
+    tc::DwProblem& P = e->dwg.p[e->dwg.n];
+    P.M = M; P.K = Kl; P.acols = acols; P.N = Nc; P.npad = npad; P.nstages = nstages; P.tma_a = ta; P.tma_b = tb; P.lddw = lddw;
+    P.octa = octa; P.transposed = transposed;
+    P.tmem_cols = cols; P.a = la; P.b = cb; P.dW = dW; P.colsum = colsum;
+    P.tmA = tmA; P.tmA2 = tmA2; P.tmB = tmB; P.tmB2 = tmB2;
+    e->dwg_weight[e->dwg.n] = (long long)tiles * (planes_a + planes_b);
+    e->dwg_tiles[e->dwg.n] = tiles;
+    if (L.total > e->dwg_smem) e->dwg_smem = L.total;
+    e->dwg.n++;
+    return 0;
+  }
+  tc::tc_dw_kernel<<<grid, tc::kDwThreads, L.total, e->stream>>>(M, Kl, acols, Nc, npad, nstages, cols, ta, tb, octa, transposed, la, cb,
+                                                               dW, lddw, colsum, tmA, tmA2, tmB, tmB2);
+  POST(name);
+  return 0;
+}
+
 int tc_dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& a, const AOp& b, float* dW,
               int lddw, float* colsum) {
+  int rc;
+  // Wide gradients (N >= 2 K): put B on the lanes in chunks of <= 128 columns and A (+ the ones column) on the N side.
+  // The MMA's N drops from up to 240 to round16(K + 1), no lane is wasted and every chunk double-buffers.
+  static const bool no_tr = getenv("CLSR_DW_NO_TRANSPOSE") != nullptr;
+  const int kones = K + (colsum ? 1 : 0);
+  // (single chunk only: with several chunks A is re-read and re-converted per chunk -- dWx as 4 x 120 lanes measured 13 % slower
+  //  than as 3 slabs of 160 columns; dWs0t, 80 lanes: 0.215 -> 0.167 ms)
+  if (!no_tr && N >= 2 * K && kones <= 64 && N <= 128) {
+    const int nch = cdiv(N, 128);
+    const int per = ((cdiv(N, nch) + 7) / 8) * 8;
+    for (int n0 = 0; n0 < N; n0 += per) {
+      const int nn = N - n0 < per ? N - n0 : per;
+      AOp b2 = b;
+      if (n0) b2.A = b.A + n0;
+      if ((rc = tc_dw_emit(e, name, M, nn, nn, K, 1, b2, a, dW + n0, lddw, colsum ? colsum + n0 : nullptr))) return rc;
+    }
+    return 0;
+  }
   // columns of A that are stored (the MMA's remaining lanes alias what follows; CLSR_DW_FULL_A=1 stores all 128: A/B switch)
   static const bool full_a = getenv("CLSR_DW_FULL_A") != nullptr;
-  const int acols = full_a ? 128 : (colsum ? K + 1 : K);
+  const int acols = full_a ? 128 : kones;
   // Column slabs of B: as few as possible (<= 240 columns: one TMEM accumulator), but when B is a plain matrix take
   // more of them if that is what lets TWO stages with TMA loads fit shared memory -- a single-staged slab loop
-  // serialises load, conversion and MMA (dWx, 480 columns: 3 slabs of 160 instead of 2 of 240).
+  // serialises load, conversion and MMA.
   int nslab = cdiv(N, 240);
   if (b.mode == A_PLAIN) {
     for (int ns = nslab; ns <= nslab + 2; ++ns) {
       const int p8 = ((cdiv(N, ns) + 7) / 8) * 8;
-      AOp bs = b;
-      const int tb0 = tma_streams(bs, p8);
-      if (tc::dw_smem_layout(K, acols, p8, round16(p8), 2, tma_streams(a, K), tb0).total <= e->tc_dw_smem_max) { nslab = ns; break; }
+      if (tc::dw_smem_layout(K, acols, p8, round16(p8), 2, tma_streams(a, K), tma_streams(b, p8)).total <= e->tc_dw_smem_max) { nslab = ns; break; }
     }
   }
   const int per = ((cdiv(N, nslab) + 7) / 8) * 8;
   for (int n0 = 0; n0 < N; n0 += per) {
-    int nn = N - n0 < per ? N - n0 : per;
-    int npad = round16(nn);
+    const int nn = N - n0 < per ? N - n0 : per;
     AOp b2 = b;
     if (n0) {
       if (b.mode != A_PLAIN) return fail(e, CLSR_ERR_ARG, "tc_dwgemm %s: column slabs need a plain B operand", name);
       b2.A = b.A + n0;
     }
-    int nstages = 2;
-    int ta = tma_streams(a, K), tb = tma_streams(b2, nn);
-    // first configuration that fits: two stages beat TMA with one stage (measured on dWs0t: 0.25 vs 0.28 ms)
-    const int cand[][3] = {{2, ta, tb}, {2, ta == 2 ? 0 : ta, tb}, {2, ta == 2 ? 0 : ta, tb == 2 ? 0 : tb}, {1, ta, tb}, {2, 0, 0}, {1, 0, 0}};
-    tc::DwSmem L;
-    bool fits = false;
-    for (int ci = 0; ci < 6; ++ci) {
-      const int* c = cand[ci];
-      L = tc::dw_smem_layout(K, acols, nn, npad, c[0], c[1], c[2]);
-      if (L.total <= e->tc_dw_smem_max) { nstages = c[0]; ta = c[1]; tb = c[2]; fits = true; break; }
-    }
-    if (!fits) return fail(e, CLSR_ERR_ARG, "tc_dwgemm %s: N slab %d does not fit", name, nn);
-    CUtensorMap tmA, tmA2, tmB, tmB2;
-    memset(&tmA, 0, sizeof tmA); memset(&tmA2, 0, sizeof tmA2); memset(&tmB, 0, sizeof tmB); memset(&tmB2, 0, sizeof tmB2);
-    bool okm = true;
-    if (ta >= 1) okm = okm && make_tmap(&tmA, a.A, tmap_cols(a, K), M, a.lda);
-    if (ta == 2) okm = okm && make_tmap(&tmA2, a.A2, K, M, a.lda2);
-    if (tb >= 1) okm = okm && make_tmap(&tmB, b2.A, tmap_cols(b2, nn), M, b2.lda);
-    if (tb == 2) okm = okm && make_tmap(&tmB2, b2.A2, nn, M, b2.lda2);
-    if (!okm) { ta = tb = 0; L = tc::dw_smem_layout(K, acols, nn, npad, nstages, 0, 0); }
-    uint32_t cols = 32;
-    while ((int)cols < npad) cols <<= 1;
-    int tiles = cdiv(M, tc::kTileM);
-    int grid = tiles < e->num_sms ? tiles : e->num_sms;
-    if (e->dw_grouping && e->dwg.n < tc::kDwGroupMax) {
-      // deferred: becomes one problem of the next grouped launch (dw_group_flush)
-      tc::DwProblem& P = e->dwg.p[e->dwg.n];
-      P.M = M; P.K = K; P.acols = acols; P.N = nn; P.npad = npad; P.nstages = nstages; P.tma_a = ta; P.tma_b = tb; P.lddw = lddw;
-      P.octa = tc::dw_split(tc::kDwProducers / 8, ((colsum ? K + 1 : K) + 7) / 8, (nn + 7) / 8, tc::piece_cost(a.mode),
-                            tc::piece_cost(b2.mode));
-      P.tmem_cols = cols; P.a = a; P.b = b2; P.dW = dW + n0; P.colsum = colsum ? colsum + n0 : nullptr;
-      P.tmA = tmA; P.tmA2 = tmA2; P.tmB = tmB; P.tmB2 = tmB2;
-      e->dwg_weight[e->dwg.n] = (long long)tiles * (((colsum ? K + 1 : K) + 7) / 8 + (nn + 7) / 8);
-      e->dwg_tiles[e->dwg.n] = tiles;
-      if (L.total > e->dwg_smem) e->dwg_smem = L.total;
-      e->dwg.n++;
-      continue;
-    }
-    const int octa = tc::dw_split(tc::kDwProducers / 8, ((colsum ? K + 1 : K) + 7) / 8, (nn + 7) / 8, tc::piece_cost(a.mode),
-                                  tc::piece_cost(b2.mode));
-    tc::tc_dw_kernel<<<grid, tc::kDwThreads, L.total, e->stream>>>(M, K, acols, nn, npad, nstages, cols, ta, tb, octa, a, b2, dW + n0, lddw,
-                                                                 colsum ? colsum + n0 : nullptr, tmA, tmA2, tmB, tmB2);
-    POST(name);
+    if ((rc = tc_dw_emit(e, name, M, K, acols, nn, 0, a, b2, dW + n0, lddw, colsum ? colsum + n0 : nullptr))) return rc;
   }
   return 0;
 }

@@ -1158,8 +1158,11 @@ constexpr int kDwThreads = 448;
 
 // Body of the weight-gradient kernel for one problem; `cta` of `nctas` CTAs share the problem's row slabs.
 // (The tensor maps are passed by address: they must stay in the kernel's parameter space.)
+// transposed: the caller has exchanged the operands (a = the wide one on the MMA's lanes, K = its width; b = the narrow one,
+// N = its width, + a constant-one column at index N when colsum is wanted): the accumulator then holds dW^T, lane = column
+// of dW.  Used when the original N >= 2 K: the MMA's N shrinks from up to 240 to <= 48 and no lane is wasted.
 CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, int acols, int N, int npad, int nstages,
-                         uint32_t tmem_cols, int tma_a, int tma_b, int octa, const AOp& a, const AOp& b,
+                         uint32_t tmem_cols, int tma_a, int tma_b, int octa, int transposed, const AOp& a, const AOp& b,
                          float* __restrict__ dW, int lddw, float* __restrict__ colsum, const CUtensorMap* tmA,
                          const CUtensorMap* tmA2, const CUtensorMap* tmB, const CUtensorMap* tmB2, int cta, int nctas) {
   const DwSmem L = dw_smem_layout(K, acols, N, npad, nstages, tma_a, tma_b);
@@ -1216,8 +1219,11 @@ CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, in
       const int m0 = tile * kTileM;
       // the producer octets are split between the two operands in proportion to their plane counts, so
       // the loads of A and B are in flight together (one exposed load latency per slab, not two)
-      if (tid < octa * 8) produce_tile(a, fa, tma_a, sva, 128, m0, M, K, colsum ? K : -1, tid, octa * 8, a_base, a_raw2);
-      else produce_tile(b, fb, tma_b, svb, 256, m0, M, N, -1, tid - octa * 8, kDwProducers - octa * 8, b_base, b_raw2);
+      if (tid < octa * 8)
+        produce_tile(a, fa, tma_a, sva, 128, m0, M, K, (colsum && !transposed) ? K : -1, tid, octa * 8, a_base, a_raw2);
+      else
+        produce_tile(b, fb, tma_b, svb, 256, m0, M, N, (colsum && transposed) ? N : -1, tid - octa * 8,
+                     kDwProducers - octa * 8, b_base, b_raw2);
       fence_proxy_async();
       mbar_arrive(&full[s]);
     }
@@ -1274,7 +1280,17 @@ CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, in
     for (int c0 = 0; c0 < npad; c0 += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      if (krow < K) {
+      if (transposed) {
+        // lane = column krow of dW, accumulator column c = row c of dW; column N = the ones column: column sums
+        if (krow < K) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + i;
+            if (c < N) atomicAdd(&dW[(size_t)c * lddw + krow], v[i]);
+            else if (colsum && c == N) atomicAdd(&colsum[krow], v[i]);
+          }
+        }
+      } else if (krow < K) {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (c0 + i < N) atomicAdd(&dW[(size_t)krow * lddw + c0 + i], v[i]);
@@ -1294,14 +1310,15 @@ CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, in
 }
 
 __global__ void __launch_bounds__(kDwThreads, 1)
-tc_dw_kernel(int M, int K, int acols, int N, int npad, int nstages, uint32_t tmem_cols, int tma_a, int tma_b, int octa, AOp a, AOp b,
+tc_dw_kernel(int M, int K, int acols, int N, int npad, int nstages, uint32_t tmem_cols, int tma_a, int tma_b, int octa, int transposed,
+             AOp a, AOp b,
              float* __restrict__ dW, int lddw, float* __restrict__ colsum, const __grid_constant__ CUtensorMap tmA,
              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmB2) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(16) float sva[3 * 128];
   __shared__ __align__(16) float svb[3 * 256];
-  dw_body(smem, sva, svb, M, K, acols, N, npad, nstages, tmem_cols, tma_a, tma_b, octa, a, b, dW, lddw, colsum, &tmA, &tmA2, &tmB,
+  dw_body(smem, sva, svb, M, K, acols, N, npad, nstages, tmem_cols, tma_a, tma_b, octa, transposed, a, b, dW, lddw, colsum, &tmA, &tmA2, &tmB,
           &tmB2, (int)blockIdx.x, (int)gridDim.x);
 }
 
@@ -1310,7 +1327,7 @@ tc_dw_kernel(int M, int K, int acols, int N, int npad, int nstages, uint32_t tme
 // partitioned between the problems in proportion to their work and every CTA runs dw_body on its share.
 constexpr int kDwGroupMax = 12;
 struct DwProblem {
-  int M, K, acols, N, npad, nstages, tma_a, tma_b, octa, lddw, cta0, ncta;
+  int M, K, acols, N, npad, nstages, tma_a, tma_b, octa, transposed, lddw, cta0, ncta;
   uint32_t tmem_cols;
   AOp a, b;
   float* dW;
@@ -1330,7 +1347,8 @@ tc_dw_group_kernel(const __grid_constant__ DwGroup g) {
   int i = 0;
   while (i + 1 < g.n && (int)blockIdx.x >= g.p[i].cta0 + g.p[i].ncta) ++i;
   const DwProblem& P = g.p[i];
-  dw_body(smem, sva, svb, P.M, P.K, P.acols, P.N, P.npad, P.nstages, P.tmem_cols, P.tma_a, P.tma_b, P.octa, P.a, P.b, P.dW, P.lddw,
+  dw_body(smem, sva, svb, P.M, P.K, P.acols, P.N, P.npad, P.nstages, P.tmem_cols, P.tma_a, P.tma_b, P.octa, P.transposed, P.a, P.b,
+          P.dW, P.lddw,
           P.colsum, &P.tmA, &P.tmA2, &P.tmB, &P.tmB2, (int)blockIdx.x - P.cta0, P.ncta);
 }
 
