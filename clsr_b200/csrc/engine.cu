@@ -845,10 +845,13 @@ int tc_dw_emit(clsr_engine* e, const char* name, int M, int Kl, int acols, int N
   int nstages = 2;
   int ta = tma_streams(la, Kl), tb = tma_streams(cb, Nc);
   // first configuration that fits: two stages beat TMA with one stage (measured on dWs0t: 0.25 vs 0.28 ms)
-  const int cand[][3] = {{2, ta, tb}, {2, ta == 2 ? 0 : ta, tb}, {2, ta == 2 ? 0 : ta, tb == 2 ? 0 : tb}, {1, ta, tb}, {2, 0, 0}, {1, 0, 0}};
+  // (three stages when they fit with full TMA: more loads in flight per SM; CLSR_DW_STAGES=2 caps it)
+  static const int max_st = getenv("CLSR_DW_STAGES") ? atoi(getenv("CLSR_DW_STAGES")) : 3;
+  const int cand[][3] = {{max_st >= 3 ? 3 : 2, ta, tb}, {2, ta, tb}, {2, ta == 2 ? 0 : ta, tb}, {2, ta == 2 ? 0 : ta, tb == 2 ? 0 : tb},
+                         {1, ta, tb}, {2, 0, 0}, {1, 0, 0}};
   tc::DwSmem L;
   bool fits = false;
-  for (int ci = 0; ci < 6; ++ci) {
+  for (int ci = 0; ci < 7; ++ci) {
     const int* c = cand[ci];
     L = tc::dw_smem_layout(Kl, acols, Nc, npad, c[0], c[1], c[2]);
     if (L.total <= e->tc_dw_smem_max) { nstages = c[0]; ta = c[1]; tb = c[2]; fits = true; break; }
@@ -915,9 +918,10 @@ int tc_dwgemm(clsr_engine* e, const char* name, int M, int K, int N, const AOp& 
   // serialises load, conversion and MMA.
   int nslab = cdiv(N, 240);
   if (b.mode == A_PLAIN) {
-    for (int ns = nslab; ns <= nslab + 2; ++ns) {
+    static const int slab_st = getenv("CLSR_DW_SLAB_STAGES") ? atoi(getenv("CLSR_DW_SLAB_STAGES")) : 2;
+    for (int ns = nslab; ns <= nslab + 3; ++ns) {
       const int p8 = ((cdiv(N, ns) + 7) / 8) * 8;
-      if (tc::dw_smem_layout(K, acols, p8, round16(p8), 2, tma_streams(a, K), tma_streams(b, p8)).total <= e->tc_dw_smem_max) { nslab = ns; break; }
+      if (tc::dw_smem_layout(K, acols, p8, round16(p8), slab_st, tma_streams(a, K), tma_streams(b, p8)).total <= e->tc_dw_smem_max) { nslab = ns; break; }
     }
   }
   const int per = ((cdiv(N, nslab) + 7) / 8) * 8;

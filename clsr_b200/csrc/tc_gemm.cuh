@@ -1168,10 +1168,10 @@ CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, in
   const DwSmem L = dw_smem_layout(K, acols, N, npad, nstages, tma_a, tma_b);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full = bars;         // [2]
-  uint64_t* empty = bars + 2;    // [2]
-  uint64_t* done = bars + 4;     // [1]
-  uint64_t* rawfull = bars + 5;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* empty = bars + 4;    // [4]   (full: bars + 0, [4]; up to four operand stages)
+  uint64_t* done = bars + 8;     // [1]
+  uint64_t* rawfull = bars + 9;  // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (M + kTileM - 1) / kTileM;
   const Fast fa = fast_eligible(a), fb = fast_eligible(b);
@@ -1183,7 +1183,7 @@ CLSR_DEVINL void dw_body(uint8_t* smem, float* sva, float* svb, int M, int K, in
   stage_vectors(a, sva, 128, K, tid, kDwThreads);
   stage_vectors(b, svb, 256, N, tid, kDwThreads);
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], kDwProducers); mbar_init(&empty[i], 1); mbar_init(&rawfull[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&full[i], kDwProducers); mbar_init(&empty[i], 1); mbar_init(&rawfull[i], 1); }
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
