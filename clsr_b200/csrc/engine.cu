@@ -724,7 +724,9 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
   int tstore = (!no_tstore && encode_tiled() && (N & 7) == 0 && (ep.ldc & 3) == 0 && al16p(ep.C) && M >= tc::kTileM) ? 1 : 0;
   // first configuration that fits shared memory: prefer two stages + operand prefetch + TMA
   // (two operand stages matter more than the prefetched epilogue operand, which matters more than the store image)
-  const int cand[][4] = {{2, eop, tma, tstore}, {2, eop, tma, 0}, {2, eop, tma == 2 ? 0 : tma, 0}, {2, 0, tma, 0}, {1, eop, tma, 0},
+  // (three operand stages when everything else still fits: more loads in flight per SM; CLSR_TC_STAGES=2 caps it)
+  static const int max_st = getenv("CLSR_TC_STAGES") ? atoi(getenv("CLSR_TC_STAGES")) : 3;
+  const int cand[][4] = {{max_st >= 3 ? 3 : 2, eop, tma, tstore}, {2, eop, tma, tstore}, {2, eop, tma, 0}, {2, eop, tma == 2 ? 0 : tma, 0}, {2, 0, tma, 0}, {1, eop, tma, 0},
                          {2, 0, 0, 0},          {1, eop, 0, 0},   {1, 0, 0, 0}};
   tc::Smem L;
   bool fits = false;
@@ -732,7 +734,7 @@ int tc_gemm_one(clsr_engine* e, const char* name, int M, int N, int K, const AOp
     L = tc::smem_layout(kpad, npad, N, c[0], c[1], st, c[2], c[3], kchunks);
     if (L.total <= e->tc_smem_max) { nstages = c[0]; eop = c[1]; tma = c[2]; tstore = c[3]; fits = true; break; }
   }
-  if (probe) return (fits && nstages == 2) ? 0 : 1;
+  if (probe) return (fits && nstages >= 2) ? 0 : 1;
   if (!fits) return fail(e, CLSR_ERR_ARG, "tc_gemm %s: K=%d N=%d does not fit shared memory", name, K, N);
   CUtensorMap tmA, tmA2, tmC;
   memset(&tmA2, 0, sizeof tmA2);

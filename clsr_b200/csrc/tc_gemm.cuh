@@ -649,7 +649,7 @@ __host__ __device__ inline Smem smem_layout(int kpad, int npad, int N, int nstag
   s.dstat = s.vec + (3 * kpad + 5 * npad) * 4;   // prologue vectors + bias / scale / shift / mean / rstd
   s.dstat = (s.dstat + 15) & ~15;
   s.bars = s.dstat + (stats ? 4 * 2 * npad * 8 : 0);
-  s.total = s.bars + 128;
+  s.total = s.bars + 192;
   return s;
 }
 
@@ -682,13 +682,13 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
   float* srstd = smr + npad;
   double* dstat = reinterpret_cast<double*>(smem + L.dstat);  // [4 quadrants][2][npad]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint64_t* full = bars;          // [2]
-  uint64_t* empty = bars + 2;     // [2]
-  uint64_t* tfull = bars + 4;     // [2]
-  uint64_t* tempty = bars + 6;    // [2]
-  uint64_t* efull = bars + 8;     // [2] epilogue-operand tile landed
-  uint64_t* rawfull = bars + 10;  // [2] raw operand planes landed (TMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* full = bars;          // [4] operand stages (up to four)
+  uint64_t* empty = bars + 4;     // [4]
+  uint64_t* rawfull = bars + 8;   // [4] raw operand planes landed (TMA)
+  uint64_t* tfull = bars + 12;    // [2] accumulators
+  uint64_t* tempty = bars + 14;   // [2]
+  uint64_t* efull = bars + 16;    // [2] epilogue-operand tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (M + kTileM - 1) / kTileM;
@@ -725,13 +725,15 @@ tc_gemm_kernel(int M, int N, int K, int kpad, int npad, int nstages, uint32_t tm
     for (int i = tid; i < 4 * 2 * npad; i += kThreads) dstat[i] = 0.0;
   }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&full[i], kProducers);
       mbar_init(&empty[i], 1);
+      mbar_init(&rawfull[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpilogue / 32);
       mbar_init(&efull[i], 1);
-      mbar_init(&rawfull[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
