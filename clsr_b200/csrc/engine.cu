@@ -112,6 +112,7 @@ struct clsr_engine {
   bool has_gru2 = true;    // causal2 GRU (predict_long_short and not manual_alpha)
   bool has_alpha = true;   // fcn_alpha MLP (not manual_alpha)
   int Hf = 0;              // width of the causal2 final state at the front of concat_all (H or 0)
+  bool plain_lstm = false; // sequential_model = 'lstm': the Time4LSTM kernels with both time gates pinned at 1 and no o-gate time terms
   int oG1, oC1, oG2, oC2, oL, oO, oTN, oTL;
   int Bmax, Smax;
 
@@ -428,23 +429,29 @@ void build_inventory(clsr_engine* e) {
     add_dense(e, gs[i] + "candidate/kernel", D + gu[i], gu[i], 1);
     add_dense(e, gs[i] + "candidate/bias", 1, gu[i], 1);
   }
-  std::string tl = st + "time4lstm/time4lstm_cell/";
+  std::string tl = st + (e->plain_lstm ? "simple_lstm/lstm_cell/" : "time4lstm/time4lstm_cell/");
   add_dense(e, tl + "kernel", D + H, 4 * H, 1);
   add_dense(e, tl + "bias", 1, 4 * H, 1);
-  const char* v1[] = {"_time_input_w1", "_time_input_bias1", "_time_input_w2", "_time_input_bias2",
-                      "_time_bias1", "_time_bias2"};
-  for (const char* n : v1) add_dense(e, tl + n, 1, H, 1);
-  add_dense(e, tl + "_time_kernel_w1", D, H, 1);
-  add_dense(e, tl + "_time_kernel_w2", D, H, 1);
-  const char* v2[] = {"_time_kernel_t1", "_time_kernel_t2", "_o_kernel_t1", "_o_kernel_t2"};
-  for (const char* n : v2) add_dense(e, tl + n, H, H, 1);
+  if (!e->plain_lstm) {
+    const char* v1[] = {"_time_input_w1", "_time_input_bias1", "_time_input_w2", "_time_input_bias2",
+                        "_time_bias1", "_time_bias2"};
+    for (const char* n : v1) add_dense(e, tl + n, 1, H, 1);
+    add_dense(e, tl + "_time_kernel_w1", D, H, 1);
+    add_dense(e, tl + "_time_kernel_w2", D, H, 1);
+    const char* v2[] = {"_time_kernel_t1", "_time_kernel_t2", "_o_kernel_t1", "_o_kernel_t2"};
+    for (const char* n : v2) add_dense(e, tl + n, H, H, 1);
+  }
   if (e->has_alpha) add_fcn(e, sc + "fcn_alpha/nn_part/", e->CA, e->A0, e->A1, &e->mlp_alpha);
   else { memset(&e->mlp_alpha, 0, sizeof e->mlp_alpha); }
   add_fcn(e, "sequential/logit_fcn/nn_part/", H + D, e->L0, e->L1, &e->mlp_logit);
   e->p_wattl = poff(e, lt + "attention_mat");
   e->p_watts = poff(e, st + "attention_fcn/attention_mat");
-  e->p_tw1 = poff(e, tl + "_time_input_w1"); e->p_tb1 = poff(e, tl + "_time_input_bias1");
-  e->p_tw2 = poff(e, tl + "_time_input_w2"); e->p_tb2 = poff(e, tl + "_time_input_bias2");
+  if (!e->plain_lstm) {
+    e->p_tw1 = poff(e, tl + "_time_input_w1"); e->p_tb1 = poff(e, tl + "_time_input_bias1");
+    e->p_tw2 = poff(e, tl + "_time_input_w2"); e->p_tb2 = poff(e, tl + "_time_input_bias2");
+  } else {
+    e->p_tw1 = e->p_tb1 = e->p_tw2 = e->p_tb2 = 0;
+  }
 }
 
 long long wd_add(clsr_engine* e, const char* name, long long n) {
@@ -467,7 +474,8 @@ int build_weight_maps(clsr_engine* e) {
   const int D = e->D, U = e->U, H = e->H, Q = e->Q, A0 = e->A0, A1 = e->A1, NX = e->NX, CA = e->CA;
   const int L0 = e->L0, L1 = e->L1;
   std::vector<BlockOp> prep, unprep;
-  std::string sc = kSC, st = sc + "short_term/", tl = st + "time4lstm/time4lstm_cell/";
+  std::string sc = kSC, st = sc + "short_term/";
+  std::string tl = st + (e->plain_lstm ? "simple_lstm/lstm_cell/" : "time4lstm/time4lstm_cell/");
   auto W = [&](const char* n) { return e->wd_off.at(n); };
 
   // ---- long attention: W0 rows [a | b | c | d], each U rows: feat = [a, q, a-q, a*q] ----
@@ -552,48 +560,50 @@ int build_weight_maps(clsr_engine* e) {
     }
     long long lk = poff(e, tl + "kernel"), lb = poff(e, tl + "bias");
     long long km = wd_add(e, "Km", (long long)H * 4 * H), kmT = wd_add(e, "KmT", (long long)H * 4 * H);
-    long long k1 = poff(e, tl + "_time_kernel_w1"), k2 = poff(e, tl + "_time_kernel_w2");
-    long long tb1 = poff(e, tl + "_time_bias1"), tb2 = poff(e, tl + "_time_bias2");
-    long long t1 = poff(e, tl + "_time_kernel_t1"), t2 = poff(e, tl + "_time_kernel_t2");
-    long long o1 = poff(e, tl + "_o_kernel_t1"), o2 = poff(e, tl + "_o_kernel_t2");
     prep.push_back(mk(wx + e->oL, NX, lk, 4 * H, D, 4 * H));
-    prep.push_back(mk(wx + e->oTN, NX, k1, H, D, H));
-    prep.push_back(mk(wx + e->oTL, NX, k2, H, D, H));
     prep.push_back(mk(wxT + (long long)e->oL * D, D, lk, 4 * H, D, 4 * H, 1.f, -1, 0, 0.f, 1));
-    prep.push_back(mk(wxT + (long long)e->oTN * D, D, k1, H, D, H, 1.f, -1, 0, 0.f, 1));
-    prep.push_back(mk(wxT + (long long)e->oTL * D, D, k2, H, D, H, 1.f, -1, 0, 0.f, 1));
     prep.push_back(mk(bx + e->oL, NX, lb, 4 * H, 1, 4 * H));
-    prep.push_back(mk(bx + e->oTN, NX, tb1, H, 1, H));
-    prep.push_back(mk(bx + e->oTL, NX, tb2, H, 1, H));
     prep.push_back(mk(km, 4 * H, lk + (long long)D * 4 * H, 4 * H, H, 4 * H));
     prep.push_back(mk(kmT, H, lk + (long long)D * 4 * H, 4 * H, H, 4 * H, 1.f, -1, 0, 0.f, 1));
-    // Wt [2H, 3H]: rows [tanh-now | tanh-last], cols [o | time-now gate | time-last gate]
-    prep.push_back(mk(wt, 3 * H, o1, H, H, H));
-    prep.push_back(mk(wt + (long long)H * 3 * H, 3 * H, o2, H, H, H));
-    prep.push_back(mk(wt + H, 3 * H, t1, H, H, H));
-    prep.push_back(mk(wt + (long long)H * 3 * H + 2 * H, 3 * H, t2, H, H, H));
-    {
-      const long long wxe = wx + (long long)D * NX + e->oO;   // same four blocks, row pitch NX
-      prep.push_back(mk(wxe, NX, o1, H, H, H));
-      prep.push_back(mk(wxe + (long long)H * NX, NX, o2, H, H, H));
-      prep.push_back(mk(wxe + H, NX, t1, H, H, H));
-      prep.push_back(mk(wxe + (long long)H * NX + 2 * H, NX, t2, H, H, H));
-    }
-    prep.push_back(mk(wtT, 2 * H, o1, H, H, H, 1.f, -1, 0, 0.f, 1));
-    prep.push_back(mk(wtT + H, 2 * H, o2, H, H, H, 1.f, -1, 0, 0.f, 1));
-    prep.push_back(mk(wtT + (long long)H * 2 * H, 2 * H, t1, H, H, H, 1.f, -1, 0, 0.f, 1));
-    prep.push_back(mk(wtT + 2LL * H * 2 * H + H, 2 * H, t2, H, H, H, 1.f, -1, 0, 0.f, 1));
     unprep.push_back(mk(lk, 4 * H, wx + e->oL, NX, D, 4 * H));
     unprep.push_back(mk(lk + (long long)D * 4 * H, 4 * H, km, 4 * H, H, 4 * H));
     unprep.push_back(mk(lb, 4 * H, bx + e->oL, NX, 1, 4 * H));
-    unprep.push_back(mk(k1, H, wx + e->oTN, NX, D, H));
-    unprep.push_back(mk(k2, H, wx + e->oTL, NX, D, H));
-    unprep.push_back(mk(tb1, H, bx + e->oTN, NX, 1, H));
-    unprep.push_back(mk(tb2, H, bx + e->oTL, NX, 1, H));
-    unprep.push_back(mk(o1, H, wt, 3 * H, H, H));
-    unprep.push_back(mk(o2, H, wt + (long long)H * 3 * H, 3 * H, H, H));
-    unprep.push_back(mk(t1, H, wt + H, 3 * H, H, H));
-    unprep.push_back(mk(t2, H, wt + (long long)H * 3 * H + 2 * H, 3 * H, H, H));
+    if (!e->plain_lstm) {
+      long long k1 = poff(e, tl + "_time_kernel_w1"), k2 = poff(e, tl + "_time_kernel_w2");
+      long long tb1 = poff(e, tl + "_time_bias1"), tb2 = poff(e, tl + "_time_bias2");
+      long long t1 = poff(e, tl + "_time_kernel_t1"), t2 = poff(e, tl + "_time_kernel_t2");
+      long long o1 = poff(e, tl + "_o_kernel_t1"), o2 = poff(e, tl + "_o_kernel_t2");
+      prep.push_back(mk(wx + e->oTN, NX, k1, H, D, H));
+      prep.push_back(mk(wx + e->oTL, NX, k2, H, D, H));
+      prep.push_back(mk(wxT + (long long)e->oTN * D, D, k1, H, D, H, 1.f, -1, 0, 0.f, 1));
+      prep.push_back(mk(wxT + (long long)e->oTL * D, D, k2, H, D, H, 1.f, -1, 0, 0.f, 1));
+      prep.push_back(mk(bx + e->oTN, NX, tb1, H, 1, H));
+      prep.push_back(mk(bx + e->oTL, NX, tb2, H, 1, H));
+      // Wt [2H, 3H]: rows [tanh-now | tanh-last], cols [o | time-now gate | time-last gate]
+      prep.push_back(mk(wt, 3 * H, o1, H, H, H));
+      prep.push_back(mk(wt + (long long)H * 3 * H, 3 * H, o2, H, H, H));
+      prep.push_back(mk(wt + H, 3 * H, t1, H, H, H));
+      prep.push_back(mk(wt + (long long)H * 3 * H + 2 * H, 3 * H, t2, H, H, H));
+      {
+        const long long wxe = wx + (long long)D * NX + e->oO;   // same four blocks, row pitch NX
+        prep.push_back(mk(wxe, NX, o1, H, H, H));
+        prep.push_back(mk(wxe + (long long)H * NX, NX, o2, H, H, H));
+        prep.push_back(mk(wxe + H, NX, t1, H, H, H));
+        prep.push_back(mk(wxe + (long long)H * NX + 2 * H, NX, t2, H, H, H));
+      }
+      prep.push_back(mk(wtT, 2 * H, o1, H, H, H, 1.f, -1, 0, 0.f, 1));
+      prep.push_back(mk(wtT + H, 2 * H, o2, H, H, H, 1.f, -1, 0, 0.f, 1));
+      prep.push_back(mk(wtT + (long long)H * 2 * H, 2 * H, t1, H, H, H, 1.f, -1, 0, 0.f, 1));
+      prep.push_back(mk(wtT + 2LL * H * 2 * H + H, 2 * H, t2, H, H, H, 1.f, -1, 0, 0.f, 1));
+      unprep.push_back(mk(k1, H, wx + e->oTN, NX, D, H));
+      unprep.push_back(mk(k2, H, wx + e->oTL, NX, D, H));
+      unprep.push_back(mk(tb1, H, bx + e->oTN, NX, 1, H));
+      unprep.push_back(mk(tb2, H, bx + e->oTL, NX, 1, H));
+      unprep.push_back(mk(o1, H, wt, 3 * H, H, H));
+      unprep.push_back(mk(o2, H, wt + (long long)H * 3 * H, 3 * H, H, H));
+      unprep.push_back(mk(t1, H, wt + H, 3 * H, H, H));
+      unprep.push_back(mk(t2, H, wt + (long long)H * 3 * H + 2 * H, 3 * H, H, H));
+    }
   }
   // ---- alpha / logit MLPs: transposed copies for the data-gradient GEMMs ----
   {
@@ -611,6 +621,12 @@ int build_weight_maps(clsr_engine* e) {
   e->n_unprep = (int)unprep.size();
   int rc;
   if ((rc = dalloc(e, &e->Wd, e->Wtot))) return rc;
+  if (e->plain_lstm) {
+    // both time gates pinned at 1: their pre-activation columns of PX are a constant bias of 1e4 (sigmoid = 1 exactly in
+    // fp32, derivative exactly 0), their weights stay zero; no o-gate time terms
+    std::vector<float> big(2 * H, 1.0e4f);
+    CK(cudaMemcpy(e->Wd + e->wd_off.at("bx_all") + e->oTN, big.data(), big.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   if ((rc = dalloc(e, &e->Pg, e->Ptot + e->Wtot))) return rc;
   e->dWd = e->Pg + e->Ptot;   // Ptot is a multiple of 4 floats: dWd stays 16-byte aligned
   if ((rc = dalloc(e, &e->ops_prep, e->n_prep, false))) return rc;
@@ -1381,6 +1397,10 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
 
   // ---- hoisted input projections of the three recurrences ----
   float *TNL = e->B("TNL"), *PX = e->B("PX");
+  if (e->plain_lstm) {
+    // no time features: one product x . Wx (+ biases, incl. the constant gate columns)
+    if ((rc = gemm(e, "px", (int)M, NX, D, a_plain(X, D), W("Wx_all"), NX, e_store(PX, NX, W("bx_all")), false))) return rc;
+  } else {
   if ((H & 3) == 0)
     time_feat_v4_kernel<<<grid1d(e, M * 2 * H / 4, 256, 16), 256, 0, st>>>(c.ttn, c.tfa, c.seq_stride, T, e->P + e->p_tw1,
                                                                           e->P + e->p_tb1, e->P + e->p_tw2, e->P + e->p_tb2, H, TNL, M);
@@ -1400,6 +1420,7 @@ int forward(clsr_engine* e, const StepCtx& c, int train, int update_bn) {
     if ((rc = gemm(e, "px_time", (int)M, 3 * H, 2 * H, a_plain(TNL, 2 * H), W("Wt"), 3 * H,
                    e_store(PX + e->oO, NX, nullptr, E_ACCUM), false)))
       return rc;
+  }
   }
 
   // ---- recurrences: three independent kernels, one per stream ----
@@ -1714,6 +1735,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
   // the seven weight gradients fed by dPX are independent of everything up to the optimizer: one grouped launch
   dw_group_begin(e);
   if ((rc = dwgemm(e, "dWx", (int)M, D, NX, a_plain(X, D), a_plain(dPX, NX), dW("Wx_all"), NX, dW("bx_all")))) return rc;
+  if (!e->plain_lstm) {
   if ((rc = gemm(e, "dTNL", (int)M, 2 * H, 3 * H, a_plain(dPX + e->oO, NX), W("WtT"), 2 * H, e_store(dTNL, 2 * H), false)))
     return rc;
   if ((rc = dwgemm(e, "dWt", (int)M, 2 * H, 3 * H, a_plain(TNL, 2 * H), a_plain(dPX + e->oO, NX), dW("Wt"), 3 * H, nullptr)))
@@ -1732,6 +1754,7 @@ int backward(clsr_engine* e, const StepCtx& c) {
           e->Pg + e->p_tb2);
     }
     POST("time_feat_bwd");
+  }
   }
   if (e->has_gru1) {
     if ((rc = dwgemm(e, "dWgh1", (int)M, U, 2 * U, a_plain(e->B("hp1"), U), a_plain(dPX + e->oG1, NX), dW("Wgh1"), 2 * U, nullptr))) return rc;
@@ -2099,6 +2122,7 @@ int clsr_create(const clsr_config* cfg, clsr_engine** out) {
 
   e->T = cfg->seq_len; e->Di = cfg->item_dim; e->Dc = cfg->cate_dim; e->D = e->Di + e->Dc; e->U = cfg->user_dim;
   e->H = cfg->hidden; e->Q = e->U + e->D; e->A0 = cfg->att0; e->A1 = cfg->att1; e->L0 = cfg->fc0; e->L1 = cfg->fc1;
+  e->plain_lstm = cfg->sequential_model == 1;
   e->has_gru1 = !cfg->no_interest_evolve;
   e->has_alpha = !cfg->manual_alpha;
   e->has_gru2 = e->has_alpha && !cfg->no_predict_long_short;

@@ -33,7 +33,7 @@ class Config(C.Structure):
         ("max_grad_norm", C.c_float), ("bn_momentum", C.c_float), ("bn_eps", C.c_float),
         ("math_mode", C.c_int32), ("max_seqs", C.c_int32),
         ("no_interest_evolve", C.c_int32), ("no_predict_long_short", C.c_int32), ("manual_alpha", C.c_int32),
-        ("manual_alpha_value", C.c_float),
+        ("manual_alpha_value", C.c_float), ("sequential_model", C.c_int32),
     ]
 
 
@@ -215,7 +215,8 @@ class Engine:
                  contrastive_weight=0.1, discrepancy_weight=0.01, contrastive_len_threshold=5,
                  contrastive_recent_k=3, optimizer="adam", learning_rate=1e-3, clip_norm=True,
                  max_grad_norm=2.0, device=0, math_mode=0, training=True, alloc_tables=True, max_seqs=0,
-                 interest_evolve=True, predict_long_short=True, manual_alpha=False, manual_alpha_value=0.5):
+                 interest_evolve=True, predict_long_short=True, manual_alpha=False, manual_alpha_value=0.5,
+                 sequential_model="time4lstm"):
         import torch
         if not torch.cuda.is_available():
             raise EngineError("clsr_b200 needs a CUDA device (no CPU fallback)")
@@ -223,6 +224,8 @@ class Engine:
         self.lib = load_library()
         if optimizer not in ("adam", "lazyadam"):
             raise EngineError("optimizer %r is not implemented on the B200 path (adam, lazyadam)" % optimizer)
+        if sequential_model not in ("time4lstm", "lstm"):
+            raise EngineError("sequential_model %r is not implemented on the B200 path (time4lstm, lstm)" % sequential_model)
         if contrastive_loss not in ("triplet", "bpr"):
             raise EngineError("contrastive_loss %r is not defined (triplet, bpr)" % contrastive_loss)
         self.cfg = Config(
@@ -236,7 +239,8 @@ class Engine:
             adam_eps=1e-8, clip_norm=1 if clip_norm else 0, max_grad_norm=max_grad_norm, bn_momentum=0.95,
             bn_eps=1e-4, math_mode=math_mode, max_seqs=int(max_seqs or 0),
             no_interest_evolve=0 if interest_evolve else 1, no_predict_long_short=0 if predict_long_short else 1,
-            manual_alpha=1 if manual_alpha else 0, manual_alpha_value=float(manual_alpha_value))
+            manual_alpha=1 if manual_alpha else 0, manual_alpha_value=float(manual_alpha_value),
+            sequential_model=1 if sequential_model == "lstm" else 0)
         self.device = torch.device("cuda", device)
         self.h = C.c_void_p()
         rc = self.lib.clsr_create(C.byref(self.cfg), C.byref(self.h))

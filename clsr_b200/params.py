@@ -35,7 +35,8 @@ def _fcn(spec, scope, in_dim, sizes):
     spec.append((scope + "b_nn_output", (1,), "zeros", True))
 
 
-def dense_spec(D, U, H, att_sizes, layer_sizes, interest_evolve=True, predict_long_short=True, manual_alpha=False):
+def dense_spec(D, U, H, att_sizes, layer_sizes, interest_evolve=True, predict_long_short=True, manual_alpha=False,
+               sequential_model="time4lstm"):
     """Ordered [(name, shape, init, trainable)] for every non-table variable.  The three flags are the graph
     variants of _build_seq_graph (clsr.py:159-274): without interest_evolve the short_term_intention GRU does not
     exist, with manual_alpha neither the causal2 GRU nor the alpha MLP, without predict_long_short the causal2 GRU
@@ -58,16 +59,28 @@ def dense_spec(D, U, H, att_sizes, layer_sizes, interest_evolve=True, predict_lo
         s.append((scope + "gates/bias", (2 * units,), "ones", True))
         s.append((scope + "candidate/kernel", (D + units, units), "glorot", True))
         s.append((scope + "candidate/bias", (units,), "zeros", True))
-    tl = st + "time4lstm/time4lstm_cell/"
-    s.append((tl + "kernel", (D + H, 4 * H), "glorot", True))
-    s.append((tl + "bias", (4 * H,), "zeros", True))
-    for n in ("_time_input_w1", "_time_input_bias1", "_time_input_w2", "_time_input_bias2",
-              "_time_bias1", "_time_bias2"):
-        s.append((tl + n, (H,), "glorot", True))
-    for n in ("_time_kernel_w1", "_time_kernel_w2"):
-        s.append((tl + n, (D, H), "glorot", True))
-    for n in ("_time_kernel_t1", "_time_kernel_t2", "_o_kernel_t1", "_o_kernel_t2"):
-        s.append((tl + n, (H, H), "glorot", True))
+    if sequential_model == "lstm":      # tf.nn.rnn_cell.LSTMCell under scope simple_lstm (clsr.py:209-216)
+        tl = st + "simple_lstm/lstm_cell/"
+        s.append((tl + "kernel", (D + H, 4 * H), "glorot", True))
+        s.append((tl + "bias", (4 * H,), "zeros", True))
+    elif sequential_model == "gru":     # tf.nn.rnn_cell.GRUCell under scope simple_gru (clsr.py:201-208)
+        tl = st + "simple_gru/gru_cell/"
+        s.append((tl + "gates/kernel", (D + H, 2 * H), "glorot", True))
+        s.append((tl + "gates/bias", (2 * H,), "ones", True))
+        s.append((tl + "candidate/kernel", (D + H, H), "glorot", True))
+        s.append((tl + "candidate/bias", (H,), "zeros", True))
+    else:
+        assert sequential_model == "time4lstm", sequential_model
+        tl = st + "time4lstm/time4lstm_cell/"
+        s.append((tl + "kernel", (D + H, 4 * H), "glorot", True))
+        s.append((tl + "bias", (4 * H,), "zeros", True))
+        for n in ("_time_input_w1", "_time_input_bias1", "_time_input_w2", "_time_input_bias2",
+                  "_time_bias1", "_time_bias2"):
+            s.append((tl + n, (H,), "glorot", True))
+        for n in ("_time_kernel_w1", "_time_kernel_w2"):
+            s.append((tl + n, (D, H), "glorot", True))
+        for n in ("_time_kernel_t1", "_time_kernel_t2", "_o_kernel_t1", "_o_kernel_t2"):
+            s.append((tl + n, (H, H), "glorot", True))
     if not manual_alpha:
         _fcn(s, SC + "fcn_alpha/nn_part/", (H if has_gru2 else 0) + 2 * D + H + 1, att_sizes)
     _fcn(s, LOGIT, H + D, layer_sizes)

@@ -64,6 +64,8 @@ typedef struct clsr_config {
   int32_t no_predict_long_short; /* hparams.predict_long_short = False: no causal2 GRU, alpha MLP input without its final state */
   int32_t manual_alpha;          /* hparams.manual_alpha = True: alpha = manual_alpha_value, no causal2 GRU, no alpha MLP */
   float manual_alpha_value;
+  int32_t sequential_model;      /* hparams.sequential_model: 0 = time4lstm (the shipped configuration), 1 = lstm
+                                  * (tf.nn.rnn_cell.LSTMCell, scope simple_lstm; clsr.py:209-216) */
 } clsr_config;
 
 /* One feed_dict (sequential_iterator.py:718-731), as plain arrays.  `group` declares that

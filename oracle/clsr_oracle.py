@@ -72,6 +72,7 @@ class OracleConfig:
     predict_long_short: bool = True
     manual_alpha: bool = False
     manual_alpha_value: float = 0.5
+    sequential_model: str = "time4lstm"   # | "lstm" | "gru" (clsr.py:179-218)
 
 
 def _t(x, dtype):
@@ -226,6 +227,43 @@ def _time4lstm(x, t_last, t_now, length, p, scope, hidden):
     return torch.stack(outs, 1)
 
 
+def _lstm_seq(x, length, p, scope, hidden):
+    """dynamic_rnn(tf.nn.rnn_cell.LSTMCell(hidden)) (clsr.py:209-216): gates i, j, f, o of [x, m].kernel + bias,
+    forget_bias 1.0, no peepholes; outputs zero / state copied through for t >= length."""
+    B = x.shape[0]
+    c = torch.zeros(B, hidden, dtype=x.dtype)
+    m = torch.zeros(B, hidden, dtype=x.dtype)
+    outs = []
+    for t in range(x.shape[1]):
+        lm = torch.cat([x[:, t], m], 1) @ p[scope + "kernel"] + p[scope + "bias"]
+        i, j, f, o = torch.split(lm, hidden, dim=1)
+        cn = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+        mn = torch.sigmoid(o) * torch.tanh(cn)
+        live = (t < length).unsqueeze(1)
+        outs.append(torch.where(live, mn, torch.zeros_like(mn)))
+        c = torch.where(live, cn, c)
+        m = torch.where(live, mn, m)
+    return torch.stack(outs, 1)
+
+
+def _gru_seq(x, length, p, scope, hidden):
+    """dynamic_rnn(tf.nn.rnn_cell.GRUCell(hidden)) outputs (clsr.py:201-208); cell as in _gru."""
+    wg, bg = p[scope + "gates/kernel"], p[scope + "gates/bias"]
+    wc, bc = p[scope + "candidate/kernel"], p[scope + "candidate/bias"]
+    h = torch.zeros(x.shape[0], hidden, dtype=x.dtype)
+    outs = []
+    for t in range(x.shape[1]):
+        xt = x[:, t]
+        g = torch.sigmoid(torch.cat([xt, h], 1) @ wg + bg)
+        r, u = g[:, :hidden], g[:, hidden:]
+        c = torch.tanh(torch.cat([xt, r * h], 1) @ wc + bc)
+        hn = u * h + (1 - u) * c
+        live = (t < length).unsqueeze(1)
+        outs.append(torch.where(live, hn, torch.zeros_like(hn)))
+        h = torch.where(live, hn, h)
+    return torch.stack(outs, 1)
+
+
 def forward(params, batch, cfg, train, dtype=torch.float64, leaves=None):
     """Forward pass.  ``params``: {TF variable name: tensor}.  ``batch``: the feed_dict
     contents keyed by placeholder name (sequential_iterator.py:48-70, 517).
@@ -284,7 +322,14 @@ def forward(params, batch, cfg, train, dtype=torch.float64, leaves=None):
     position = torch.flip(torch.cumsum(torch.flip(real_mask, [1]), 1), [1])
     recent = ((position >= 1) & (position <= cfg.contrastive_recent_k)).to(dtype)
     hist_recent = (hist * recent.unsqueeze(-1)).sum(1) / recent.sum(1, keepdim=True)
-    rnn_out = _time4lstm(hist, tfa, ttn, length, p, SC + "short_term/time4lstm/time4lstm_cell/", H)
+    if cfg.sequential_model == "time4lstm":
+        rnn_out = _time4lstm(hist, tfa, ttn, length, p, SC + "short_term/time4lstm/time4lstm_cell/", H)
+    elif cfg.sequential_model == "lstm":
+        rnn_out = _lstm_seq(hist, length, p, SC + "short_term/simple_lstm/lstm_cell/", H)
+    elif cfg.sequential_model == "gru":
+        rnn_out = _gru_seq(hist, length, p, SC + "short_term/simple_gru/gru_cell/", H)
+    else:
+        raise ValueError(cfg.sequential_model)
     sq = torch.cat([sti, target], -1)
     att_short = _attention_fcn(sq, rnn_out, mask_b, p, SC + "short_term/attention_fcn/", train, cfg, stats,
                                inter, "short")

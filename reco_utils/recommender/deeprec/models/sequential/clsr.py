@@ -25,7 +25,7 @@ class CLSRModel(SequentialBaseModel):
     def _build_seq_graph(self):
         hp = self.hparams
         unsupported = []
-        if hp.sequential_model != "time4lstm": unsupported.append("sequential_model=%s" % hp.sequential_model)
+        if hp.sequential_model not in ("time4lstm", "lstm"): unsupported.append("sequential_model=%s" % hp.sequential_model)
         if hp.loss != "softmax": unsupported.append("loss=%s" % hp.loss)
         if hp.enable_BN is not True: unsupported.append("enable_BN=%s" % hp.enable_BN)
         if list(hp.activation) != ["relu", "relu"]: unsupported.append("activation=%s" % hp.activation)
@@ -84,7 +84,8 @@ class CLSRModel(SequentialBaseModel):
         hp = self.hparams
         return dict(interest_evolve=bool(hp.interest_evolve), predict_long_short=bool(hp.predict_long_short),
                     manual_alpha=bool(hp.manual_alpha),
-                    manual_alpha_value=float(hp.manual_alpha_value if "manual_alpha_value" in hp else 0.5))
+                    manual_alpha_value=float(hp.manual_alpha_value if "manual_alpha_value" in hp else 0.5),
+                    sequential_model=str(hp.sequential_model))
 
     # ---- variables <-> checkpoints ---------------------------------------------------------------
     def _export_variables(self):
