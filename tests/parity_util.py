@@ -103,6 +103,8 @@ def engine_relu_masks(eng, B, S, T, group):
             ("logit", 0, "hl0", (B, L0), False), ("logit", 1, "hl1", (B, L1), False)]
     masks = {}
     for tag, i, buf, shp, per_seq in spec:
+        if tag == "alpha" and getattr(c, "manual_alpha", 0):
+            continue   # graph variant without the alpha MLP
         h = eng.debug(buf, shp)
         sc = eng.debug("bn/%s%d/scale" % (tag, i), (shp[-1],))
         sh = eng.debug("bn/%s%d/shift" % (tag, i), (shp[-1],))

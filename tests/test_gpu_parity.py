@@ -510,10 +510,15 @@ def test_graph_variants_match_oracle(cuda_lib, variant, math_mode):
     assert not gone, gone
     losses = eng.train_step(feed, group=G, flags=STEP_NO_OPTIMIZER | STEP_NO_BN_UPDATE)
     cfg = PU.oracle_config(G, **variant)
-    out, L, dense, slices, _ = O.compute_gradients(prm, feed, cfg, torch.float64)
-    # tensor-core path: raw comparison (the oracle's own ReLU decisions; a handful of flips near zero move the gradients
-    # by ~2e-2 relative L2, see test_step_matches_oracle_tensor_core_path) -- the fp32 path holds 2e-3
-    ftol, btol = (2e-4, 4e-2) if math_mode else (FWD_TOL, BWD_TOL)
+    if math_mode:
+        # tensor-core path: the engine's ReLU decisions are fed into the oracle (a handful of pre-activations within
+        # 1e-5 of zero flip with 2^-16 operand error and each flip is an O(1) change of that unit's derivative; see
+        # test_step_matches_oracle_tensor_core_path), which holds the gradients to 5e-3 instead of a flaky 2-5e-2
+        with O.relu_decisions(PU.engine_relu_masks(eng, B, S, 50, G)):
+            out, L, dense, slices, _ = O.compute_gradients(prm, feed, cfg, torch.float64)
+    else:
+        out, L, dense, slices, _ = O.compute_gradients(prm, feed, cfg, torch.float64)
+    ftol, btol = (2e-4, 5e-3) if math_mode else (FWD_TOL, BWD_TOL)
     assert PU.relerr(eng.debug("logit", (B,)), out["logit"].detach().numpy().reshape(-1)) < ftol
     a_ref = out["alpha"].detach().numpy().reshape(-1)
     assert PU.relerr(eng.debug("alpha", (B,)), np.broadcast_to(a_ref, (B,)) if a_ref.size == 1 else a_ref) < ftol
