@@ -133,3 +133,38 @@ def test_oracle_train_step_semantics():
     mm = "sequential/logit_fcn/nn_part/batch_normalization/moving_variance"
     assert not np.allclose(prm[mm], before[mm])
     assert np.array_equal(prm["sequential/embedding/user_embedding"], before["sequential/embedding/user_embedding"])
+
+
+def test_graph_variants_select_the_reference_inventories():
+    """hparams.interest_evolve / predict_long_short / manual_alpha / sequential_model decide which variables the
+    reference graph creates (clsr.py:159-274); the parameter inventory follows, and the oracle runs every variant."""
+    import torch
+    from clsr_b200 import params as P
+    from clsr_b200 import synth
+    from oracle import clsr_oracle as O
+    base = {n for n, *_ in P.dense_spec(40, 40, 40, [80, 40], [100, 64])}
+    sti = {n for n in base if "short_term_intention/" in n}
+    c2 = {n for n in base if "causal2/" in n}
+    fa = {n for n in base if "fcn_alpha/" in n}
+    t4 = {n for n in base if "time4lstm/" in n}
+    assert len(sti) == 4 and len(c2) == 4 and len(fa) == 14 and len(t4) == 14
+    spec = lambda **kw: {n: shp for n, shp, *_ in P.dense_spec(40, 40, 40, [80, 40], [100, 64], **kw)}
+    assert set(spec(interest_evolve=False)) == base - sti
+    assert set(spec(manual_alpha=True)) == base - c2 - fa
+    nl = spec(predict_long_short=False)
+    assert set(nl) == base - c2 and nl["sequential/clsr/fcn_alpha/nn_part/w_nn_layer0"] == (40 + 40 + 40 + 1, 80)
+    ls = spec(sequential_model="lstm")
+    assert set(ls) == (base - t4) | {"sequential/clsr/short_term/simple_lstm/lstm_cell/kernel",
+                                     "sequential/clsr/short_term/simple_lstm/lstm_cell/bias"}
+    assert ls["sequential/clsr/short_term/simple_lstm/lstm_cell/kernel"] == (80, 160)
+    src = synth.SyntheticSource(n_items=300, n_cates=20, n_users=30, T=12, seed=1)
+    feed = src.batch(4, 4)
+    for kw in (dict(interest_evolve=False), dict(predict_long_short=False), dict(manual_alpha=True, manual_alpha_value=0.25),
+               dict(sequential_model="lstm"), dict(sequential_model="gru")):
+        vkw = {k: v for k, v in kw.items() if k != "manual_alpha_value"}
+        prm = P.init_params(300, 20, 30, seed=2, **vkw)
+        cfg = O.OracleConfig(max_seq_length=12, **kw)
+        out, L, dense, slices, _ = O.compute_gradients(prm, feed, cfg, torch.float64)
+        assert all(torch.isfinite(g).all() for g in dense.values()) and set(dense) == {k for k in prm if "/embedding/" not in k and "moving_" not in k}
+        if kw.get("manual_alpha"):
+            assert float(out["alpha"].min()) == float(out["alpha"].max()) == 0.25

@@ -12,6 +12,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SRC = r'''
 #include <cstdio>
 #include "tc_gemm.cuh"
+#include "head_mlp.cuh"
 using namespace clsr;
 int main() {
   // (planes_a, planes_b, mode_a, mode_b) of the model's weight-gradient launches
@@ -38,6 +39,19 @@ int main() {
     tc::DwSmem E = tc::dw_smem_layout(c[0], c[1], c[2], (c[2] + 15) / 16 * 16, 2, c[3], c[4]);
     printf("dw2 %d %d %d %d\n", c[0], c[2], E.total, (2 - 1) * E.stage_bytes + 16 * 4096);
   }
+  // fused _fcn_net kernels (head_mlp.cuh): alpha gate (K = 161) and logit (K = 80) blocks at 139 rows per CTA (20480 / 148)
+  const int m[][3] = {{161, 80, 40}, {80, 100, 64}, {121, 80, 40}};
+  for (auto& c : m) {
+    CoopFwdSmem F = coop_fwd_smem(c[0], c[1], c[2], 139);
+    CoopBwdSmem B = coop_bwd_smem(c[0], c[1], c[2], 139);
+    printf("coop %d %d %d %d %d %d\n", c[0], c[1], c[2], F.total * 4, B.total * 4, F.rc);
+  }
+  // three weight-gradient stages where a stage is <= 75 KB (dWgh: 40 x 80 transposed -> 80 lanes + 48 columns)
+  tc::DwSmem T3 = tc::dw_smem_layout(80, 80, 40, 48, 3, 1, 1);
+  printf("dw3 %d %d\n", T3.total, 2 * T3.stage_bytes + 16 * 4096);
+  // chunked contraction (dX: 6 chunks of 80, N = 40) with two stages and the store images
+  tc::Smem KX = tc::smem_layout(80, 48, 40, 2, 0, 0, 1, 1, 6);
+  printf("kloop %d %d\n", KX.total, KX.a_stage0);
   return 0;
 }
 '''
@@ -81,3 +95,20 @@ def test_operand_stage_is_one_plane_per_eight_columns(host_out):
             k, n, tot, window = map(int, ln[1:])
             # two stages fit, and the 16-plane window the MMA reads from the last stage stays inside the allocation
             assert tot <= 227 * 1024 - 4608 - 256 and window <= tot, ln
+
+
+def test_fused_head_and_pipeline_layouts_fit(host_out):
+    """Shared-memory budgets the round-2 kernels rely on: the cooperative _fcn_net kernels (one CTA per SM, 512 threads,
+    ~8 KB of static shared memory), three weight-gradient stages, the chunked-K GEMM with all of W resident."""
+    limit = 227 * 1024
+    for ln in host_out:
+        if ln[0] == "coop":
+            k, n0, n1, fwd, bwd, rc = map(int, ln[1:])
+            assert fwd + 8 * 1024 <= limit and bwd + 8 * 1024 <= limit, ln
+            assert rc % 4 == 0 and rc >= 4
+        if ln[0] == "dw3":
+            tot, window = map(int, ln[1:])
+            assert tot <= limit - 4608 - 256 and window <= tot, ln
+        if ln[0] == "kloop":
+            tot, a0 = map(int, ln[1:])
+            assert tot <= limit - 1024 and a0 == 2 * 6 * 80 * 48 * 2, ln   # hi + lo copies of all six W chunks
