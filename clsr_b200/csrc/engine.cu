@@ -1118,6 +1118,7 @@ bool coop_usable(const clsr_engine* e, const Mlp& m, int rows) {
   // data parallel without the peer-memory exchange (plain NCCL mode before clsr_peer_setup_*): layer-by-layer path
   return on && rows <= (long long)e->coop_rpc * e->num_sms && (e->world == 1 || e->peer_ready);
 }
+constexpr int kCoopUnavailable = -1000;
 template <typename Kern>
 int coop_launch(clsr_engine* e, Kern kern, const CoopMlp& a, size_t smem, const char* name) {
   cudaLaunchConfig_t cfg;
@@ -1127,7 +1128,15 @@ int coop_launch(clsr_engine* e, Kern kern, const CoopMlp& a, size_t smem, const 
   at[0].id = cudaLaunchAttributeCooperative;
   at[0].val.cooperative = 1;    // all CTAs co-resident: the kernels synchronise through a grid barrier
   cfg.attrs = at; cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, kern, a, e->coop_rpc));
+  const cudaError_t lc = cudaLaunchKernelEx(&cfg, kern, a, e->coop_rpc);
+  if (lc == cudaErrorCooperativeLaunchTooLarge || lc == cudaErrorNotSupported) {
+    // the device cannot co-schedule one CTA per SM right now (MPS / MIG partitions, SM limits): use the
+    // layer-by-layer kernels from here on -- they read and write the same buffers
+    cudaGetLastError();
+    e->coop_alpha = e->coop_logit = false;
+    return kCoopUnavailable;
+  }
+  CK(lc);
   POST(name);
   return 0;
 }
@@ -1140,7 +1149,8 @@ int mlp_fwd(clsr_engine* e, Mlp& m, const float* in, int rows, float* h0, float*
     coop_args(e, m, in, rows, h0, h1, &a);
     a.out = out; a.update_moving = update;
     const CoopFwdSmem L = coop_fwd_smem(m.in, m.n0, m.n1, e->coop_rpc);
-    return coop_launch(e, mlp_fwd_coop_kernel, a, (size_t)L.total * 4, "mlp_fwd_fused");
+    rc = coop_launch(e, mlp_fwd_coop_kernel, a, (size_t)L.total * 4, "mlp_fwd_fused");
+    if (rc != kCoopUnavailable) return rc;
   }
   EpiOp ep = e_store(h0, m.n0, e->P + m.b0);
   ep.stat = m.bn0.stat_f;
@@ -1166,7 +1176,8 @@ int mlp_bwd(clsr_engine* e, Mlp& m, const float* in, int rows, const float* h0, 
     coop_args(e, m, in, rows, const_cast<float*>(h0), const_cast<float*>(h1), &a);
     a.dout = dout; a.din = din; a.w0T = w0T; a.w1T = w1T;
     const CoopBwdSmem L = coop_bwd_smem(m.in, m.n0, m.n1, e->coop_rpc);
-    return coop_launch(e, mlp_bwd_coop_kernel, a, (size_t)L.total * 4, "mlp_bwd_fused");
+    rc = coop_launch(e, mlp_bwd_coop_kernel, a, (size_t)L.total * 4, "mlp_bwd_fused");
+    if (rc != kCoopUnavailable) return rc;
   }
   {
     int nx = ((m.n1 + 31) / 32) * 32;
